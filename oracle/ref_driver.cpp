@@ -1,0 +1,169 @@
+// oracle/ref_driver.cpp — C entry points over the UNMODIFIED libMems reference sources.
+//
+// TEST INFRASTRUCTURE ONLY (checker + CPU baseline).  This file contains no algorithm: it
+// instantiates the reference's own classes (DNAMemorySML, MemHash, RepeatHash, MatchList —
+// /root/reference/libMems/*.cpp compiled where they lie, see oracle/Makefile) and copies their
+// results into flat C arrays so that Python tests and bench.py can read them through ctypes.
+// The built library lives in oracle/_ref/ (git-ignored) and is never linked into the product.
+#include "libMems/DNAMemorySML.h"
+#include "libMems/MemHash.h"
+#include "libMems/RepeatHash.h"
+#include "libMems/PairwiseMatchFinder.h"
+#include "libMems/MatchList.h"
+#include "libMems/SeedMasks.h"
+#include "libMems/SeedOccurrenceList.h"
+
+#include <chrono>
+#include <vector>
+#include <string>
+#include <cstring>
+
+using namespace mems;
+using namespace genome;
+
+namespace {
+double now_s() {
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+std::string g_err;
+}
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// SeedMasks.h:298-401
+uint64_t ref_get_seed(int weight, int rank) { return (uint64_t)getSeed(weight, rank); }
+int ref_seed_length(uint64_t seed) { return getSeedLength((int64)seed); }
+int ref_seed_weight(uint64_t seed) { return getSeedWeight((int64)seed); }
+unsigned ref_default_seed_weight(uint64_t avg_len) { return getDefaultSeedWeight(avg_len); }
+
+// DNAMemorySML::Create (MemorySML.cpp:45-60) on one sequence.
+// positions_out / mers_out (both optional) receive SMLLength() entries: sml[i].position / sml[i].mer.
+// packed_out (optional) receives the 2-bit words of SortedMerList::SetSequence without the two pad words.
+int ref_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* positions_out, uint64_t* mers_out,
+                  uint64_t* sml_len_out, uint64_t* seed_mask_out, uint64_t* mer_mask_out, double* secs_out) {
+	try {
+		gnSequence gs(seq, n);
+		DNAMemorySML sml;
+		double t0 = now_s();
+		sml.Create(gs, seed);
+		double t1 = now_s();
+		if (secs_out) *secs_out = t1 - t0;
+		uint64_t len = sml.SMLLength();
+		if (sml_len_out) *sml_len_out = len;
+		if (seed_mask_out) *seed_mask_out = sml.GetSeedMask();
+		if (mer_mask_out) *mer_mask_out = sml.GetMerMask();
+		if (positions_out || mers_out) {
+			for (uint64_t i = 0; i < len; ++i) {
+				bmer b = sml[i];
+				if (positions_out) positions_out[i] = b.position;
+				if (mers_out) mers_out[i] = b.mer;
+			}
+		}
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	} catch (const char* s) {
+		g_err = s;
+		return 2;
+	}
+}
+
+// SortedMerList::GetSeedMer (forward, SortedMerList.cpp:726-762) and GetDnaSeedMer (canonical, :764-769)
+// at a list of positions.
+int ref_seed_mers(const char* seq, uint64_t n, uint64_t seed, const uint64_t* pos, uint64_t npos,
+                  uint64_t* fwd_out, uint64_t* dna_out) {
+	try {
+		gnSequence gs(seq, n);
+		DNAMemorySML sml;
+		// Create() would also sort; SortedMerList::Create only packs and sets masks.
+		sml.SortedMerList::Create(gs, seed);
+		for (uint64_t i = 0; i < npos; ++i) {
+			if (fwd_out) fwd_out[i] = sml.SortedMerList::GetSeedMer(pos[i]);
+			if (dna_out) dna_out[i] = sml.GetDnaSeedMer(pos[i]);
+		}
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	}
+}
+
+// MatchList::CreateMemorySMLs + {MemHash,RepeatHash,PairwiseMatchFinder}::FindMatches.
+// mode: 0 = MemHash (multi-MUM), 1 = RepeatHash (single genome self-match), 2 = PairwiseMatchFinder.
+// Output (malloc'd, release with ref_free): flat int64 records in the reference's own output order
+//   [SeqCount, Length, Start(0) … Start(SeqCount-1)] per match.
+// times_out[0] = SML build seconds (all genomes), times_out[1] = FindMatches seconds.
+// counts_out[0] = MemCount, counts_out[1] = MemCollisionCount.
+int ref_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed,
+                     int64_t** flat_out, uint64_t* n_flat_out, uint64_t* n_matches_out,
+                     double* times_out, uint64_t* counts_out) {
+	try {
+		MatchList ml;
+		for (int g = 0; g < n_seqs; ++g) {
+			ml.seq_table.push_back(new gnSequence(seqs[g], lens[g]));
+			ml.seq_filename.push_back("mem");
+		}
+		double t0 = now_s();
+		for (int g = 0; g < n_seqs; ++g) {
+			DNAMemorySML* sml = new DNAMemorySML();
+			sml->Create(*ml.seq_table[g], seed);
+			ml.sml_table.push_back(sml);
+		}
+		double t1 = now_s();
+		MemHash* mh = NULL;
+		if (mode == 0) mh = new MemHash();
+		else if (mode == 1) mh = new RepeatHash();
+		else if (mode == 2) mh = new PairwiseMatchFinder();
+		else { g_err = "bad mode"; return 3; }
+		mh->FindMatches(ml);
+		double t2 = now_s();
+		if (times_out) { times_out[0] = t1 - t0; times_out[1] = t2 - t1; }
+		if (counts_out) { counts_out[0] = mh->MemCount(); counts_out[1] = mh->MemCollisionCount(); }
+		std::vector<int64_t> flat;
+		for (size_t i = 0; i < ml.size(); ++i) {
+			Match* m = ml[i];
+			flat.push_back((int64_t)m->SeqCount());
+			flat.push_back((int64_t)m->Length());
+			for (uint s = 0; s < m->SeqCount(); ++s) flat.push_back((int64_t)m->Start(s));
+		}
+		*n_matches_out = ml.size();
+		*n_flat_out = flat.size();
+		*flat_out = (int64_t*)malloc(sizeof(int64_t) * (flat.size() ? flat.size() : 1));
+		memcpy(*flat_out, flat.data(), sizeof(int64_t) * flat.size());
+		mh->Clear();
+		delete mh;
+		ml.Clear();
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	} catch (const char* s) {
+		g_err = s;
+		return 2;
+	}
+}
+
+// SeedOccurrenceList::construct (SeedOccurrenceList.h:21-63) — per-position seed multiplicity, smoothed.
+int ref_seed_occurrence(const char* seq, uint64_t n, uint64_t seed, float* out, uint64_t* n_out) {
+	try {
+		gnSequence gs(seq, n);
+		DNAMemorySML sml;
+		sml.Create(gs, seed);
+		SeedOccurrenceList sol;
+		sol.construct(sml);
+		*n_out = sml.Length();  // construct() sizes its table to sml.Length()
+		if (out)
+			for (uint64_t i = 0; i < sml.Length(); ++i) out[i] = sol.getFrequency(i);
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	}
+}
+
+void ref_free(void* p) { free(p); }
+
+}  // extern "C"
