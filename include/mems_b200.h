@@ -1,0 +1,149 @@
+/* mems_b200.h — C-ABI of the B200-native seed-and-extend anchoring path of libMems.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, int error codes, no C++ or torch types.
+ * Every entry point names the libMems interface it replaces (file:line under libMems/ of
+ * koadman/libMems 1.6.1).  The C++ façade in libmems_b200/host/ (same class and method names as
+ * the reference) and the ctypes binding in libmems_b200/__init__.py are the only callers.
+ *
+ * Threading: a context owns one CUDA stream and its scratch memory.  Contexts are independent, so
+ * one context per host thread reproduces the reference's "one MemHash per thread" rule
+ * (TLS<MemHash> gap_mh, Aligner.h:198).  Calls on ONE context must not overlap.
+ *
+ * There is no CPU fallback: every compute entry point fails with MEMS_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef MEMS_B200_H
+#define MEMS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEMS_OK 0
+#define MEMS_ERR_INVALID 1      /* bad argument (InvalidData / SMLCreateError in the reference) */
+#define MEMS_ERR_GAP 2          /* '-' in a sequence (SortedMerList.cpp:433-437 throws) */
+#define MEMS_ERR_CUDA 3         /* CUDA runtime error; see mems_last_error */
+#define MEMS_ERR_UNSUPPORTED 4  /* outside this implementation's limits; see mems_last_error */
+#define MEMS_ERR_SEED_MISMATCH 5 /* SMLs with different seed patterns (MatchFinder.cpp:190-199) */
+#define MEMS_ERR_NCCL 6
+
+#define MEMS_MODE_MEMHASH 0   /* MemHash::FindMatches, multi-MUM (MemHash.cpp:109-162) */
+#define MEMS_MODE_REPEAT 1    /* RepeatHash::FindMatches (RepeatHash.cpp:34-62) */
+#define MEMS_MODE_PAIRWISE 2  /* PairwiseMatchFinder::FindMatches (PairwiseMatchFinder.cpp:37-71) */
+
+/* output ordering of a match list */
+#define MEMS_ORDER_CANONICAL 0 /* distinct matches sorted by (SeqCount, Length, Start(0..)) */
+#define MEMS_ORDER_REFERENCE 1 /* the reference's hash-table order incl. its collision drops
+                                  (MemHash.cpp:209-251, MemHash.h:183-203); always used for RepeatHash */
+
+#define MEMS_MAX_SEQS 64           /* sequences per FindMatches call */
+#define MEMS_MER_REPEAT_LIMIT 1000 /* MatchFinder.cpp:166 — larger seed runs are outside the parity contract */
+
+typedef struct mems_ctx* mems_ctx_t;
+typedef struct mems_sml* mems_sml_t;
+typedef struct mems_matches* mems_matches_t;
+
+/* ---- seed patterns: SeedMasks.h:276-401 (host arithmetic, no device needed) ---- */
+uint64_t mems_get_seed(int weight, int seed_rank);           /* getSeed */
+uint64_t mems_get_solid_seed(int weight);                    /* getSolidSeed */
+int mems_get_seed_length(uint64_t seed);                     /* getSeedLength */
+int mems_get_seed_weight(uint64_t seed);                     /* getSeedWeight */
+unsigned mems_get_default_seed_weight(uint64_t avg_seq_len); /* getDefaultSeedWeight */
+
+/* ---- context ---- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on, or NULL for a private stream. */
+int mems_ctx_create(int device, void* stream, mems_ctx_t* out);
+void mems_ctx_destroy(mems_ctx_t ctx);
+/* last error text of this context (ctx may be NULL for creation failures) */
+const char* mems_last_error(mems_ctx_t ctx);
+/* block until all work queued on the context's stream is done */
+int mems_ctx_synchronize(mems_ctx_t ctx);
+/* pinned host memory helpers (optional; any host pointer is accepted by the calls below) */
+int mems_host_alloc(void** ptr, uint64_t bytes);
+void mems_host_free(void* ptr);
+
+/* ---- sorted mer lists ---- */
+typedef struct {
+	uint64_t length;      /* SortedMerList::Length()      — bases */
+	uint64_t sml_length;  /* SortedMerList::SMLLength()   — seed positions (linear sequences) */
+	uint64_t seed;        /* SortedMerList::Seed() */
+	uint32_t seed_length; /* SeedLength() */
+	uint32_t seed_weight; /* SeedWeight() */
+	uint64_t seed_mask;   /* GetSeedMask(): top 2*weight bits */
+	uint64_t mer_mask;    /* GetMerMask():  top 2*length bits */
+} mems_sml_info_t;
+
+/* DNAMemorySML::Create(seq, seed) (MemorySML.cpp:45-60, SortedMerList.cpp:786-824) for one linear
+ * sequence of n ASCII bases.  The sorted list stays resident in device memory. */
+int mems_sml_create(mems_ctx_t ctx, const char* seq, uint64_t n, uint64_t seed, mems_sml_t* out);
+/* MatchList::CreateMemorySMLs (MatchList.h:408-435): one SML per sequence, same seed.  The batch
+ * is extracted and sorted as one union so a following mems_find_matches over exactly these
+ * handles (same order) reuses the sorted union instead of merging. */
+int mems_sml_create_batch(mems_ctx_t ctx, int n_seqs, const char* const* seqs, const uint64_t* lens,
+                          uint64_t seed, mems_sml_t* out);
+void mems_sml_destroy(mems_sml_t sml);
+int mems_sml_info(mems_sml_t sml, mems_sml_info_t* out);
+/* MemorySML::Read / operator[] (MemorySML.cpp:62-94): entries [offset, offset+count) of the sorted
+ * list as (position, canonical mer).  Either output may be NULL.  *n_read receives the count. */
+int mems_sml_read(mems_sml_t sml, uint64_t offset, uint64_t count, uint32_t* positions_out,
+                  uint64_t* mers_out, uint64_t* n_read);
+/* SortedMerList::GetSeedMer (forward, SortedMerList.cpp:726-762) and DNAMemorySML::GetSeedMer ==
+ * GetDnaSeedMer (canonical, :764-769) at arbitrary positions.  Either output may be NULL. */
+int mems_sml_seed_mers(mems_sml_t sml, const uint64_t* positions, uint64_t n, uint64_t* fwd_out,
+                       uint64_t* dna_out);
+/* SortedMerList::FindMer (SortedMerList.cpp:170-179): *found=1 and *index = a sorted-list index
+ * whose masked mer equals query_mer's, else *found=0 and *index = insertion point. */
+int mems_sml_find_mer(mems_sml_t sml, uint64_t query_mer, int* found, uint64_t* index);
+/* The 2-bit packed sequence as SortedMerList::SetSequence lays it out (MSB-first uint32 words,
+ * ceil(2n/32)+2 words, pad words zero). words_out may be NULL to query *n_words only. */
+int mems_sml_packed(mems_sml_t sml, uint32_t* words_out, uint64_t* n_words);
+
+/* ---- match finding ---- */
+typedef struct {
+	int mode;          /* MEMS_MODE_* */
+	int order;         /* MEMS_ORDER_* */
+	uint32_t table_size; /* MemHash::SetTableSize; 0 = DEFAULT_MEM_TABLE_SIZE 40000 (MemHash.h:30) */
+	uint32_t reserved;
+} mems_match_params_t;
+
+typedef struct {
+	uint64_t n_matches;
+	uint64_t n_flat;      /* int64 entries mems_matches_copy writes */
+	uint64_t n_hits;      /* seed hits handed to HashMatch (MemHash.cpp:167) */
+	uint64_t mem_count;   /* MemHash::MemCount()          (ORDER_REFERENCE only, else == n_matches) */
+	uint64_t collisions;  /* MemHash::MemCollisionCount() (ORDER_REFERENCE only, else n_hits - n_matches) */
+	uint64_t max_run;     /* largest equal-seed run seen; > MEMS_MER_REPEAT_LIMIT voids parity */
+	uint32_t seq_count;   /* sequences searched */
+	uint32_t seed_length;
+} mems_matches_info_t;
+
+/* MemHash/RepeatHash/PairwiseMatchFinder::FindMatches (MemHash.cpp:109-127) over n_smls sorted mer
+ * lists that share one seed: equal-seed runs -> hits -> ungapped extension (MatchFinder.h:219-374)
+ * -> distinct matches. */
+int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls,
+                      const mems_match_params_t* params, mems_matches_t* out);
+int mems_matches_info(mems_matches_t m, mems_matches_info_t* out);
+/* Flat records [SeqCount, Length, Start(0) .. Start(SeqCount-1)] per match; starts are 1-based,
+ * negative = reverse strand, 0 = NO_MATCH (AbstractMatch.h:27, UngappedLocalAlignment.h:201-206). */
+int mems_matches_copy(mems_matches_t m, int64_t* flat_out);
+void mems_matches_destroy(mems_matches_t m);
+
+/* ---- measurement ---- */
+/* With profiling on, every kernel launch is bracketed by CUDA events on the context's stream. */
+int mems_profile_enable(mems_ctx_t ctx, int on);
+int mems_profile_reset(mems_ctx_t ctx);
+typedef struct {
+	char name[48];
+	uint64_t launches;
+	double ms;       /* summed device time of those launches */
+	double bytes;    /* summed algorithmic bytes the launches were given (0 if not tracked) */
+} mems_profile_entry_t;
+/* Synchronises the stream, then fills up to cap entries; *n receives the number available. */
+int mems_profile_get(mems_ctx_t ctx, mems_profile_entry_t* entries, int cap, int* n);
+/* kernels launched on this context since creation / last reset (counted even with profiling off) */
+uint64_t mems_launch_count(mems_ctx_t ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMS_B200_H */

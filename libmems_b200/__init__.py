@@ -1,0 +1,285 @@
+"""libmems_b200 — ctypes binding to the B200-native anchoring path (include/mems_b200.h).
+
+This module is plumbing only: it loads ``libmems_b200.so`` (hand-written sm_100a CUDA kernels behind
+a C-ABI) and exposes the reference's vocabulary — sorted mer lists (``SortedMerList``), ``MemHash`` /
+``RepeatHash`` match finding, match lists.  There is NO CPU fallback: importing works without a GPU
+(so the symbol table can be checked), but every compute call raises ``MemsError`` unless an sm_100
+device is present, and ``load()`` raises if the shared library has not been built.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmems_b200.so")
+
+MODE_MEMHASH, MODE_REPEAT, MODE_PAIRWISE = 0, 1, 2
+ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
+
+_u64 = ctypes.c_uint64
+_vp = ctypes.c_void_p
+
+
+class MemsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mems error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SmlInfo(ctypes.Structure):
+    _fields_ = [("length", _u64), ("sml_length", _u64), ("seed", _u64), ("seed_length", ctypes.c_uint32),
+                ("seed_weight", ctypes.c_uint32), ("seed_mask", _u64), ("mer_mask", _u64)]
+
+
+class MatchParams(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int), ("order", ctypes.c_int), ("table_size", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
+
+
+class MatchesInfo(ctypes.Structure):
+    _fields_ = [("n_matches", _u64), ("n_flat", _u64), ("n_hits", _u64), ("mem_count", _u64), ("collisions", _u64),
+                ("max_run", _u64), ("seq_count", ctypes.c_uint32), ("seed_length", ctypes.c_uint32)]
+
+
+class ProfileEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("launches", _u64), ("ms", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
+# every symbol include/mems_b200.h declares
+EXPORTS = [
+    "mems_get_seed", "mems_get_solid_seed", "mems_get_seed_length", "mems_get_seed_weight",
+    "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
+    "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
+    "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
+    "mems_sml_packed", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_destroy",
+    "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it was not built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MemsError(-1, "%s not found — build it with `make -C libmems_b200/csrc` "
+                            "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mems_get_seed.restype = _u64
+    lib.mems_get_seed.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.mems_get_solid_seed.restype = _u64
+    lib.mems_get_seed_length.argtypes = [_u64]
+    lib.mems_get_seed_weight.argtypes = [_u64]
+    lib.mems_get_default_seed_weight.argtypes = [_u64]
+    lib.mems_get_default_seed_weight.restype = ctypes.c_uint
+    lib.mems_last_error.restype = ctypes.c_char_p
+    lib.mems_last_error.argtypes = [_vp]
+    lib.mems_ctx_create.argtypes = [ctypes.c_int, _vp, ctypes.POINTER(_vp)]
+    lib.mems_ctx_destroy.argtypes = [_vp]
+    lib.mems_ctx_synchronize.argtypes = [_vp]
+    lib.mems_host_alloc.argtypes = [ctypes.POINTER(_vp), _u64]
+    lib.mems_host_free.argtypes = [_vp]
+    lib.mems_sml_create.argtypes = [_vp, _vp, _u64, _u64, ctypes.POINTER(_vp)]
+    lib.mems_sml_create_batch.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _u64,
+                                          ctypes.POINTER(_vp)]
+    lib.mems_sml_destroy.argtypes = [_vp]
+    lib.mems_sml_info.argtypes = [_vp, ctypes.POINTER(SmlInfo)]
+    lib.mems_sml_read.argtypes = [_vp, _u64, _u64, _vp, _vp, ctypes.POINTER(_u64)]
+    lib.mems_sml_seed_mers.argtypes = [_vp, _vp, _u64, _vp, _vp]
+    lib.mems_sml_find_mer.argtypes = [_vp, _u64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_u64)]
+    lib.mems_sml_packed.argtypes = [_vp, _vp, ctypes.POINTER(_u64)]
+    lib.mems_find_matches.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(MatchParams),
+                                      ctypes.POINTER(_vp)]
+    lib.mems_matches_info.argtypes = [_vp, ctypes.POINTER(MatchesInfo)]
+    lib.mems_matches_copy.argtypes = [_vp, _vp]
+    lib.mems_matches_destroy.argtypes = [_vp]
+    lib.mems_profile_enable.argtypes = [_vp, ctypes.c_int]
+    lib.mems_profile_reset.argtypes = [_vp]
+    lib.mems_profile_get.argtypes = [_vp, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.mems_launch_count.argtypes = [_vp]
+    lib.mems_launch_count.restype = _u64
+    _lib = lib
+    return lib
+
+
+# ---- seed patterns (SeedMasks.h) --------------------------------------------------------------------
+def get_seed(weight, rank=0):
+    return int(load().mems_get_seed(int(weight), int(rank)))
+
+
+def get_seed_length(seed):
+    return int(load().mems_get_seed_length(seed))
+
+
+def get_seed_weight(seed):
+    return int(load().mems_get_seed_weight(seed))
+
+
+def get_default_seed_weight(avg_len):
+    return int(load().mems_get_default_seed_weight(int(avg_len)))
+
+
+def _host_ptr(seq):
+    """(pointer, length, keepalive) for bytes / numpy uint8 / (ptr, len) inputs."""
+    if isinstance(seq, np.ndarray):
+        a = np.ascontiguousarray(seq, dtype=np.uint8)
+        return a.ctypes.data, a.size, a
+    if isinstance(seq, tuple):
+        return int(seq[0]), int(seq[1]), None
+    b = bytes(seq)
+    buf = ctypes.create_string_buffer(b, len(b)) if len(b) else ctypes.create_string_buffer(1)
+    return ctypes.addressof(buf), len(b), buf
+
+
+class Context:
+    """One stream + scratch pool; the analogue of holding one MemHash per thread (Aligner.h:198)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.mems_ctx_create(int(device), _vp(stream) if stream else None, ctypes.byref(h))
+        if rc:
+            raise MemsError(rc, self.lib.mems_last_error(None).decode())
+        self.h = h
+
+    def _check(self, rc):
+        if rc:
+            raise MemsError(rc, self.lib.mems_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mems_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self.lib.mems_ctx_synchronize(self.h))
+
+    # -- SML construction -----------------------------------------------------------------------------
+    def create_sml(self, seq, seed):
+        """DNAMemorySML::Create (MemorySML.cpp:45-60)."""
+        p, n, keep = _host_ptr(seq)
+        h = _vp()
+        self._check(self.lib.mems_sml_create(self.h, p, n, seed, ctypes.byref(h)))
+        return SortedMerList(self, h)
+
+    def create_smls(self, seqs, seed):
+        """MatchList::CreateMemorySMLs (MatchList.h:408-435): one SML per sequence, built as one batch."""
+        parts = [_host_ptr(s) for s in seqs]
+        n = len(parts)
+        ptrs = (_vp * n)(*[p[0] for p in parts])
+        lens = (_u64 * n)(*[p[1] for p in parts])
+        out = (_vp * n)()
+        self._check(self.lib.mems_sml_create_batch(self.h, n, ptrs, lens, seed, out))
+        return [SortedMerList(self, _vp(out[i])) for i in range(n)]
+
+    # -- match finding --------------------------------------------------------------------------------
+    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_CANONICAL, table_size=0):
+        """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches.  Returns (matches, info) where
+        matches is a list of tuples (SeqCount, Length, Start(0), ...)."""
+        n = len(smls)
+        arr = (_vp * n)(*[s.h for s in smls])
+        params = MatchParams(mode, order, table_size, 0)
+        h = _vp()
+        self._check(self.lib.mems_find_matches(self.h, n, arr, ctypes.byref(params), ctypes.byref(h)))
+        try:
+            info = MatchesInfo()
+            self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
+            flat = np.zeros(max(int(info.n_flat), 1), np.int64)
+            self._check(self.lib.mems_matches_copy(h, flat.ctypes.data))
+        finally:
+            self.lib.mems_matches_destroy(h)
+        flat = flat[:int(info.n_flat)]
+        d = {k: int(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        return flat, d
+
+    # -- measurement ----------------------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._check(self.lib.mems_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._check(self.lib.mems_profile_reset(self.h))
+
+    def profile(self):
+        n = ctypes.c_int()
+        ent = (ProfileEntry * 64)()
+        self._check(self.lib.mems_profile_get(self.h, ent, 64, ctypes.byref(n)))
+        return {ent[i].name.decode(): {"launches": int(ent[i].launches), "ms": float(ent[i].ms),
+                                       "bytes": float(ent[i].bytes)} for i in range(min(n.value, 64))}
+
+    def launch_count(self):
+        return int(self.lib.mems_launch_count(self.h))
+
+
+def flat_to_matches(flat):
+    """[SeqCount, Len, starts...]* -> list of tuples."""
+    out, i, n = [], 0, len(flat)
+    while i < n:
+        k = int(flat[i])
+        out.append(tuple(int(x) for x in flat[i:i + 2 + k]))
+        i += 2 + k
+    return out
+
+
+class SortedMerList:
+    """Device-resident sorted mer list (SortedMerList.h:69-282 accessors)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        info = SmlInfo()
+        ctx._check(ctx.lib.mems_sml_info(self.h, ctypes.byref(info)))
+        self.info = {k: int(getattr(info, k)) for k, _ in SmlInfo._fields_}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.mems_sml_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sml_length(self):
+        return self.info["sml_length"]
+
+    def read(self, offset=0, count=None):
+        """MemorySML::Read: (positions, mers) of sorted-list entries [offset, offset+count)."""
+        if count is None:
+            count = self.info["sml_length"]
+        pos = np.zeros(max(count, 1), np.uint32)
+        mers = np.zeros(max(count, 1), np.uint64)
+        n = _u64()
+        self.ctx._check(self.ctx.lib.mems_sml_read(self.h, offset, count, pos.ctypes.data, mers.ctypes.data,
+                                                   ctypes.byref(n)))
+        return pos[:n.value], mers[:n.value]
+
+    def seed_mers(self, positions):
+        """(GetSeedMer forward, GetDnaSeedMer canonical) at the given positions."""
+        p = np.ascontiguousarray(positions, dtype=np.uint64)
+        fwd = np.zeros(max(len(p), 1), np.uint64)
+        dna = np.zeros(max(len(p), 1), np.uint64)
+        self.ctx._check(self.ctx.lib.mems_sml_seed_mers(self.h, p.ctypes.data, len(p), fwd.ctypes.data, dna.ctypes.data))
+        return fwd[:len(p)], dna[:len(p)]
+
+    def find_mer(self, mer):
+        found = ctypes.c_int()
+        idx = _u64()
+        self.ctx._check(self.ctx.lib.mems_sml_find_mer(self.h, mer, ctypes.byref(found), ctypes.byref(idx)))
+        return bool(found.value), int(idx.value)
+
+    def packed(self):
+        n = _u64()
+        self.ctx._check(self.ctx.lib.mems_sml_packed(self.h, None, ctypes.byref(n)))
+        w = np.zeros(n.value, np.uint32)
+        self.ctx._check(self.ctx.lib.mems_sml_packed(self.h, w.ctypes.data, ctypes.byref(n)))
+        return w

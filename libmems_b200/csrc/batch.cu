@@ -1,0 +1,163 @@
+// batch.cu — SML construction for a batch of sequences:
+//   H2D of the ASCII bases -> pack -> extract (+ digit histograms) -> LSD radix sort of the union.
+// MemorySML::Create (MemorySML.cpp:45-60) builds one list per sequence; here all sequences of a create
+// call are sorted together as ONE array whose ties are in (sequence, position) order.  That single sort
+// serves both consumers:
+//   * match finding reads the union directly — equal-seed runs across sequences are contiguous, which is
+//     what MatchFinder::SearchRange's k-way merge (MatchFinder.cpp:172-340) produces on the CPU;
+//   * the per-sequence lists the SortedMerList interface exposes are one more stable counting pass on the
+//     sequence tag (done on first use).
+#include <algorithm>
+
+#include "common.cuh"
+#include "mems_b200.h"
+
+namespace mems {
+
+static int bits_for(uint64_t max_value) {  // bits needed to store values 0..max_value
+	int b = 1;
+	while (b < 64 && (max_value >> b)) ++b;
+	return b;
+}
+
+static void layout_batch(Batch& b, const std::vector<uint64_t>& lens) {
+	b.n_seqs = (int)lens.size();
+	b.meta.resize(b.n_seqs);
+	uint64_t byte_off = 0, word_off = 0, seed_off = 0;
+	uint32_t max_seeds = 0;
+	for (int g = 0; g < b.n_seqs; ++g) {
+		if (lens[g] > 0xffffffffull)
+			throw Error(MEMS_ERR_UNSUPPORTED, "sequence longer than 2^32-1 bases (positions are uint32, SortedMerList.h:40)");
+		SeqMeta& m = b.meta[g];
+		m.n_bases = (uint32_t)lens[g];
+		m.n_seeds = lens[g] >= (uint64_t)b.sd.L ? (uint32_t)(lens[g] - b.sd.L + 1) : 0u;  // SMLLength, linear
+		m.byte_off = byte_off;
+		m.word_off = word_off;
+		m.seed_off = seed_off;
+		byte_off += (lens[g] + 15) / 16 * 16;
+		word_off += ((lens[g] + 15) / 16 + 2 + 3) / 4 * 4;  // keep every sequence 16-byte aligned
+		seed_off += m.n_seeds;
+		max_seeds = std::max(max_seeds, m.n_seeds);
+	}
+	b.n_total = seed_off;
+	b.pos_bits = bits_for(max_seeds ? max_seeds - 1 : 0);
+	b.seq_bits = b.n_seqs > 1 ? bits_for((uint64_t)b.n_seqs - 1) : 0;
+	if (b.pos_bits + b.seq_bits > 32)
+		throw Error(MEMS_ERR_UNSUPPORTED,
+		            "sequence count x longest sequence does not fit the 32-bit (sequence, position) tag; "
+		            "shard the sequences across devices");
+	if (b.n_total > radix_max_items())
+		throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30-1 seed positions in one device batch; shard across devices");
+	b.key64 = b.sd.key_bits > 32;
+}
+
+// packed sequences are in place: extract keys, sort the union
+static void extract_and_sort(Batch& b) {
+	Ctx* c = b.ctx.get();
+	const size_t key_bytes = b.key64 ? 8 : 4;
+	const uint64_t n = b.n_total;
+	SortPlan plan = make_sort_plan(b.sd.key_bits);
+	DevBuf<uint8_t> keys_a(c, n * key_bytes), keys_b(c, n * key_bytes);
+	DevBuf<uint32_t> vals_a(c, n), vals_b(c, n);
+	DevBuf<uint32_t> hist(c, (size_t)plan.n_passes * 256);
+	MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)plan.n_passes * 256 * sizeof(uint32_t), c->stream));
+	launch_extract(c, b.packed.p, b.d_meta.p, b.meta.data(), b.n_seqs, b.sd, b.pos_bits, b.key64, keys_a.p, vals_a.p,
+	               hist.p, plan.n_passes, plan.shift, plan.bits);
+	void* kp[2] = {keys_a.p, keys_b.p};
+	uint32_t* vp[2] = {vals_a.p, vals_b.p};
+	int r = radix_sort_pairs(c, b.key64, kp, vp, n, plan, hist.p, "radix_pass");
+	if (r == 0) {
+		b.keys = std::move(keys_a);
+		b.vals = std::move(vals_a);
+	} else {
+		b.keys = std::move(keys_b);
+		b.vals = std::move(vals_b);
+	}
+}
+
+std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
+                                              const uint64_t* lens, uint64_t seed) {
+	if (n_seqs < 1) throw Error(MEMS_ERR_INVALID, "need at least one sequence");
+	auto b = std::make_shared<Batch>();
+	b->ctx = ctx;
+	b->sd = make_seed_desc(seed);
+	Ctx* c = ctx.get();
+	MEMS_CUDA(cudaSetDevice(c->device));
+	layout_batch(*b, std::vector<uint64_t>(lens, lens + n_seqs));
+	const SeqMeta& last = b->meta.back();
+	const uint64_t total_bytes = last.byte_off + ((uint64_t)last.n_bases + 15) / 16 * 16;
+	const uint64_t total_words = last.word_off + (((uint64_t)last.n_bases + 15) / 16 + 2 + 3) / 4 * 4;
+
+	b->d_meta = DevBuf<SeqMeta>(c, b->n_seqs);
+	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
+	b->packed = DevBuf<uint32_t>(c, total_words);
+	DevBuf<uint8_t> ascii(c, total_bytes + 16);
+	DevBuf<uint32_t> gap_flag(c, 1);
+	MEMS_CUDA(cudaMemsetAsync(gap_flag.p, 0, sizeof(uint32_t), c->stream));
+	for (int g = 0; g < n_seqs; ++g)
+		if (lens[g])
+			MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyHostToDevice, c->stream));
+	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
+	extract_and_sort(*b);
+	uint32_t gap = 0;
+	MEMS_CUDA(cudaMemcpyAsync(&gap, gap_flag.p, sizeof gap, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	if (gap)
+		throw Error(MEMS_ERR_GAP, "Gap in genome sequence: input sequences must be unaligned and ungapped "
+		                          "(SortedMerList.cpp:433-437)");
+	return b;
+}
+
+std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const std::vector<SeqRef>& seqs) {
+	if (seqs.empty()) throw Error(MEMS_ERR_INVALID, "need at least one sequence");
+	auto b = std::make_shared<Batch>();
+	b->ctx = ctx;
+	b->sd = seqs[0].batch->sd;
+	Ctx* c = ctx.get();
+	MEMS_CUDA(cudaSetDevice(c->device));
+	std::vector<uint64_t> lens;
+	for (const SeqRef& s : seqs) lens.push_back(s.batch->meta[s.index].n_bases);
+	layout_batch(*b, lens);
+	const SeqMeta& last = b->meta.back();
+	const uint64_t total_words = last.word_off + (((uint64_t)last.n_bases + 15) / 16 + 2 + 3) / 4 * 4;
+	b->d_meta = DevBuf<SeqMeta>(c, b->n_seqs);
+	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
+	b->packed = DevBuf<uint32_t>(c, total_words);
+	for (size_t g = 0; g < seqs.size(); ++g) {
+		const SeqMeta& src = seqs[g].batch->meta[seqs[g].index];
+		// the source lives on another context's stream: make sure its producer has finished
+		if (seqs[g].batch->ctx.get() != c) MEMS_CUDA(cudaStreamSynchronize(seqs[g].batch->ctx->stream));
+		uint64_t words = ((uint64_t)src.n_bases + 15) / 16 + 2;
+		MEMS_CUDA(cudaMemcpyAsync(b->packed.p + b->meta[g].word_off, seqs[g].batch->packed.p + src.word_off,
+		                          words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+	}
+	extract_and_sort(*b);
+	return b;
+}
+
+// Per-sequence sorted position lists: one stable counting pass of the union on the sequence tag.
+const uint32_t* Batch::sorted_positions() {
+	if (have_positions) return n_seqs == 1 ? vals.p : positions.p;
+	Ctx* c = ctx.get();
+	MEMS_CUDA(cudaSetDevice(c->device));
+	if (n_seqs > 1 && n_total > 0) {
+		SortPlan plan;
+		plan.n_passes = 1;
+		plan.shift[0] = pos_bits;
+		plan.bits[0] = seq_bits;
+		std::vector<uint32_t> h(256, 0);
+		for (int g = 0; g < n_seqs; ++g) h[g] = meta[g].n_seeds;
+		DevBuf<uint32_t> hist(c, 256);
+		MEMS_CUDA(cudaMemcpyAsync(hist.p, h.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+		DevBuf<uint32_t> out_keys(c, n_total), out_vals(c, n_total);
+		void* kp[2] = {vals.p, out_keys.p};
+		uint32_t* vp[2] = {vals.p, out_vals.p};
+		radix_sort_pairs(c, false, kp, vp, n_total, plan, hist.p, "split_by_seq");
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // h (host) is read by the async copy above
+		positions = std::move(out_keys);
+	}
+	have_positions = true;
+	return n_seqs == 1 ? vals.p : positions.p;
+}
+
+}  // namespace mems

@@ -1,0 +1,196 @@
+// common.cuh — internal declarations shared by the CUDA translation units of libmems_b200.
+// Nothing here is part of the public ABI (see include/mems_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mems {
+
+constexpr int kMaxSeedRuns = 16;  // a pattern of span <= 31 has at most 16 runs of ones
+
+// Spaced-seed pattern decomposed into its runs of ones: extraction is a software PEXT,
+// one shift+mask+shift per run (SortedMerList::GetSeedMer, SortedMerList.cpp:726-762, does it bit-serially).
+struct SeedDesc {
+	uint64_t seed;
+	int32_t L;       // span (getSeedLength)
+	int32_t w;       // weight (getSeedWeight)
+	int32_t n_runs;
+	int32_t key_bits;  // 2w+1: compact sort key = (canonical w-mer << 1) | strand
+	uint8_t run_rshift[kMaxSeedRuns];  // window >> rshift brings the run's last base to bits 1..0
+	uint8_t run_bits[kMaxSeedRuns];    // 2 * run length
+	uint8_t run_lshift[kMaxSeedRuns];  // position of the run inside the right-justified w-mer
+};
+
+// One sequence of a batch, as laid out in device memory.
+struct SeqMeta {
+	uint64_t word_off;  // first uint32 word of this sequence inside the batch's packed buffer
+	uint64_t byte_off;  // first byte inside the batch's ASCII staging buffer
+	uint64_t seed_off;  // first index inside the batch's union key/value arrays
+	uint32_t n_bases;
+	uint32_t n_seeds;   // SMLLength: n_bases - L + 1, or 0
+};
+
+struct Error : std::runtime_error {
+	int code;
+	Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define MEMS_CUDA(expr)                                                                          \
+	do {                                                                                         \
+		cudaError_t _e = (expr);                                                                 \
+		if (_e != cudaSuccess)                                                                   \
+			throw mems::Error(3, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +      \
+			                         __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+	} while (0)
+
+struct ProfEntry {
+	uint64_t launches = 0;
+	double ms = 0, bytes = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+	std::vector<double> pending_bytes;
+};
+
+struct Ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaMemPool_t pool = nullptr;
+	int sm_count = 148;
+	bool profiling = false;
+	uint64_t launch_count = 0;
+	std::map<std::string, ProfEntry> prof;
+	std::vector<cudaEvent_t> free_events;
+	std::string last_error;
+
+	void* alloc(size_t bytes);  // stream-ordered
+	void free(void* p);
+	cudaEvent_t get_event();
+	void prof_begin(const char* name, double bytes);
+	void prof_end(const char* name);
+	void prof_collect();
+	~Ctx();
+};
+
+// RAII device buffer, stream-ordered on its context.
+template <class T>
+struct DevBuf {
+	Ctx* ctx = nullptr;
+	T* p = nullptr;
+	size_t n = 0;
+	DevBuf() {}
+	DevBuf(Ctx* c, size_t count) : ctx(c), n(count) { p = (T*)c->alloc((count ? count : 1) * sizeof(T)); }
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+	DevBuf(DevBuf&& o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; }
+	DevBuf& operator=(DevBuf&& o) noexcept {
+		if (this != &o) {
+			reset();
+			ctx = o.ctx; p = o.p; n = o.n;
+			o.p = nullptr;
+		}
+		return *this;
+	}
+	void reset() {
+		if (p) ctx->free(p);
+		p = nullptr;
+		n = 0;
+	}
+	~DevBuf() { reset(); }
+};
+
+struct KernelScope {
+	Ctx* c;
+	const char* name;
+	KernelScope(Ctx* ctx, const char* nm, double bytes = 0) : c(ctx), name(nm) {
+		c->launch_count++;
+		if (c->profiling) c->prof_begin(nm, bytes);
+	}
+	~KernelScope() {
+		if (c->profiling) c->prof_end(name);
+	}
+};
+
+SeedDesc make_seed_desc(uint64_t seed);  // throws Error(MEMS_ERR_INVALID/UNSUPPORTED)
+
+// ---- kernels_sml.cu ----
+// ASCII -> 2-bit words for every sequence of a batch; sets *d_gap_flag if a '-' is seen.
+void launch_pack(Ctx* c, const uint8_t* d_ascii, uint32_t* d_packed, const SeqMeta* d_meta, const SeqMeta* h_meta,
+                 int n_seqs, uint32_t* d_gap_flag);
+// Canonical compact keys + (seq << pos_bits | pos) values for every seed position of the batch, plus the
+// digit histograms of all radix passes (n_passes x 256 counters, zeroed by the caller).
+void launch_extract(Ctx* c, const uint32_t* d_packed, const SeqMeta* d_meta, const SeqMeta* h_meta, int n_seqs,
+                    const SeedDesc& sd, int pos_bits, bool key64, void* d_keys, uint32_t* d_vals, uint32_t* d_hist,
+                    int n_passes, const int* pass_shift, const int* pass_bits);
+// mers at arbitrary positions of one sequence (reference 64-bit layout)
+void launch_seed_mers(Ctx* c, const uint32_t* d_words, uint32_t n_seeds, const SeedDesc& sd, const uint64_t* d_pos,
+                      uint64_t n, uint64_t* d_fwd, uint64_t* d_dna);
+// (position, reference-layout canonical mer) for sorted-list entries [offset, offset+count)
+// (positions carry the sequence tag above pos_mask)
+void launch_sml_read(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const uint32_t* d_positions, uint32_t pos_mask,
+                     uint64_t count, uint64_t* d_mers);
+// SortedMerList::bsearch (SortedMerList.cpp:380-394) over sorted-list entries [0, n): d_result[0] = index, [1] = found
+void launch_find_mer(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const uint32_t* d_positions, uint32_t pos_mask,
+                     uint64_t n, uint64_t query_mer, uint64_t* d_result);
+
+// ---- radix_sort.cu ----
+struct SortPlan {
+	int n_passes;
+	int shift[10];
+	int bits[10];
+};
+SortPlan make_sort_plan(int key_bits, int begin_bit = 0);
+size_t radix_max_items();  // largest n one sort call accepts
+// Stable LSD radix sort of (key, u32 value) pairs over plan's digits.  keys/vals are double buffers;
+// d_hist holds n_passes x 256 digit counts of the input (computed by the caller, e.g. fused in extraction).
+// Returns 0 or 1: the index of the buffer pair that holds the sorted result.
+int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], uint64_t n, const SortPlan& plan,
+                     uint32_t* d_hist, const char* prof_name);
+// standalone digit histograms of a key array (for inputs not produced by launch_extract)
+void launch_histogram(Ctx* c, bool key64, const void* d_keys, uint64_t n, const SortPlan& plan, uint32_t* d_hist);
+// exclusive prefix sum of n u32 values (in -> out, may alias); *d_total (optional, device) gets the sum
+void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n, uint32_t* d_total);
+
+
+// ---- batch.cu ----
+// All sequences handed to one create call: packed sequences, the union of their seeds sorted by key, and
+// (lazily) the per-sequence sorted position lists.
+struct Batch {
+	std::shared_ptr<Ctx> ctx;
+	SeedDesc sd;
+	int n_seqs = 0;
+	int pos_bits = 0;  // value = (seq << pos_bits) | position
+	int seq_bits = 0;
+	bool key64 = false;
+	uint64_t n_total = 0;  // seeds in the union
+	std::vector<SeqMeta> meta;
+	DevBuf<SeqMeta> d_meta;
+	DevBuf<uint32_t> packed;
+	DevBuf<uint8_t> keys;      // union, ascending compact key (u32 or u64); ties in (seq, position) order
+	DevBuf<uint32_t> vals;     // union, (seq << pos_bits) | position
+	DevBuf<uint32_t> positions;  // per sequence: slice [seed_off, +n_seeds) sorted by key, still tagged
+	bool have_positions = false;
+	uint32_t pos_mask() const { return pos_bits >= 32 ? 0xffffffffu : ((1u << pos_bits) - 1u); }
+	const uint32_t* sorted_positions();  // builds the per-sequence lists on first use
+};
+std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
+                                              const uint64_t* lens, uint64_t seed);
+struct SeqRef {
+	const Batch* batch;
+	int index;
+};
+std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const std::vector<SeqRef>& seqs);
+
+// ---- kernels_match.cu ----
+struct MatchResult {
+	std::vector<int64_t> flat;  // [SeqCount, Length, starts...] per match
+	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0;
+	uint32_t seq_count = 0, seed_length = 0;
+};
+void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out);
+
+}  // namespace mems

@@ -1,0 +1,237 @@
+// kernels_sml.cu — 2-bit packing and spaced-seed mer extraction (SML build, stage 1).
+//
+// Replaces, for DNA: SortedMerList::translate32 (SortedMerList.cpp:425-460), GetMer (:321-342),
+// GetSeedMer (:726-762), RevCompMer (:597-614), GetDnaSeedMer (:764-769), FillDnaSeedSML (:771-783)
+// and the rolling FillDnaSML (:617-723), which yields the same keys for solid seeds.
+#include "common.cuh"
+#include "seed_dev.cuh"
+
+namespace mems {
+
+// ------------------------------------------------------------------------------------------------
+// pack: one thread per output word = 16 bases, one 128-bit load of ASCII per thread.
+// grid.y = sequence, grid.x covers the longest sequence's words (incl. the two zero pad words).
+constexpr int kPackThreads = 256;
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_kernel(const uint8_t* __restrict__ ascii, uint32_t* __restrict__ packed, const SeqMeta* __restrict__ meta,
+            uint32_t* __restrict__ gap_flag) {
+	// BasicDNATable (SortedMerList.cpp:29-47): c,b,y -> 1; g,s,k -> 2; t -> 3; everything else (incl. N) -> 0
+	__shared__ uint8_t lut[256];
+	for (int i = threadIdx.x; i < 256; i += kPackThreads) {
+		int c = i | 0x20;  // fold case
+		uint8_t v = 0;
+		bool alpha = (i >= 'A' && i <= 'Z') || (i >= 'a' && i <= 'z');
+		if (alpha) {
+			if (c == 'c' || c == 'b' || c == 'y') v = 1;
+			else if (c == 'g' || c == 's' || c == 'k') v = 2;
+			else if (c == 't') v = 3;
+		}
+		if (i == '-') v = 4;  // gap marker: reported, packed as 0
+		lut[i] = v;
+	}
+	__syncthreads();
+	const SeqMeta m = meta[blockIdx.y];
+	const uint64_t n_words = ((uint64_t)m.n_bases + 15) / 16 + 2;
+	uint64_t wi = (uint64_t)blockIdx.x * kPackThreads + threadIdx.x;
+	if (wi >= n_words) return;
+	uint32_t out = 0;
+	uint64_t base0 = wi * 16;
+	if (base0 < m.n_bases) {
+		const uint8_t* src = ascii + m.byte_off + base0;  // byte_off is 16-byte aligned, base0 a multiple of 16
+		uint4 raw = *reinterpret_cast<const uint4*>(src);  // staging buffer is padded to 16 bytes per sequence
+		uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+		uint32_t n_here = m.n_bases - base0 < 16 ? (uint32_t)(m.n_bases - base0) : 16u;
+		bool gap = false;
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			uint32_t ch = (r[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+			uint32_t v = k < (int)n_here ? lut[ch] : 0u;
+			gap |= (v == 4u);
+			out |= (v & 3u) << (30 - 2 * k);
+		}
+		if (gap) atomicOr(gap_flag, 1u);
+	}
+	packed[m.word_off + wi] = out;
+}
+
+void launch_pack(Ctx* c, const uint8_t* d_ascii, uint32_t* d_packed, const SeqMeta* d_meta, const SeqMeta* h_meta,
+                 int n_seqs, uint32_t* d_gap_flag) {
+	uint64_t max_words = 0, total_bases = 0;
+	for (int g = 0; g < n_seqs; ++g) {
+		uint64_t nw = ((uint64_t)h_meta[g].n_bases + 15) / 16 + 2;
+		if (nw > max_words) max_words = nw;
+		total_bases += h_meta[g].n_bases;
+	}
+	dim3 grid((unsigned)((max_words + kPackThreads - 1) / kPackThreads), (unsigned)n_seqs);
+	KernelScope ks(c, "pack", 1.25 * (double)total_bases);
+	pack_kernel<<<grid, kPackThreads, 0, c->stream>>>(d_ascii, d_packed, d_meta, d_gap_flag);
+	MEMS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// extract: one CTA per tile of kExtractTile consecutive seed positions of one sequence.
+// The tile's packed words are staged in shared memory with coalesced loads; every thread then builds
+// its windows from shared memory, so global traffic is 0.25 B/base read + one key/value write per seed.
+// The digit histograms of ALL radix passes are accumulated here (shared-memory atomics, one flush per
+// CTA), which removes the separate 8 B/seed histogram pre-pass of a classic onesweep sort.
+constexpr int kExtractThreads = 256;
+constexpr int kExtractItems = 8;
+constexpr int kExtractTile = kExtractThreads * kExtractItems;
+constexpr int kExtractWords = kExtractTile / 16 + 4;  // tile + up to 31 bases of overhang + funnel word
+constexpr int kMaxPasses = 8;
+
+struct PassDesc {
+	int n_passes;
+	int shift[kMaxPasses];
+	int bits[kMaxPasses];
+};
+
+template <class KeyT>
+__global__ void __launch_bounds__(kExtractThreads)
+extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ meta, SeedDesc sd, int pos_bits,
+               KeyT* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist, PassDesc pd) {
+	__shared__ uint32_t s_words[kExtractWords];
+	__shared__ uint32_t s_hist[kMaxPasses * 256];
+	const SeqMeta m = meta[blockIdx.y];
+	const uint32_t tile0 = blockIdx.x * (uint32_t)kExtractTile;
+	if (tile0 >= m.n_seeds) return;
+	for (int i = threadIdx.x; i < pd.n_passes * 256; i += kExtractThreads) s_hist[i] = 0;
+	// words [tile0/16, ...): the sequence buffer carries two zero pad words, and reads are clamped to it
+	const uint64_t n_words = ((uint64_t)m.n_bases + 15) / 16 + 2;
+	const uint32_t w0 = tile0 >> 4;
+	const uint32_t* src = packed + m.word_off;
+	for (int i = threadIdx.x; i < kExtractWords; i += kExtractThreads) {
+		uint64_t wi = (uint64_t)w0 + i;
+		s_words[i] = wi < n_words ? src[wi] : 0u;
+	}
+	__syncthreads();
+	const uint32_t seq_tag = (uint32_t)blockIdx.y << pos_bits;
+#pragma unroll
+	for (int k = 0; k < kExtractItems; ++k) {
+		uint32_t local = k * kExtractThreads + threadIdx.x;  // striped: a warp writes 32 consecutive keys
+		uint32_t p = tile0 + local;
+		if (p < m.n_seeds) {
+			uint64_t win = window64(s_words, local);  // tile0 is a multiple of 16, so local indexes s_words directly
+			uint64_t ck = canonical_key(extract_fwd(win, sd), sd.w);
+			keys[m.seed_off + p] = (KeyT)ck;
+			vals[m.seed_off + p] = seq_tag | p;
+#pragma unroll
+			for (int q = 0; q < kMaxPasses; ++q) {
+				if (q >= pd.n_passes) break;
+				uint32_t d = (uint32_t)(ck >> pd.shift[q]) & ((1u << pd.bits[q]) - 1u);
+				atomicAdd(&s_hist[q * 256 + d], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < pd.n_passes * 256; i += kExtractThreads) {
+		uint32_t v = s_hist[i];
+		if (v) atomicAdd(&hist[i], v);
+	}
+}
+
+void launch_extract(Ctx* c, const uint32_t* d_packed, const SeqMeta* d_meta, const SeqMeta* h_meta, int n_seqs,
+                    const SeedDesc& sd, int pos_bits, bool key64, void* d_keys, uint32_t* d_vals, uint32_t* d_hist,
+                    int n_passes, const int* pass_shift, const int* pass_bits) {
+	uint32_t max_seeds = 0;
+	uint64_t total = 0;
+	for (int g = 0; g < n_seqs; ++g) {
+		if (h_meta[g].n_seeds > max_seeds) max_seeds = h_meta[g].n_seeds;
+		total += h_meta[g].n_seeds;
+	}
+	if (max_seeds == 0) return;
+	if (n_passes > kMaxPasses) throw Error(4, "too many radix passes");
+	PassDesc pd;
+	pd.n_passes = n_passes;
+	for (int q = 0; q < n_passes; ++q) {
+		pd.shift[q] = pass_shift[q];
+		pd.bits[q] = pass_bits[q];
+	}
+	dim3 grid((max_seeds + kExtractTile - 1) / kExtractTile, (unsigned)n_seqs);
+	double bytes = (double)total * (0.25 + (key64 ? 8.0 : 4.0) + 4.0);
+	KernelScope ks(c, "extract", bytes);
+	if (key64)
+		extract_kernel<uint64_t><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
+		                                                                   (uint64_t*)d_keys, d_vals, d_hist, pd);
+	else
+		extract_kernel<uint32_t><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
+		                                                                   (uint32_t*)d_keys, d_vals, d_hist, pd);
+	MEMS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// accessors (SortedMerList::GetSeedMer / GetDnaSeedMer / MemorySML::Read): gather-style, one thread per query.
+__global__ void seed_mers_kernel(const uint32_t* __restrict__ words, uint32_t n_seeds, SeedDesc sd,
+                                 const uint64_t* __restrict__ pos, uint64_t n, uint64_t* __restrict__ fwd_out,
+                                 uint64_t* __restrict__ dna_out) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t p = pos[i];
+	uint64_t f = 0, d = 0;
+	if (p < n_seeds) {
+		uint64_t fw = extract_fwd(window64(words, (uint32_t)p), sd);
+		f = fw << (64 - 2 * sd.w);
+		d = to_reference_mer(canonical_key(fw, sd.w), sd.w);
+	}
+	if (fwd_out) fwd_out[i] = f;
+	if (dna_out) dna_out[i] = d;
+}
+
+void launch_seed_mers(Ctx* c, const uint32_t* d_words, uint32_t n_seeds, const SeedDesc& sd, const uint64_t* d_pos,
+                      uint64_t n, uint64_t* d_fwd, uint64_t* d_dna) {
+	if (n == 0) return;
+	KernelScope ks(c, "seed_mers");
+	seed_mers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_words, n_seeds, sd, d_pos, n, d_fwd, d_dna);
+	MEMS_CUDA(cudaGetLastError());
+}
+
+__global__ void sml_read_kernel(const uint32_t* __restrict__ words, SeedDesc sd, const uint32_t* __restrict__ positions,
+                                uint32_t pos_mask, uint64_t count, uint64_t* __restrict__ mers) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	uint64_t fw = extract_fwd(window64(words, positions[i] & pos_mask), sd);
+	mers[i] = to_reference_mer(canonical_key(fw, sd.w), sd.w);
+}
+
+// SortedMerList::FindMer/bsearch (SortedMerList.cpp:170-179,380-394): the same bisection (middle = (start+end)/2,
+// inclusive bounds), so "not found" reports the same index the reference would.  One thread; a few dozen probes.
+__global__ void find_mer_kernel(const uint32_t* __restrict__ words, SeedDesc sd, const uint32_t* __restrict__ positions,
+                                uint32_t pos_mask, uint64_t n, uint64_t query, uint64_t* __restrict__ result) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	uint64_t start = 0, end = n - 1, middle = 0;
+	bool found = false;
+	while (true) {
+		middle = (start + end) / 2;
+		uint64_t fw = extract_fwd(window64(words, positions[middle] & pos_mask), sd);
+		uint64_t mer = to_reference_mer(canonical_key(fw, sd.w), sd.w);
+		if (mer == query) {
+			found = true;
+			break;
+		} else if (mer < query && middle < end)
+			start = middle + 1;
+		else if (mer > query && start < middle)
+			end = middle - 1;
+		else
+			break;
+	}
+	result[0] = middle;
+	result[1] = found ? 1 : 0;
+}
+
+void launch_find_mer(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const uint32_t* d_positions, uint32_t pos_mask,
+                     uint64_t n, uint64_t query_mer, uint64_t* d_result) {
+	KernelScope ks(c, "find_mer");
+	find_mer_kernel<<<1, 32, 0, c->stream>>>(d_words, sd, d_positions, pos_mask, n, query_mer, d_result);
+	MEMS_CUDA(cudaGetLastError());
+}
+
+void launch_sml_read(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const uint32_t* d_positions, uint32_t pos_mask,
+                     uint64_t count, uint64_t* d_mers) {
+	if (count == 0) return;
+	KernelScope ks(c, "sml_read");
+	sml_read_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(d_words, sd, d_positions, pos_mask, count, d_mers);
+	MEMS_CUDA(cudaGetLastError());
+}
+
+}  // namespace mems

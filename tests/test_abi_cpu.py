@@ -1,0 +1,49 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every declared symbol, its host-side seed
+arithmetic matches the reference's golden table, and compute calls fail loudly without a GPU."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+
+import libmems_b200 as mems
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mems_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mems_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    lib = mems.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(mems.EXPORTS) == declared
+
+
+def test_seed_table_matches_reference_golden():
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "seeds.json")))
+    for key, (seed, length, weight) in g["seeds"].items():
+        w, r = (int(x) for x in key.split(","))
+        assert mems.get_seed(w, r) == seed
+        assert mems.get_seed_length(seed) == length
+        assert mems.get_seed_weight(seed) == weight
+    for n, w in g["default_weight"].items():
+        assert mems.get_default_seed_weight(int(n)) == w
+    assert mems.get_seed(40, 0) == (1 << 32) - 1  # weight > 31 -> solid 32 (SeedMasks.h:309-310)
+    assert mems.get_seed(13, 9) == (1 << 13) - 1  # rank > 5 -> solid
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mems.MemsError) as e:
+        mems.Context(0)
+    assert e.value.code == 3  # MEMS_ERR_CUDA
