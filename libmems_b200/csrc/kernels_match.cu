@@ -1,8 +1,773 @@
-// kernels_match.cu — placeholder until the match pipeline lands (next commit).
+// kernels_match.cu — match finding on the sorted union of a batch (MemHash / RepeatHash).
+//
+// Reference flow (CPU, sequential): MatchFinder::SearchRange k-way merges the SMLs and hands every
+// equal-seed run to EnumerateMatches (MatchFinder.cpp:172-340); MemHash keeps runs that hold the seed at
+// most once per sequence and in >= 2 sequences (MemHash.cpp:139-162), RepeatHash keeps every run of its
+// single sequence (RepeatHash.cpp:34-62); each kept run is a "hit" that AddHashEntry drops if an
+// already-stored match contains it on the same diagonal, else extends with ExtendMatch
+// (MatchFinder.h:219-374) and stores (MemHash.cpp:209-251).
+//
+// The extended result of a hit is the connected component of matching seed windows on the hit's
+// diagonal, where windows count as adjacent when they start <= L apart.  That
+// turns the sequential table into data-parallel steps:
+//   1. run scan     — one thread per union entry; run heads validate their run -> hit list (key order)
+//   2. describe     — per hit: first member, 64-bit hash of its diagonal (member set, orientations,
+//                     offsets) -> sort key (diagonal hash | first-member position)
+//   3. sort         — hits by that key (radix_sort.cu): hits of one diagonal become contiguous, by position
+//   4. segments     — neighbours on the same diagonal <= L apart are connected without looking at sequence
+//   5. extend       — one warp per segment walks left/right with the window test (lane d tests the window
+//                     d positions away; ballot picks the farthest), hopping over later segments of the
+//                     same diagonal; a segment that reaches its predecessor is absorbed by it
+//   6. emit         — surviving components -> [SeqCount, Length, starts] records
+// Hash collisions between diagonals only split segments (more window tests), never merge them: every
+// merge decision compares the full member lists.
+#include <algorithm>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "mems_b200.h"
+#include "seed_dev.cuh"
+
 namespace mems {
-void find_matches_on_batch(Batch&, int, int, uint32_t, MatchResult&) {
-	throw Error(MEMS_ERR_UNSUPPORTED, "match finding not built yet");
+
+constexpr uint32_t kRunCap = MEMS_MER_REPEAT_LIMIT;  // longer runs are dropped and reported via max_run
+constexpr uint16_t kFirstStrandBit = 0x8000;         // hit_len bit 15: strand of the hit's first member
+
+struct MatchArgs {
+	const void* keys;      // union compact keys
+	const uint32_t* vals;  // union (seq << pos_bits) | pos
+	uint32_t n;
+	int pos_bits;
+	uint32_t pos_mask;
+	int n_seqs;
+	int mode;
+	const uint32_t* packed;
+	const SeqMeta* meta;
+};
+
+template <class KeyT>
+__device__ __forceinline__ uint64_t masked_of(const void* keys, uint32_t i) {
+	return (uint64_t)(reinterpret_cast<const KeyT*>(keys)[i] >> 1);
 }
+template <class KeyT>
+__device__ __forceinline__ uint32_t strand_of(const void* keys, uint32_t i) {
+	return (uint32_t)(reinterpret_cast<const KeyT*>(keys)[i] & 1);
 }
+
+// ------------------------------------------------------------------------------------------------ 1. run scan
+constexpr int kScanBlock = 256;
+
+// run_info[i] = number of union entries in the hit that starts at i (0 = no hit starts here)
+template <class KeyT>
+__global__ void __launch_bounds__(kScanBlock)
+run_scan_kernel(MatchArgs a, uint16_t* __restrict__ run_info, uint32_t* __restrict__ block_hits,
+                uint32_t* __restrict__ max_run) {
+	__shared__ uint32_t s_cnt[kScanBlock / 32];
+	__shared__ uint32_t s_max[kScanBlock / 32];
+	const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+	uint16_t info = 0;
+	uint32_t my_run = 0;
+	if (i < a.n) {
+		const uint64_t mk = masked_of<KeyT>(a.keys, i);
+		const bool head = i == 0 || masked_of<KeyT>(a.keys, i - 1) != mk;
+		if (head && i + 1 < a.n && masked_of<KeyT>(a.keys, i + 1) == mk) {
+			uint32_t len = 1;
+			bool ok = true;
+			if (a.mode == MEMS_MODE_MEMHASH) {
+				// at most one occurrence per sequence (repeat_tolerance 0), >= 2 sequences
+				uint64_t seen = 1ull << (a.vals[i] >> a.pos_bits);
+				uint32_t j = i + 1;
+				while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
+					if (ok) {
+						uint64_t bit = 1ull << (a.vals[j] >> a.pos_bits);
+						if (seen & bit) ok = false;
+						seen |= bit;
+					}
+					++len;
+					++j;
+				}
+			} else {
+				uint32_t j = i + 1;
+				while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
+					++len;
+					++j;
+				}
+			}
+			my_run = len;
+			if (len > kRunCap) ok = false;
+			if (ok) info = (uint16_t)len;
+		}
+		run_info[i] = info;
+	}
+	uint32_t b = __ballot_sync(0xffffffffu, info != 0);
+	my_run = __reduce_max_sync(0xffffffffu, my_run);
+	if ((threadIdx.x & 31) == 0) {
+		s_cnt[threadIdx.x >> 5] = __popc(b);
+		s_max[threadIdx.x >> 5] = my_run;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0, mx = 0;
+		for (int w = 0; w < kScanBlock / 32; ++w) {
+			t += s_cnt[w];
+			mx = max(mx, s_max[w]);
+		}
+		block_hits[blockIdx.x] = t;
+		if (mx > 1) atomicMax(max_run, mx);  // one atomic per CTA
+	}
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+hit_compact_kernel(const uint16_t* __restrict__ run_info, uint32_t n, const uint32_t* __restrict__ block_off,
+                   uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len) {
+	__shared__ uint32_t s_cnt[kScanBlock / 32];
+	const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+	const uint16_t info = i < n ? run_info[i] : (uint16_t)0;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t b = __ballot_sync(0xffffffffu, info != 0);
+	if (lane == 0) s_cnt[warp] = __popc(b);
+	__syncthreads();
+	uint32_t off = block_off[blockIdx.x];
+	for (uint32_t w = 0; w < warp; ++w) off += s_cnt[w];
+	if (info) {
+		uint32_t at = off + __popc(b & ((1u << lane) - 1u));
+		hit_start[at] = i;
+		hit_len[at] = info;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ members
+// Members of a hit in ascending (sequence, position) order.  Inside a run the union is ordered by strand
+// first (the strand is the key's low bit), then by (sequence, position): two sorted sublists to merge.
+template <class KeyT>
+struct MemberIter {
+	const MatchArgs& a;
+	uint32_t i0, m, i1, e;
+	__device__ MemberIter(const MatchArgs& args, uint32_t s, uint32_t len) : a(args), i0(s), e(s + len) {
+		m = s;
+		while (m < e && strand_of<KeyT>(a.keys, m) == 0) ++m;
+		i1 = m;
+	}
+	__device__ bool next(uint32_t& val, uint32_t& strand) {
+		if (i0 >= m && i1 >= e) return false;
+		bool take0 = i1 >= e || (i0 < m && a.vals[i0] < a.vals[i1]);
+		if (take0) {
+			val = a.vals[i0++];
+			strand = 0;
+		} else {
+			val = a.vals[i1++];
+			strand = 1;
+		}
+		return true;
+	}
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
+	h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+	h *= 0xBF58476D1CE4E5B9ull;
+	h ^= h >> 31;
+	return h;
+}
+
+// ------------------------------------------------------------------------------------------------ 2. describe
+constexpr int kMaxHitPasses = 8;
+
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len, uint32_t n_hits,
+                    uint64_t* __restrict__ hkey, uint32_t* __restrict__ hid, uint32_t* __restrict__ hist, SortPlan plan) {
+	__shared__ uint32_t s_hist[kMaxHitPasses * 256];
+	for (int i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) s_hist[i] = 0;
+	__syncthreads();
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h < n_hits) {
+		const uint32_t s = hit_start[h];
+		const uint32_t len = hit_len[h];
+		MemberIter<KeyT> it(a, s, len);
+		uint32_t val, st;
+		it.next(val, st);
+		const uint32_t sf = st;
+		const int64_t x0 = val & a.pos_mask;
+		uint64_t hash = mix64(0x1234567ull + len, val >> a.pos_bits);
+		while (it.next(val, st)) {
+			const uint32_t o = st ^ sf;
+			const int64_t p = val & a.pos_mask;
+			const int64_t diag = o ? p + x0 : p - x0;
+			hash = mix64(hash, ((uint64_t)(val >> a.pos_bits) << 1) | o);
+			hash = mix64(hash, (uint64_t)diag);
+		}
+		const uint64_t key = ((hash >> a.pos_bits) << a.pos_bits) | (uint64_t)x0;
+		hkey[h] = key;
+		hid[h] = h;
+		hit_len[h] = (uint16_t)(len | (sf ? kFirstStrandBit : 0));
+#pragma unroll
+		for (int q = 0; q < kMaxHitPasses; ++q) {
+			if (q >= plan.n_passes) break;
+			atomicAdd(&s_hist[q * 256 + ((uint32_t)(key >> plan.shift[q]) & ((1u << plan.bits[q]) - 1u))], 1u);
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) {
+		uint32_t v = s_hist[i];
+		if (v) atomicAdd(&hist[i], v);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ 4. segments
+// same diagonal: same member sequences, same relative orientations, same offsets to the first member
+template <class KeyT>
+__device__ bool same_diagonal(const MatchArgs& a, uint32_t sa, uint32_t la, uint32_t sb, uint32_t lb) {
+	if (la != lb) return false;
+	MemberIter<KeyT> ia(a, sa, la), ib(a, sb, lb);
+	uint32_t va, ta, vb, tb;
+	ia.next(va, ta);
+	ib.next(vb, tb);
+	if ((va >> a.pos_bits) != (vb >> a.pos_bits)) return false;
+	const uint32_t fa = ta, fb = tb;
+	const int64_t xa = va & a.pos_mask, xb = vb & a.pos_mask;
+	while (ia.next(va, ta)) {
+		ib.next(vb, tb);
+		if ((va >> a.pos_bits) != (vb >> a.pos_bits)) return false;
+		const uint32_t oa = ta ^ fa, ob = tb ^ fb;
+		if (oa != ob) return false;
+		const int64_t pa = va & a.pos_mask, pb = vb & a.pos_mask;
+		if ((oa ? pa + xa : pa - xa) != (ob ? pb + xb : pb - xb)) return false;
+	}
+	return true;
+}
+
+constexpr uint8_t kFlagHead = 1;      // starts a new segment
+constexpr uint8_t kFlagSameDiag = 2;  // same diagonal as the previous entry in sorted order
+
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
+                    const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
+                    uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_hits) return;
+	uint8_t f = kFlagHead;
+	if (i > 0) {
+		const uint64_t k = hkey[i], kp = hkey[i - 1];
+		if ((k >> a.pos_bits) == (kp >> a.pos_bits)) {
+			const uint32_t ha = hid[i], hb = hid[i - 1];
+			if (same_diagonal<KeyT>(a, hit_start[ha], hit_len[ha] & ~kFirstStrandBit, hit_start[hb],
+			                        hit_len[hb] & ~kFirstStrandBit)) {
+				f = kFlagSameDiag;
+				const uint64_t gap = (k & a.pos_mask) - (kp & a.pos_mask);
+				if (gap > (uint64_t)L) f |= kFlagHead;
+			}
+		}
+	}
+	flags[i] = f;
+	is_head[i] = (f & kFlagHead) ? 1u : 0u;
+}
+
+__global__ void segment_compact_kernel(const uint32_t* __restrict__ is_head, const uint32_t* __restrict__ seg_of,
+                                       uint32_t n_hits, uint32_t* __restrict__ seg_head) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_hits && is_head[i]) seg_head[seg_of[i]] = i;
+}
+
+// ------------------------------------------------------------------------------------------------ 5. extend
+// The window test of MatchFinder::ExtendMatch (MatchFinder.h:264-308) for the window k positions from the
+// hit (k < 0: towards the first member's start): every member's seed position must be valid, all masked
+// keys equal, and all (strand xor orientation) parities equal.
+template <class KeyT>
+__device__ bool window_matches(const MatchArgs& a, const SeedDesc& sd, uint32_t s, uint32_t len, uint32_t sf, int64_t k) {
+	uint64_t ref = 0;
+	bool have = false;
+	for (uint32_t j = s; j < s + len; ++j) {
+		const uint32_t val = a.vals[j];
+		const uint32_t o = strand_of<KeyT>(a.keys, j) ^ sf;
+		const uint32_t seq = val >> a.pos_bits;
+		const int64_t p = val & a.pos_mask;
+		const int64_t q = o ? p - k : p + k;
+		const SeqMeta m = a.meta[seq];
+		if (q < 0 || q >= (int64_t)m.n_seeds) return false;
+		const uint64_t ck = canonical_key(extract_fwd(window64(a.packed + m.word_off, (uint32_t)q), sd), sd.w);
+		const uint64_t tagged = ck ^ (uint64_t)o;  // flips the strand bit for reverse members
+		if (!have) {
+			ref = tagged;
+			have = true;
+		} else if (tagged != ref)
+			return false;
+	}
+	return true;
+}
+
+constexpr int kExtendWarps = 4;
+
+template <class KeyT>
+__global__ void __launch_bounds__(kExtendWarps * 32)
+extend_kernel(MatchArgs a, SeedDesc sd, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
+              const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
+              const uint8_t* __restrict__ flags, const uint32_t* __restrict__ seg_head, uint32_t n_seg,
+              int32_t* __restrict__ seg_kl, int32_t* __restrict__ seg_kr, uint32_t* __restrict__ seg_emit) {
+	const uint32_t seg = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
+	if (seg >= n_seg) return;
+	const int lane = threadIdx.x & 31;
+	const int L = sd.L;
+	const uint32_t hi = seg_head[seg];
+	const uint32_t h = hid[hi];
+	const uint32_t s = hit_start[h];
+	const uint32_t len = hit_len[h] & ~kFirstStrandBit;
+	const uint32_t sf = (hit_len[h] & kFirstStrandBit) ? 1u : 0u;
+	const int64_t x0 = (int64_t)(hkey[hi] & a.pos_mask);
+	const int d = lane + 1;  // lanes 0..L-1 probe distances 1..L
+
+	// ---- left
+	int64_t kl = 0;
+	bool absorbed = false;
+	const bool prev_same = (flags[hi] & kFlagSameDiag) != 0;
+	const int64_t absorb_at = prev_same ? (int64_t)(hkey[hi - 1] & a.pos_mask) - x0 + L : 0;
+	while (true) {
+		bool ok = d <= L && window_matches<KeyT>(a, sd, s, len, sf, kl - d);
+		uint32_t b = __ballot_sync(0xffffffffu, ok);
+		if (!b) break;
+		kl -= 32 - __clz(b);
+		if (prev_same && kl <= absorb_at) {
+			absorbed = true;
+			break;
+		}
+	}
+	// ---- right
+	int64_t c = 0;
+	if (!absorbed) {
+		uint32_t cur = seg;
+		uint32_t end = cur + 1 < n_seg ? seg_head[cur + 1] : n_hits;
+		c = (int64_t)(hkey[end - 1] & a.pos_mask) - x0;
+		while (true) {
+			if (cur + 1 < n_seg) {
+				const uint32_t nh = seg_head[cur + 1];
+				if ((flags[nh] & kFlagSameDiag) && (int64_t)(hkey[nh] & a.pos_mask) - x0 <= c + L) {
+					// the next segment of this diagonal starts within reach: everything up to its last hit is connected
+					++cur;
+					end = cur + 1 < n_seg ? seg_head[cur + 1] : n_hits;
+					const int64_t t = (int64_t)(hkey[end - 1] & a.pos_mask) - x0;
+					if (t > c) c = t;
+					continue;
+				}
+			}
+			bool ok = d <= L && window_matches<KeyT>(a, sd, s, len, sf, c + d);
+			uint32_t b = __ballot_sync(0xffffffffu, ok);
+			if (!b) break;
+			c += 32 - __clz(b);
+		}
+	}
+	if (lane == 0) {
+		seg_kl[seg] = (int32_t)kl;
+		seg_kr[seg] = (int32_t)c;
+		seg_emit[seg] = absorbed ? 0u : 1u;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ 6. emit
+__global__ void emit_size_kernel(const uint32_t* __restrict__ seg_emit, const uint32_t* __restrict__ seg_head,
+                                 const uint32_t* __restrict__ hid, const uint16_t* __restrict__ hit_len, uint32_t n_seg,
+                                 int mode, int n_seqs, uint32_t* __restrict__ rec_size) {
+	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg >= n_seg) return;
+	uint32_t sz = 0;
+	if (seg_emit[seg]) {
+		const uint32_t len = hit_len[hid[seg_head[seg]]] & ~kFirstStrandBit;
+		sz = 2u + (mode == MEMS_MODE_REPEAT ? len : (uint32_t)n_seqs);
+	}
+	rec_size[seg] = sz;
+}
+
+template <class KeyT>
+__global__ void emit_kernel(MatchArgs a, int L, const uint32_t* __restrict__ seg_emit, const uint32_t* __restrict__ seg_head,
+                            const uint32_t* __restrict__ hid, const uint32_t* __restrict__ hit_start,
+                            const uint16_t* __restrict__ hit_len, const int32_t* __restrict__ seg_kl,
+                            const int32_t* __restrict__ seg_kr, const uint32_t* __restrict__ rec_off, uint32_t n_seg,
+                            int64_t* __restrict__ flat) {
+	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg >= n_seg || !seg_emit[seg]) return;
+	const uint32_t h = hid[seg_head[seg]];
+	const uint32_t s = hit_start[h];
+	const uint32_t len = hit_len[h] & ~kFirstStrandBit;
+	const uint32_t sf = (hit_len[h] & kFirstStrandBit) ? 1u : 0u;
+	const int64_t kl = seg_kl[seg], kr = seg_kr[seg];
+	int64_t* rec = flat + rec_off[seg];
+	const uint32_t seqcount = a.mode == MEMS_MODE_REPEAT ? len : (uint32_t)a.n_seqs;
+	rec[0] = seqcount;
+	rec[1] = kr - kl + L;
+	if (a.mode != MEMS_MODE_REPEAT)
+		for (uint32_t g = 0; g < seqcount; ++g) rec[2 + g] = 0;  // NO_MATCH
+	MemberIter<KeyT> it(a, s, len);
+	uint32_t val, st, idx = 0;
+	while (it.next(val, st)) {
+		const uint32_t o = st ^ sf;
+		const int64_t p = val & a.pos_mask;
+		// forward member: first covered base p+kl (1-based start p+kl+1); reverse member: covers p-kr .. p-kl+L-1
+		const int64_t start = o ? -(p - kr + 1) : (p + kl + 1);
+		const uint32_t slot = a.mode == MEMS_MODE_REPEAT ? idx : (val >> a.pos_bits);
+		rec[2 + slot] = start;
+		++idx;
+	}
+}
+
+// hit members in merged order, for the host-side table emulation (ORDER_REFERENCE)
+template <class KeyT>
+__global__ void gather_members_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len,
+                                      const uint32_t* __restrict__ mem_off, uint32_t n_hits, uint32_t* __restrict__ mem_val,
+                                      uint8_t* __restrict__ mem_strand) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h >= n_hits) return;
+	MemberIter<KeyT> it(a, hit_start[h], hit_len[h] & ~kFirstStrandBit);
+	uint32_t val, st, at = mem_off[h];
+	while (it.next(val, st)) {
+		mem_val[at] = val;
+		mem_strand[at] = (uint8_t)st;
+		++at;
+	}
+}
+
+__global__ void hit_len_widen_kernel(const uint16_t* __restrict__ hit_len, uint32_t n_hits, uint32_t* __restrict__ out) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h < n_hits) out[h] = hit_len[h] & ~kFirstStrandBit;
+}
+
+// record index of every hit: sorted entry -> segment -> the emitted component it belongs to
+__global__ void hit_record_kernel(const uint32_t* __restrict__ hid, const uint32_t* __restrict__ is_head,
+                                  const uint32_t* __restrict__ seg_of, const uint32_t* __restrict__ emit_excl,
+                                  const uint32_t* __restrict__ seg_emit, uint32_t n_hits, uint32_t* __restrict__ rec_of_hit) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_hits) return;
+	// seg_of is an exclusive scan of is_head: a head's own segment is seg_of[i], a follower's is seg_of[i]-1
+	const uint32_t seg = is_head[i] ? seg_of[i] : seg_of[i] - 1;
+	// an absorbed segment belongs to the closest emitted segment before it
+	const uint32_t rec = emit_excl[seg] + (seg_emit[seg] ? 1u : 0u) - 1u;
+	rec_of_hit[hid[i]] = rec;
+}
+
+// ================================================================================================ host side
+namespace {
+
+uint32_t d2h_u32(Ctx* c, const uint32_t* d) {
+	uint32_t v = 0;
+	MEMS_CUDA(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	return v;
+}
+
+struct Rec {
+	const int64_t* p;  // [SeqCount, Len, starts...]
+	size_t size() const { return (size_t)p[0] + 2; }
+};
+bool rec_less(const Rec& x, const Rec& y) { return std::lexicographical_compare(x.p, x.p + x.size(), y.p, y.p + y.size()); }
+bool rec_equal(const Rec& x, const Rec& y) { return x.size() == y.size() && std::equal(x.p, x.p + x.size(), y.p); }
+
+std::vector<Rec> split_records(const std::vector<int64_t>& flat) {
+	std::vector<Rec> recs;
+	for (size_t i = 0; i < flat.size(); i += (size_t)flat[i] + 2) recs.push_back({flat.data() + i});
+	return recs;
+}
+
+// ---- the reference's hash table, replayed on the host over (hit, extended match) pairs ------------------
+// MemHash::AddHashEntry (MemHash.cpp:209-251) with MheCompare (MatchHashEntry.h:121-143),
+// MatchHashEntry::Contains (MatchHashEntry.cpp:164-200), strict_start_lessthan_ptr (:48-67) and
+// CalculateOffset (:141-160).  Needed because the table's lower_bound over a comparator that is not a
+// strict weak order decides WHICH hits are dropped as collisions and the output order.
+struct Entry {
+	uint32_t seqcount;
+	int64_t len, mersize, offset;
+	const int64_t* start;  // seqcount values
+	std::vector<int64_t> own;
+};
+inline int64_t e_start(const Entry& e, uint32_t i) { return i < e.seqcount ? e.start[i] : 0; }
+inline uint32_t e_first(const Entry& e) {
+	for (uint32_t i = 0; i < e.seqcount; ++i)
+		if (e.start[i] != 0) return i;
+	return 0xffffffffu;
+}
+void e_calc_offset(Entry& e) {
+	e.offset = 0;
+	uint32_t i = e_first(e);
+	if (i == 0xffffffffu) return;
+	const int64_t ref = e.start[i];
+	for (++i; i < e.seqcount; ++i)
+		if (e.start[i] != 0) {
+			int64_t t = e.start[i] - ref;
+			if (e.start[i] < 0) t -= e.len;
+			e.offset += t;
+		}
+}
+bool e_contains(const Entry& A, const Entry& m) {
+	if (A.seqcount != m.seqcount || A.offset != m.offset) return false;
+	uint32_t i = e_first(m);
+	const int64_t diff = e_start(m, i) - e_start(A, i);
+	if (e_start(A, i) == 0) return false;
+	if (diff < 0 || A.len < m.len + diff) return false;
+	const int64_t diff_rc = m.len - A.len + diff;
+	for (++i; i < m.seqcount; ++i) {
+		const int64_t d = m.start[i] - A.start[i];
+		if (m.start[i] == 0 && A.start[i] == 0) continue;
+		else if (m.start[i] < 0 && diff_rc == d) continue;
+		else if (diff != d) return false;
+	}
+	return true;
+}
+bool e_strict_less(const Entry& a, const Entry& b) {
+	const int fa = (int)e_first(a), fb = (int)e_first(b);
+	const int start_diff = fa - fb;
+	if (start_diff == 0) {
+		const uint32_t cnt = std::min(a.seqcount, b.seqcount);
+		for (uint32_t s = 0; s < cnt; ++s) {
+			int64_t x = a.start[s], y = b.start[s];
+			if (x < 0) x = -x + a.len - a.mersize;
+			if (y < 0) y = -y + b.len - b.mersize;
+			if (x != y) return x < y;
+		}
+	}
+	return start_diff < 0;
+}
+bool e_compare(const Entry& a, const Entry& b) {
+	const uint32_t fa = e_first(a), fb = e_first(b);
+	if (fa > fb) return true;
+	if (fa == fb) {
+		for (uint32_t i = fa; i < a.seqcount; ++i) {
+			const int64_t as = e_start(a, i), bs = e_start(b, i);
+			if (as == 0 && bs != 0) return true;
+			else if (as != 0 && bs == 0) return false;
+		}
+		if (e_contains(a, b) || e_contains(b, a)) return false;
+		return e_strict_less(a, b);
+	}
+	return false;
+}
+size_t bucket_lower_bound(const std::vector<Entry*>& v, const Entry& x) {
+	size_t first = 0, len = v.size();
+	while (len > 0) {
+		size_t half = len >> 1, mid = first + half;
+		if (e_compare(*v[mid], x)) {
+			first = mid + 1;
+			len = len - half - 1;
+		} else
+			len = half;
+	}
+	return first;
+}
+
+}  // namespace
+
+template <class KeyT>
+static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
+	Ctx* c = b.ctx.get();
+	const uint32_t n = (uint32_t)b.n_total;
+	const int L = b.sd.L;
+	out.seq_count = (uint32_t)b.n_seqs;
+	out.seed_length = (uint32_t)L;
+	if (n < 2) return;
+
+	MatchArgs a;
+	a.keys = b.keys.p;
+	a.vals = b.vals.p;
+	a.n = n;
+	a.pos_bits = b.pos_bits;
+	a.pos_mask = b.pos_mask();
+	a.n_seqs = b.n_seqs;
+	a.mode = mode;
+	a.packed = b.packed.p;
+	a.meta = b.d_meta.p;
+
+	// ---- 1. run scan -> hits in key order
+	const uint32_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
+	DevBuf<uint16_t> run_info(c, n);
+	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 4);
+	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 4 * sizeof(uint32_t), c->stream));
+	{
+		KernelScope ks(c, "run_scan", (double)n * (sizeof(KeyT) + 2.0));
+		run_scan_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, run_info.p, block_hits.p, scalars.p + 0);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	exclusive_scan_u32(c, block_hits.p, block_hits.p, n_blocks, scalars.p + 1);
+	uint32_t h_scal[2];
+	MEMS_CUDA(cudaMemcpyAsync(h_scal, scalars.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	out.max_run = h_scal[0];
+	const uint32_t n_hits = h_scal[1];
+	out.n_hits = n_hits;
+	if (n_hits == 0) return;
+	DevBuf<uint32_t> hit_start(c, n_hits);
+	DevBuf<uint16_t> hit_len(c, n_hits);
+	{
+		KernelScope ks(c, "hit_compact", (double)n * 2.0);
+		hit_compact_kernel<<<n_blocks, kScanBlock, 0, c->stream>>>(run_info.p, n, block_hits.p, hit_start.p, hit_len.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	run_info.reset();
+
+	// ---- 2. describe + 3. sort by (diagonal hash, first-member position)
+	SortPlan plan = make_sort_plan(64);
+	DevBuf<uint64_t> hk_a(c, n_hits), hk_b(c, n_hits);
+	DevBuf<uint32_t> hid_a(c, n_hits), hid_b(c, n_hits), hist(c, (size_t)plan.n_passes * 256);
+	MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)plan.n_passes * 256 * sizeof(uint32_t), c->stream));
+	const uint32_t hit_blocks = (n_hits + 255) / 256;
+	{
+		KernelScope ks(c, "hit_describe");
+		hit_describe_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, hit_start.p, hit_len.p, n_hits, hk_a.p, hid_a.p,
+		                                                             hist.p, plan);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	void* kp[2] = {hk_a.p, hk_b.p};
+	uint32_t* vp[2] = {hid_a.p, hid_b.p};
+	const int r = radix_sort_pairs(c, true, kp, vp, n_hits, plan, hist.p, "hit_sort_pass");
+	const uint64_t* hkey = r ? hk_b.p : hk_a.p;
+	const uint32_t* hid = r ? hid_b.p : hid_a.p;
+
+	// ---- 4. segments
+	DevBuf<uint8_t> flags(c, n_hits);
+	DevBuf<uint32_t> is_head(c, n_hits), seg_of(c, n_hits);
+	{
+		KernelScope ks(c, "segment_flag");
+		segment_flag_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, L, hkey, hid, hit_start.p, hit_len.p, n_hits,
+		                                                             flags.p, is_head.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	exclusive_scan_u32(c, is_head.p, seg_of.p, n_hits, scalars.p + 2);
+	const uint32_t n_seg = d2h_u32(c, scalars.p + 2);
+	DevBuf<uint32_t> seg_head(c, n_seg);
+	{
+		KernelScope ks(c, "segment_compact");
+		segment_compact_kernel<<<hit_blocks, 256, 0, c->stream>>>(is_head.p, seg_of.p, n_hits, seg_head.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+
+	// ---- 5. extend
+	DevBuf<int32_t> seg_kl(c, n_seg), seg_kr(c, n_seg);
+	DevBuf<uint32_t> seg_emit(c, n_seg), rec_size(c, n_seg), rec_off(c, n_seg);
+	{
+		KernelScope ks(c, "extend");
+		extend_kernel<KeyT><<<(n_seg + kExtendWarps - 1) / kExtendWarps, kExtendWarps * 32, 0, c->stream>>>(
+		    a, b.sd, hkey, hid, hit_start.p, hit_len.p, n_hits, flags.p, seg_head.p, n_seg, seg_kl.p, seg_kr.p, seg_emit.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+
+	// ---- 6. emit
+	const uint32_t seg_blocks = (n_seg + 255) / 256;
+	{
+		KernelScope ks(c, "emit_size");
+		emit_size_kernel<<<seg_blocks, 256, 0, c->stream>>>(seg_emit.p, seg_head.p, hid, hit_len.p, n_seg, mode, b.n_seqs,
+		                                                    rec_size.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	exclusive_scan_u32(c, rec_size.p, rec_off.p, n_seg, scalars.p + 3);
+	const uint32_t n_flat = d2h_u32(c, scalars.p + 3);
+	DevBuf<int64_t> d_flat(c, n_flat);
+	{
+		KernelScope ks(c, "emit");
+		emit_kernel<KeyT><<<seg_blocks, 256, 0, c->stream>>>(a, L, seg_emit.p, seg_head.p, hid, hit_start.p, hit_len.p,
+		                                                     seg_kl.p, seg_kr.p, rec_off.p, n_seg, d_flat.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	std::vector<int64_t> raw(n_flat);
+	MEMS_CUDA(cudaMemcpyAsync(raw.data(), d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+
+	if (order == MEMS_ORDER_CANONICAL) {
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		// distinct matches in canonical order; duplicates only arise when a diagonal-hash collision kept a
+		// segment from seeing its predecessor
+		std::vector<Rec> recs = split_records(raw);
+		std::sort(recs.begin(), recs.end(), rec_less);
+		recs.erase(std::unique(recs.begin(), recs.end(), rec_equal), recs.end());
+		out.flat.reserve(raw.size());
+		for (const Rec& r2 : recs) out.flat.insert(out.flat.end(), r2.p, r2.p + r2.size());
+		out.n_matches = recs.size();
+		out.mem_count = out.n_matches;
+		out.collisions = out.n_hits - out.n_matches;
+		return;
+	}
+
+	// ---- ORDER_REFERENCE: replay the reference's hash table over (hit, extended match) on the host
+	DevBuf<uint32_t> emit_excl(c, n_seg), rec_of_hit(c, n_hits), len32(c, n_hits), mem_off(c, n_hits);
+	exclusive_scan_u32(c, seg_emit.p, emit_excl.p, n_seg, nullptr);
+	{
+		KernelScope ks(c, "hit_record");
+		hit_record_kernel<<<hit_blocks, 256, 0, c->stream>>>(hid, is_head.p, seg_of.p, emit_excl.p, seg_emit.p, n_hits,
+		                                                     rec_of_hit.p);
+		MEMS_CUDA(cudaGetLastError());
+		hit_len_widen_kernel<<<hit_blocks, 256, 0, c->stream>>>(hit_len.p, n_hits, len32.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	exclusive_scan_u32(c, len32.p, mem_off.p, n_hits, scalars.p + 3);
+	const uint32_t n_mem = d2h_u32(c, scalars.p + 3);
+	DevBuf<uint32_t> mem_val(c, n_mem);
+	DevBuf<uint8_t> mem_strand(c, n_mem);
+	{
+		KernelScope ks(c, "gather_members");
+		gather_members_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, hit_start.p, hit_len.p, mem_off.p, n_hits,
+		                                                               mem_val.p, mem_strand.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	std::vector<uint32_t> h_rec(n_hits), h_off(n_hits), h_val(n_mem);
+	std::vector<uint8_t> h_strand(n_mem);
+	MEMS_CUDA(cudaMemcpyAsync(h_rec.data(), rec_of_hit.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaMemcpyAsync(h_off.data(), mem_off.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaMemcpyAsync(h_val.data(), mem_val.p, (size_t)n_mem * 4, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaMemcpyAsync(h_strand.data(), mem_strand.p, (size_t)n_mem, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+
+	// emitted records in segment order: record r starts at raw[rec_start[r]]
+	std::vector<size_t> rec_start;
+	for (size_t i = 0; i < raw.size(); i += (size_t)raw[i] + 2) rec_start.push_back(i);
+
+	std::vector<std::vector<Entry*>> table(table_size);
+	std::vector<std::unique_ptr<Entry>> stored;
+	std::vector<int64_t> probe_start;
+	for (uint32_t h = 0; h < n_hits; ++h) {
+		const uint32_t m0 = h_off[h], m1 = h + 1 < n_hits ? h_off[h + 1] : n_mem;
+		Entry probe;
+		probe.seqcount = mode == MEMS_MODE_REPEAT ? (m1 - m0) : (uint32_t)b.n_seqs;
+		probe.len = L;
+		probe.mersize = L;
+		probe_start.assign(probe.seqcount, 0);
+		const uint32_t sf = h_strand[m0];
+		for (uint32_t j = m0; j < m1; ++j) {
+			const uint32_t slot = mode == MEMS_MODE_REPEAT ? (j - m0) : (h_val[j] >> b.pos_bits);
+			const int64_t st = (int64_t)(h_val[j] & b.pos_mask()) + 1;
+			probe_start[slot] = (h_strand[j] != sf) ? -st : st;  // SetDirection, MemHash.cpp:189-203
+		}
+		probe.start = probe_start.data();
+		e_calc_offset(probe);
+		const int64_t ts = (int64_t)table_size;
+		std::vector<Entry*>& bucket = table[(size_t)(((probe.offset % ts) + ts) % ts)];
+		size_t at = bucket_lower_bound(bucket, probe);
+		if (at != bucket.size() && !e_compare(*bucket[at], probe) && !e_compare(probe, *bucket[at])) {
+			++out.collisions;
+			continue;
+		}
+		// "ExtendMatch": the extended form of this hit is the component the device computed for it
+		const int64_t* rec = raw.data() + rec_start[h_rec[h]];
+		auto e = std::make_unique<Entry>();
+		e->seqcount = (uint32_t)rec[0];
+		e->len = rec[1];
+		e->mersize = 0;  // stored copies lose m_mersize (MatchHashEntry.cpp:118-126)
+		e->start = rec + 2;
+		e_calc_offset(*e);
+		at = bucket_lower_bound(bucket, *e);
+		bucket.insert(bucket.begin() + at, e.get());
+		stored.push_back(std::move(e));
+		++out.mem_count;
+	}
+	// MemHash::GetMatchList (MemHash.h:183-203): buckets in order, front to back
+	for (auto& bucket : table)
+		for (Entry* e : bucket) {
+			out.flat.push_back(e->seqcount);
+			out.flat.push_back(e->len);
+			out.flat.insert(out.flat.end(), e->start, e->start + e->seqcount);
+		}
+	out.n_matches = out.mem_count;
+}
+
+void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
+	if (mode == MEMS_MODE_PAIRWISE) throw Error(MEMS_ERR_UNSUPPORTED, "PairwiseMatchFinder policy is not built yet");
+	if (b.n_seqs > 64) throw Error(MEMS_ERR_UNSUPPORTED, "more than 64 sequences in one match-finding call");
+	if (b.key64)
+		find_matches_typed<uint64_t>(b, mode, order, table_size, out);
+	else
+		find_matches_typed<uint32_t>(b, mode, order, table_size, out);
+}
+
+}  // namespace mems

@@ -1,0 +1,127 @@
+"""MemHash / RepeatHash match finding on the GPU against the oracle and the reference's golden MatchLists.
+All calls go through the C-ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import libmems_b200 as mems
+from checkers import Oracle
+from gpu_util import gpu_context
+from libmems_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = gpu_context()
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def gpu_matches(ctx, seqs, seed, mode, order=mems.ORDER_CANONICAL):
+    smls = ctx.create_smls(seqs, seed)
+    flat, info = ctx.find_matches(smls, mode=mode, order=order)
+    return mems.flat_to_matches(flat), info
+
+
+def canonical(matches):
+    """tuples (SeqCount, Length, Start...) sorted lexicographically, compared as sets."""
+    return sorted(set(matches))
+
+
+def test_golden_matchlists(ctx):
+    for case in json.load(open(os.path.join(GOLD, "matchlists.json"))):
+        if case["mode"] == mems.MODE_PAIRWISE:
+            continue
+        seqs = [s.encode() for s in case["seqs"]]
+        want = [tuple(m) for m in case["matches"]]
+        got, info = gpu_matches(ctx, seqs, case["seed"], case["mode"], mems.ORDER_REFERENCE)
+        assert got == want, case["tag"]  # same matches in the reference's own output order
+        assert info["mem_count"] == case["mem_count"] and info["collisions"] == case["collisions"], case["tag"]
+        if case["mode"] == mems.MODE_MEMHASH:
+            got, _ = gpu_matches(ctx, seqs, case["seed"], case["mode"], mems.ORDER_CANONICAL)
+            assert got == canonical(want), case["tag"]
+
+
+@pytest.mark.parametrize("it", range(16))
+def test_memhash_vs_oracle(ctx, orc, it):
+    rng = np.random.default_rng(5000 + it)
+    w = int(rng.integers(5, 25))
+    seed = mems.get_seed(w, int(rng.integers(0, 3)))
+    G = int(rng.integers(2, 9))
+    n = int(rng.integers(200, 60000))
+    gs = synth.genome_family(G, n, seed=700 + it, snp_rate=float(rng.choice([0.0, 0.01, 0.05])),
+                             n_indels=int(rng.integers(0, 8)), max_indel=30)
+    want, winfo = orc.find_matches(0, gs, seed)
+    got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
+    assert got == canonical(want)
+    assert info["n_hits"] == winfo["hits"]
+    got_ref, info_ref = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH, mems.ORDER_REFERENCE)
+    assert got_ref == want
+    assert info_ref["collisions"] == winfo["collisions"] and info_ref["mem_count"] == winfo["mem_count"]
+
+
+@pytest.mark.parametrize("it", range(10))
+def test_repeathash_vs_oracle(ctx, orc, it):
+    rng = np.random.default_rng(6000 + it)
+    seed = mems.get_seed(int(rng.integers(7, 25)), int(rng.integers(0, 2)))
+    g = synth.repeat_genome(int(rng.integers(5000, 80000)), seed=40 + it, families=int(rng.integers(1, 10)),
+                            copies=int(rng.integers(2, 12)), min_len=50, max_len=800, divergence=0.03)
+    want, winfo = orc.find_matches(1, [g], seed)
+    got, info = gpu_matches(ctx, [g], seed, mems.MODE_REPEAT)
+    assert got == want  # RepeatHash is always replayed in reference order (its drops are order dependent)
+    assert info["collisions"] == winfo["collisions"]
+
+
+def test_singles_then_find_equals_batch(ctx, orc):
+    """DNAMemorySML::Create one by one, then FindMatches (the reference's calling pattern)."""
+    seed = mems.get_seed(15)
+    gs = synth.genome_family(4, 20000, seed=77)
+    smls = [ctx.create_sml(g, seed) for g in gs]
+    flat, _ = ctx.find_matches(smls, mode=mems.MODE_MEMHASH)
+    want, _ = orc.find_matches(0, gs, seed)
+    assert mems.flat_to_matches(flat) == canonical(want)
+    # a subset, in another order, of a batch
+    b = ctx.create_smls(gs, seed)
+    flat, _ = ctx.find_matches([b[2], b[0]], mode=mems.MODE_MEMHASH)
+    want, _ = orc.find_matches(0, [gs[2], gs[0]], seed)
+    assert mems.flat_to_matches(flat) == canonical(want)
+
+
+def test_edge_cases(ctx, orc):
+    seed = mems.get_seed(15)
+    g = synth.genome_family(1, 3000, seed=8)[0]
+    # identical sequences: one match spanning everything
+    got, _ = gpu_matches(ctx, [g, g], seed, mems.MODE_MEMHASH)
+    assert got == [(2, 3000, 1, 1)]
+    # a sequence and its reverse complement
+    got, _ = gpu_matches(ctx, [g, synth.revcomp(g)], seed, mems.MODE_MEMHASH)
+    assert got == canonical(orc.find_matches(0, [g, synth.revcomp(g)], seed)[0])
+    # nothing in common / too short / empty
+    h = synth.genome_family(1, 3000, seed=9)[0]
+    assert gpu_matches(ctx, [g, h], seed, mems.MODE_MEMHASH)[0] == canonical(orc.find_matches(0, [g, h], seed)[0])
+    assert gpu_matches(ctx, [g, b"ACGT", b""], seed, mems.MODE_MEMHASH)[0] == []
+    # different seeds are rejected like MatchFinder.cpp:190-199
+    a = ctx.create_sml(g, mems.get_seed(15))
+    b = ctx.create_sml(g, mems.get_seed(13))
+    with pytest.raises(mems.MemsError) as e:
+        ctx.find_matches([a, b])
+    assert e.value.code == 5
+
+
+def test_medium_size_vs_oracle(ctx, orc):
+    seed = mems.get_seed(15)
+    gs = synth.genome_family(4, 400_000, seed=123)
+    want, winfo = orc.find_matches(0, gs, seed)
+    got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
+    assert got == canonical(want)
+    assert info["n_hits"] == winfo["hits"]
