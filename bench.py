@@ -1,0 +1,279 @@
+#!/usr/bin/env python3
+"""bench.py — genome Mbp/s of the anchoring hot path (SML build + MemHash match find) on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic genomes: 2-bit pack, spaced-seed
+extraction, LSD radix sort of the seed union (SML build), then multi-MUM finding with ungapped
+extension.  Default workload = BASELINE.json configs[1]: 8 synthetic 5 Mbp genomes, weight-15
+palindromic spaced seed (progressiveMauve default), 1 GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|small]
+
+value  : Mbp/s with the ASCII genomes already resident in HBM when the timed region starts.
+e2e    : Mbp/s through the public C-ABI call with pinned HOST buffers (H2D of the genomes and D2H of the
+         MatchList inside the timed region).
+N > 1  : launched by torchrun, one rank per GPU.  This round every rank anchors its own independent
+         genome set (weak scaling, no data-path collective); the seed-range all-to-all is not built yet.
+--impl reference : times the UNMODIFIED reference (oracle/_ref, single-threaded MemorySML + MemHash) on
+         the host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (n_genomes, length, seed weight, mode, description)
+    "c1": (2, 5_000_000, 15, "memhash", "2 x 5 Mbp pairwise MUMs, w15 (BASELINE configs[0])"),
+    "c2": (8, 5_000_000, 15, "memhash", "8 x 5 Mbp multi-MUM, w15 palindromic spaced seed (BASELINE configs[1])"),
+    "c3": (1, 100_000_000, 19, "repeat", "1 x 100 Mbp RepeatHash, 200 families x 20 copies, w19 (BASELINE configs[2])"),
+    "small": (4, 200_000, 15, "memhash", "4 x 0.2 Mbp (debug)"),
+}
+# bounded CPU samples of each workload (about 10-30 s of single-thread reference work)
+CPU_SAMPLE = {"c1": (2, 2_000_000), "c2": (8, 500_000), "c3": (1, 10_000_000), "small": (4, 200_000)}
+REF_STEP_SAMPLE = {"c1": (2, 500_000), "c2": (8, 150_000), "c3": (1, 3_000_000), "small": (4, 100_000)}
+
+
+def make_genomes(name, n_genomes, length, seed):
+    from libmems_b200 import synth
+    if WORKLOADS[name][3] == "repeat":
+        fam = max(2, int(200 * length / 100_000_000))
+        return [synth.repeat_genome(length, seed=seed, families=fam, copies=20)]
+    return synth.genome_family(n_genomes, length, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, name):
+    """The reference's own CPU implementation (oracle/_ref) on a bounded sample, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from checkers import Reference
+    n_genomes, length, weight, mode, desc = WORKLOADS[name]
+    sg, sl = REF_STEP_SAMPLE[name]
+    line = {"impl": "reference", "metric": "genome Mbp/s (SML build + MemHash match find)", "unit": "Mbp/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "genomes": n_genomes, "genome_length": length, "seed_weight": weight}}
+    if not Reference.available():
+        line["unavailable"] = "oracle/_ref/libmems_ref.so not present (needs /root/reference at build time)"
+        print(json.dumps(line))
+        return
+    R = Reference()
+    seed = R.get_seed(weight)
+    gs = make_genomes(name, sg, sl, seed=2)
+    mbp = sum(len(g) for g in gs) / 1e6
+    m = 1 if mode == "repeat" else 0
+    for _ in range(args.warmup):
+        R.find_matches(m, gs, seed)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, info = R.find_matches(m, gs, seed)
+    dt = time.perf_counter() - t0
+    v = mbp * args.steps / dt
+    sample = "%d x %.2f Mbp per step (same generator and seed pattern as the full workload)" % (sg, sl / 1e6)
+    line.update({"value": v, "ms_per_step": 1e3 * dt / args.steps,
+                 "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "reference", "sample": sample,
+                                  "sml_s": info["sml_s"], "find_s": info["find_s"]},
+                 "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def cpu_baseline(name):
+    from checkers import Reference
+    n_genomes, length, weight, mode, desc = WORKLOADS[name]
+    if not Reference.available():
+        return {"value": None, "unit": "Mbp/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
+    R = Reference()
+    sg, sl = CPU_SAMPLE[name]
+    seed = R.get_seed(weight)
+    gs = make_genomes(name, sg, sl, seed=2)
+    t0 = time.perf_counter()
+    _, info = R.find_matches(1 if mode == "repeat" else 0, gs, seed)
+    dt = time.perf_counter() - t0
+    mbp = sum(len(g) for g in gs) / 1e6
+    return {"value": mbp / dt, "unit": "Mbp/s", "cores": 1, "kind": "reference",
+            "sample": "%d x %.2f Mbp of the same synthetic family (one pass)" % (sg, sl / 1e6),
+            "sml_build_mbp_s": mbp / info["sml_s"], "sml_s": info["sml_s"], "find_s": info["find_s"],
+            "host_cores_available": os.cpu_count()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    name = args.workload
+    if args.impl == "reference":
+        return run_reference(args, name)
+
+    import torch
+    import libmems_b200 as mems
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_genomes, length, weight, mode, desc = WORKLOADS[name]
+    seed = mems.get_seed(weight)
+    match_mode = mems.MODE_REPEAT if mode == "repeat" else mems.MODE_MEMHASH
+    gs = make_genomes(name, n_genomes, length, seed=2 + rank)  # every rank anchors its own genome set
+    mbp_rank = sum(len(g) for g in gs) / 1e6
+    host = [torch.from_numpy(g).pin_memory() for g in gs]
+    dev = [h.cuda(non_blocking=False) for h in host]
+    stream = torch.cuda.Stream()
+    ctx = mems.Context(local_rank, stream=stream.cuda_stream)
+
+    def step(bufs):
+        smls = ctx.create_smls([(b.data_ptr(), b.numel()) for b in bufs], seed)
+        flat, info = ctx.find_matches(smls, mode=match_mode)
+        for s in smls:
+            s.close()
+        return flat, info
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(bufs, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        info = None
+        for _ in range(steps):
+            flat, info = step(bufs)
+        b.record(stream)
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, flat, info
+
+    for _ in range(args.warmup):
+        step(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    ms_dev, flat, info = timed(dev, args.steps)
+    prof = ctx.profile()
+    launches = ctx.launch_count()
+    ctx.profile_enable(False)
+    for _ in range(2):
+        step(host)
+    ms_e2e, flat_h, info_h = timed(host, args.steps)
+    clocks = sampler.stop()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        kernels = {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                       "share": v["ms"] / total_ms,
+                       "gbs": (v["bytes"] / v["ms"] / 1e6) if v["ms"] > 0 and v["bytes"] > 0 else None}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        # dominant kernel = largest share of device time among the launches of the timed region
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        hbm_kernels = {k: v for k, v in prof.items() if v["bytes"] > 0}
+        roof_name, roof = max(hbm_kernels.items(), key=lambda kv: kv[1]["ms"])
+        achieved = roof["bytes"] / roof["ms"] / 1e6
+        roofline = {"bound": "hbm", "kernel": roof_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                    "launches": roof["launches"], "avg_launch_ms": roof["ms"] / max(roof["launches"], 1),
+                    "dominant_kernel_by_time": top[0]}
+        mbp_total = mbp_rank * world
+        line = {
+            "metric": "genome Mbp/s (SML build + MemHash match find)",
+            "value": mbp_total * args.steps / (ms_dev / 1e3), "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32" if 2 * weight + 1 <= 32 else "u64", "data": "synthetic",
+            "config": {"workload": desc, "genomes": n_genomes, "genome_length": length, "seed_weight": weight,
+                       "seed_pattern": hex(seed), "multi_gpu": "independent genome sets per rank" if world > 1 else "n/a",
+                       "l2": "per-step working set (%.0f MB of seed records) exceeds the 126 MB L2" %
+                             (sum(len(g) for g in gs) * (8 if 2 * weight + 1 <= 32 else 12) / 1e6)},
+            "e2e": {"value": mbp_total * args.steps / (ms_e2e / 1e3), "unit": "Mbp/s",
+                    "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(sum(len(g) for g in gs)),
+                    "d2h_bytes_per_step": int(len(flat_h) * 8 + 64)},
+            "gpu_launches": launches, "matches_per_step": info["n_matches"], "hits_per_step": info["n_hits"],
+            "matches_per_s": info["n_matches"] * world * args.steps / (ms_dev / 1e3),
+            "roofline": roofline, "kernels": kernels, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(name)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

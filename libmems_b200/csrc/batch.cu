@@ -96,7 +96,8 @@ std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_se
 	MEMS_CUDA(cudaMemsetAsync(gap_flag.p, 0, sizeof(uint32_t), c->stream));
 	for (int g = 0; g < n_seqs; ++g)
 		if (lens[g])
-			MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyHostToDevice, c->stream));
+			// cudaMemcpyDefault: seqs[g] may be pageable or pinned host memory, or already a device pointer
+			MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyDefault, c->stream));
 	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
 	extract_and_sort(*b);
 	uint32_t gap = 0;
