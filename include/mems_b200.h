@@ -32,9 +32,10 @@ extern "C" {
 #define MEMS_MODE_PAIRWISE 2  /* PairwiseMatchFinder::FindMatches (PairwiseMatchFinder.cpp:37-71) */
 
 /* output ordering of a match list */
-#define MEMS_ORDER_CANONICAL 0 /* distinct matches sorted by (SeqCount, Length, Start(0..)) */
+#define MEMS_ORDER_ANY 0       /* distinct matches in device order (deterministic, unspecified) — fastest */
 #define MEMS_ORDER_REFERENCE 1 /* the reference's hash-table order incl. its collision drops
                                   (MemHash.cpp:209-251, MemHash.h:183-203); always used for RepeatHash */
+#define MEMS_ORDER_CANONICAL 2 /* distinct matches sorted by (SeqCount, Length, Start(0..)) on the host */
 
 #define MEMS_MAX_SEQS 64           /* sequences per FindMatches call */
 #define MEMS_MER_REPEAT_LIMIT 1000 /* MatchFinder.cpp:166 — larger seed runs are outside the parity contract */
@@ -113,6 +114,7 @@ typedef struct {
 	uint64_t mem_count;   /* MemHash::MemCount()          (ORDER_REFERENCE only, else == n_matches) */
 	uint64_t collisions;  /* MemHash::MemCollisionCount() (ORDER_REFERENCE only, else n_hits - n_matches) */
 	uint64_t max_run;     /* largest equal-seed run seen; > MEMS_MER_REPEAT_LIMIT voids parity */
+	uint64_t n_segments;  /* groups of hits connected without a window test (extension work items) */
 	uint32_t seq_count;   /* sequences searched */
 	uint32_t seed_length;
 } mems_matches_info_t;

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmems_b200.so")
 
 MODE_MEMHASH, MODE_REPEAT, MODE_PAIRWISE = 0, 1, 2
-ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
+ORDER_ANY, ORDER_REFERENCE, ORDER_CANONICAL = 0, 1, 2
 
 _u64 = ctypes.c_uint64
 _vp = ctypes.c_void_p
@@ -39,7 +39,7 @@ class MatchParams(ctypes.Structure):
 
 class MatchesInfo(ctypes.Structure):
     _fields_ = [("n_matches", _u64), ("n_flat", _u64), ("n_hits", _u64), ("mem_count", _u64), ("collisions", _u64),
-                ("max_run", _u64), ("seq_count", ctypes.c_uint32), ("seed_length", ctypes.c_uint32)]
+                ("max_run", _u64), ("n_segments", _u64), ("seq_count", ctypes.c_uint32), ("seed_length", ctypes.c_uint32)]
 
 
 class ProfileEntry(ctypes.Structure):
@@ -182,7 +182,7 @@ class Context:
         return [SortedMerList(self, _vp(out[i])) for i in range(n)]
 
     # -- match finding --------------------------------------------------------------------------------
-    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_CANONICAL, table_size=0):
+    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0):
         """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches.  Returns (matches, info) where
         matches is a list of tuples (SeqCount, Length, Start(0), ...)."""
         n = len(smls)

@@ -57,15 +57,17 @@ static void extract_and_sort(Batch& b) {
 	const size_t key_bytes = b.key64 ? 8 : 4;
 	const uint64_t n = b.n_total;
 	SortPlan plan = make_sort_plan(b.sd.key_bits);
-	DevBuf<uint8_t> keys_a(c, n * key_bytes), keys_b(c, n * key_bytes);
+	// extraction output stays resident in position order: the window test of match extension reads it
+	DevBuf<uint8_t> keys_pos(c, n * key_bytes), keys_a(c, n * key_bytes), keys_b(c, n * key_bytes);
 	DevBuf<uint32_t> vals_a(c, n), vals_b(c, n);
 	DevBuf<uint32_t> hist(c, (size_t)plan.n_passes * 256);
 	MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)plan.n_passes * 256 * sizeof(uint32_t), c->stream));
-	launch_extract(c, b.packed.p, b.d_meta.p, b.meta.data(), b.n_seqs, b.sd, b.pos_bits, b.key64, keys_a.p, vals_a.p,
+	launch_extract(c, b.packed.p, b.d_meta.p, b.meta.data(), b.n_seqs, b.sd, b.pos_bits, b.key64, keys_pos.p, vals_a.p,
 	               hist.p, plan.n_passes, plan.shift, plan.bits);
 	void* kp[2] = {keys_a.p, keys_b.p};
 	uint32_t* vp[2] = {vals_a.p, vals_b.p};
-	int r = radix_sort_pairs(c, b.key64, kp, vp, n, plan, hist.p, "radix_pass");
+	int r = radix_sort_pairs(c, b.key64, kp, vp, n, plan, hist.p, "radix_pass", keys_pos.p);
+	b.keys_by_pos = std::move(keys_pos);
 	if (r == 0) {
 		b.keys = std::move(keys_a);
 		b.vals = std::move(vals_a);

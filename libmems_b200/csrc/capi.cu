@@ -266,6 +266,7 @@ int mems_matches_info(mems_matches_t m, mems_matches_info_t* out) {
 	out->mem_count = m->r.mem_count;
 	out->collisions = m->r.collisions;
 	out->max_run = m->r.max_run;
+	out->n_segments = m->r.n_segments;
 	out->seq_count = m->r.seq_count;
 	out->seed_length = m->r.seed_length;
 	return MEMS_OK;

@@ -147,9 +147,10 @@ SortPlan make_sort_plan(int key_bits, int begin_bit = 0);
 size_t radix_max_items();  // largest n one sort call accepts
 // Stable LSD radix sort of (key, u32 value) pairs over plan's digits.  keys/vals are double buffers;
 // d_hist holds n_passes x 256 digit counts of the input (computed by the caller, e.g. fused in extraction).
-// Returns 0 or 1: the index of the buffer pair that holds the sorted result.
+// Returns 0 or 1: the index of the buffer pair that holds the sorted result.  If first_keys_in is given, the
+// first pass reads its keys from there (and leaves that array untouched) instead of d_keys[0].
 int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], uint64_t n, const SortPlan& plan,
-                     uint32_t* d_hist, const char* prof_name);
+                     uint32_t* d_hist, const char* prof_name, const void* first_keys_in = nullptr);
 // standalone digit histograms of a key array (for inputs not produced by launch_extract)
 void launch_histogram(Ctx* c, bool key64, const void* d_keys, uint64_t n, const SortPlan& plan, uint32_t* d_hist);
 // exclusive prefix sum of n u32 values (in -> out, may alias); *d_total (optional, device) gets the sum
@@ -170,6 +171,7 @@ struct Batch {
 	std::vector<SeqMeta> meta;
 	DevBuf<SeqMeta> d_meta;
 	DevBuf<uint32_t> packed;
+	DevBuf<uint8_t> keys_by_pos;  // compact key of every seed position, in (seq, position) order (extraction output)
 	DevBuf<uint8_t> keys;      // union, ascending compact key (u32 or u64); ties in (seq, position) order
 	DevBuf<uint32_t> vals;     // union, (seq << pos_bits) | position
 	DevBuf<uint32_t> positions;  // per sequence: slice [seed_off, +n_seeds) sorted by key, still tagged
@@ -188,7 +190,7 @@ std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const s
 // ---- kernels_match.cu ----
 struct MatchResult {
 	std::vector<int64_t> flat;  // [SeqCount, Length, starts...] per match
-	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0;
+	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0, n_segments = 0;
 	uint32_t seq_count = 0, seed_length = 0;
 };
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out);

@@ -15,13 +15,16 @@
 //                     offsets) -> sort key (diagonal hash | first-member position)
 //   3. sort         — hits by that key (radix_sort.cu): hits of one diagonal become contiguous, by position
 //   4. segments     — neighbours on the same diagonal <= L apart are connected without looking at sequence
-//   5. extend       — one warp per segment walks left/right with the window test (lane d tests the window
-//                     d positions away; ballot picks the farthest), hopping over later segments of the
-//                     same diagonal; a segment that reaches its predecessor is absorbed by it
-//   6. emit         — surviving components -> [SeqCount, Length, starts] records
+//   5. extend       — one warp per segment walks RIGHT from its last hit with the window test (lane d tests
+//                     the window d positions away; ballot picks the farthest) until it reaches the next
+//                     segment of its diagonal (link) or fails (component end); chains of linked segments
+//                     are the components, and only each chain's first segment walks LEFT
+//   6. emit         — components -> [SeqCount, Length, starts] records
 // Hash collisions between diagonals only split segments (more window tests), never merge them: every
 // merge decision compares the full member lists.
 #include <algorithm>
+#include <cstdio>
+#include <cstring>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -243,7 +246,7 @@ template <class KeyT>
 __global__ void __launch_bounds__(256)
 segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
                     const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
-                    uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head) {
+                    uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head, uint32_t* __restrict__ collision_seen) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_hits) return;
 	uint8_t f = kFlagHead;
@@ -256,6 +259,8 @@ segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const
 				f = kFlagSameDiag;
 				const uint64_t gap = (k & a.pos_mask) - (kp & a.pos_mask);
 				if (gap > (uint64_t)L) f |= kFlagHead;
+			} else {
+				atomicOr(collision_seen, 1u);  // two diagonals in one hash bucket (rare): duplicates become possible
 			}
 		}
 	}
@@ -270,126 +275,411 @@ __global__ void segment_compact_kernel(const uint32_t* __restrict__ is_head, con
 }
 
 // ------------------------------------------------------------------------------------------------ 5. extend
-// The window test of MatchFinder::ExtendMatch (MatchFinder.h:264-308) for the window k positions from the
+// The window test of MatchFinder::ExtendMatch (MatchFinder.h:264-308) for the window k positions from a
 // hit (k < 0: towards the first member's start): every member's seed position must be valid, all masked
-// keys equal, and all (strand xor orientation) parities equal.
+// keys equal, and all (strand xor orientation) parities equal.  The reference recomputes two spaced-seed
+// mers per member and window (GetSeedMer, ~84 ns each); here the canonical key of every position is
+// already resident from extraction (Batch::keys_by_pos), so a member costs one 4/8-byte load:
+//     tagged(member, k) = keys_by_pos[base + (reverse ? -k : +k)] ^ reverse
+// and the window matches iff all tagged values are equal.  Position validity collapses to one interval
+// [kmin, kmax] per hit (intersection of the members' valid ranges).
+constexpr int kExtendWarps = 4;
+constexpr int kMemberTile = 64;  // members staged in shared memory per warp (MEMS_MAX_SEQS fits at once)
+constexpr uint32_t kReverseBit = 0x80000000u;
+constexpr int kWarpProbeBudget = 16;  // probes (of 128 windows) a single warp spends on one walk before deferring
+
 template <class KeyT>
-__device__ bool window_matches(const MatchArgs& a, const SeedDesc& sd, uint32_t s, uint32_t len, uint32_t sf, int64_t k) {
-	uint64_t ref = 0;
-	bool have = false;
-	for (uint32_t j = s; j < s + len; ++j) {
+struct WarpHit {
+	const MatchArgs& a;
+	const KeyT* key_pos;
+	uint32_t* s_mem;  // this warp's kMemberTile slots: (seed_off + pos) | reverse << 31
+	uint32_t s, len, sf;
+	int64_t kmin, kmax;
+	int lane;
+#ifdef MEMS_WALK_STATS
+	uint32_t n_probes = 0;
+#endif
+
+	__device__ uint32_t member_entry(uint32_t j, int64_t& lo, int64_t& hi) const {
 		const uint32_t val = a.vals[j];
 		const uint32_t o = strand_of<KeyT>(a.keys, j) ^ sf;
-		const uint32_t seq = val >> a.pos_bits;
-		const int64_t p = val & a.pos_mask;
-		const int64_t q = o ? p - k : p + k;
-		const SeqMeta m = a.meta[seq];
-		if (q < 0 || q >= (int64_t)m.n_seeds) return false;
-		const uint64_t ck = canonical_key(extract_fwd(window64(a.packed + m.word_off, (uint32_t)q), sd), sd.w);
-		const uint64_t tagged = ck ^ (uint64_t)o;  // flips the strand bit for reverse members
-		if (!have) {
-			ref = tagged;
-			have = true;
-		} else if (tagged != ref)
-			return false;
+		const SeqMeta m = a.meta[val >> a.pos_bits];
+		const int64_t p = val & a.pos_mask, last = (int64_t)m.n_seeds - 1;
+		lo = o ? p - last : -p;
+		hi = o ? p : last - p;
+		return ((uint32_t)m.seed_off + (uint32_t)p) | (o ? kReverseBit : 0u);
 	}
-	return true;
-}
+	__device__ void load_tile(uint32_t first) {
+		for (uint32_t t = lane; t < kMemberTile && first + t < len; t += 32) {
+			int64_t lo, hi;
+			s_mem[t] = member_entry(s + first + t, lo, hi);
+		}
+		__syncwarp();
+	}
+	__device__ void init(uint32_t hit_s, uint32_t hit_len, uint32_t first_strand) {
+		s = hit_s;
+		len = hit_len;
+		sf = first_strand;
+		int64_t lo = INT64_MIN, hi = INT64_MAX;
+		for (uint32_t t = lane; t < len; t += 32) {
+			int64_t l2, h2;
+			member_entry(s + t, l2, h2);
+			lo = l2 > lo ? l2 : lo;
+			hi = h2 < hi ? h2 : hi;
+		}
+		for (int o = 16; o; o >>= 1) {
+			int64_t l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+			lo = l2 > lo ? l2 : lo;
+			hi = h2 < hi ? h2 : hi;
+		}
+		kmin = lo;
+		kmax = hi;
+		load_tile(0);
+	}
+	__device__ uint64_t tagged(uint32_t e, int64_t k) const {
+		const uint32_t rev = e >> 31;
+		const int64_t idx = (int64_t)(e & ~kReverseBit) + (rev ? -k : k);
+		return (uint64_t)key_pos[idx] ^ (uint64_t)rev;
+	}
+	// Probe the kProbe windows at distances 1..kProbe from k0 in direction dir (+1/-1): lane l tests distances
+	// l+1, l+33, l+65, l+97.  All loads of one member are independent (no early exit inside a lane), so a probe
+	// costs about one memory round trip per member instead of one per member and window.  Returns the match
+	// bits, bit i = distance i+1, identical in every lane.
+	__device__ void probe(int64_t k0, int dir, uint64_t& m_lo, uint64_t& m_hi) {
+		int64_t kk[4];
+		bool ok[4];
+		uint64_t ref[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			kk[j] = k0 + (int64_t)dir * (lane + 32 * j + 1);
+			ok[j] = kk[j] >= kmin && kk[j] <= kmax;
+			if (!ok[j]) kk[j] = 0;  // window 0 is the hit itself, always valid: keeps the loads in range
+		}
+		for (uint32_t first = 0; first < len; first += kMemberTile) {
+			if (first) load_tile(first);
+			const uint32_t cnt = len - first < kMemberTile ? len - first : kMemberTile;
+			for (uint32_t t = 0; t < cnt; ++t) {
+				const uint32_t e = s_mem[t];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint64_t v = tagged(e, kk[j]);
+					if (first == 0 && t == 0) ref[j] = v;
+					else ok[j] = ok[j] && v == ref[j];
+				}
+				// whole-warp early exit, checked every 8 members so the loads in between stay independent
+				if ((t & 7) == 7 && !__any_sync(0xffffffffu, ok[0] | ok[1] | ok[2] | ok[3])) {
+					t = cnt;
+					first = len;
+				}
+			}
+			if (len > kMemberTile) __syncwarp();
+		}
+		if (len > kMemberTile) load_tile(0);
+		const uint32_t b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
+		const uint32_t b2 = __ballot_sync(0xffffffffu, ok[2]), b3 = __ballot_sync(0xffffffffu, ok[3]);
+		m_lo = ((uint64_t)b1 << 32) | b0;
+		m_hi = ((uint64_t)b3 << 32) | b2;
+	}
+	// Walk from window k0 in direction dir over matching windows that start <= L apart, as far as they go
+	// (the closure loop of MatchFinder::ExtendMatch, MatchFinder.h:259-355).  If stop_dist >= 0 the walk ends as
+	// soon as it stands within L of that distance (the next segment of the diagonal) and *linked is set.
+	// Returns the distance walked.  After max_probes probes the walk gives up with *exhausted set: such
+	// walks (a handful per genome set, but up to hundreds of kbp long) are finished by whole CTAs, see cta_walk.
+	__device__ int64_t walk(int64_t k0, int dir, int L, int64_t stop_dist, bool* linked, int max_probes, bool* exhausted) {
+		int64_t walked = 0;
+		*linked = false;
+		*exhausted = false;
+		for (int n = 0;; ++n) {
+			if (stop_dist >= 0 && stop_dist <= walked + L) {
+				*linked = true;
+				return walked;
+			}
+			if (n == max_probes) {
+				*exhausted = true;
+				return walked;
+			}
+			uint64_t m_lo, m_hi;
+			probe(k0 + dir * walked, dir, m_lo, m_hi);
+#ifdef MEMS_WALK_STATS
+			++n_probes;
+#endif
+			int pos = 0;  // distance reached inside this probe
+			while (true) {
+				if (stop_dist >= 0 && stop_dist <= walked + pos + L) {
+					*linked = true;
+					return walked + pos;
+				}
+				const int limit = pos + L < kProbe ? pos + L : kProbe;
+				const int best = highest_set_in(m_lo, m_hi, pos, limit);  // farthest match in (pos, limit]
+				if (best) {
+					pos = best;
+					continue;
+				}
+				if (pos + L <= kProbe) return walked + pos;  // a full L-window without a match: the chain ends here
+				break;  // the rest of the L-window lies beyond this probe
+			}
+			walked += pos;
+		}
+	}
+	static constexpr int kProbe = 128;
+	// highest distance d in (a, b] whose bit (d-1) is set, 0 if none; 0 <= a < b <= 128
+	__device__ static int highest_set_in(uint64_t lo, uint64_t hi, int a, int b) {
+		if (b > 64) {
+			const int from = a > 64 ? a - 64 : 0, to = b - 64;  // bits [from, to) of hi
+			uint64_t w = hi;
+			if (to < 64) w &= (1ull << to) - 1ull;
+			w = from < 64 ? (w >> from) << from : 0ull;
+			if (w) return 64 + 64 - __clzll(w);
+		}
+		if (a < 64) {
+			const int to = b < 64 ? b : 64;  // bits [a, to) of lo
+			uint64_t w = lo;
+			if (to < 64) w &= (1ull << to) - 1ull;
+			w = (w >> a) << a;
+			if (w) return 64 - __clzll(w);
+		}
+		return 0;
+	}
+};
 
-constexpr int kExtendWarps = 4;
+#ifdef MEMS_WALK_STATS
+__device__ unsigned long long g_walk_stats[16];  // [0] probes total, [1] max per walk, [2+i] walks with 2^i probes
+#endif
 
+struct SegView {
+	const uint64_t* hkey;
+	const uint32_t* hid;
+	const uint32_t* hit_start;
+	const uint16_t* hit_len;
+	const uint8_t* flags;
+	const uint32_t* seg_head;
+	uint32_t n_hits, n_seg;
+};
+
+// Right walk of every segment: from its last hit, follow matching windows until either the next segment of
+// the same diagonal is within reach (link = 1: the two are connected, its own walk continues from there) or
+// no window within L matches (link = 0: reach = last matching window, the component's right end).
 template <class KeyT>
 __global__ void __launch_bounds__(kExtendWarps * 32)
-extend_kernel(MatchArgs a, SeedDesc sd, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
-              const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
-              const uint8_t* __restrict__ flags, const uint32_t* __restrict__ seg_head, uint32_t n_seg,
-              int32_t* __restrict__ seg_kl, int32_t* __restrict__ seg_kr, uint32_t* __restrict__ seg_emit) {
+walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, uint32_t* __restrict__ seg_link,
+                  uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
+	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
 	const uint32_t seg = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
-	if (seg >= n_seg) return;
+	if (seg >= v.n_seg) return;
+	const uint32_t hi = v.seg_head[seg];
+	const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
+	const uint32_t h = v.hid[hi];
+	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
+	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
+	int64_t c = (int64_t)(v.hkey[end - 1] & a.pos_mask) - x0;
+	const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
+	const int64_t next_at = has_next ? (int64_t)(v.hkey[end] & a.pos_mask) - x0 : 0;
+	bool linked, exhausted;
+	c += w.walk(c, +1, L, has_next ? next_at - c : -1, &linked, kWarpProbeBudget, &exhausted);
+	if (exhausted) {  // hand the rest of this walk to a whole CTA (long_walk_kernel)
+		if (w.lane == 0) {
+			const uint32_t at = atomicAdd(defer_count, 1u);
+			defer[at] = make_uint2(seg, (uint32_t)(int32_t)c);
+		}
+		return;
+	}
+	const uint32_t link = linked ? 1u : 0u;
+#ifdef MEMS_WALK_STATS
+	if (w.lane == 0) {
+		atomicAdd(&g_walk_stats[0], (unsigned long long)w.n_probes);
+		atomicMax(&g_walk_stats[1], (unsigned long long)w.n_probes);
+		atomicAdd(&g_walk_stats[2 + min(31 - __clz(w.n_probes | 1), 13)], 1ull);
+	}
+#endif
+	if (w.lane == 0) {
+		seg_link[seg] = link;
+		seg_reach[seg] = (uint32_t)(x0 + c);
+	}
+}
+
+// a segment starts a component unless its predecessor linked to it
+__global__ void chain_first_kernel(const uint32_t* __restrict__ seg_link, uint32_t n_seg, uint32_t* __restrict__ first) {
+	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg < n_seg) first[seg] = (seg == 0 || !seg_link[seg - 1]) ? 1u : 0u;
+}
+
+// Left walk of every component's first segment, and scatter of both component ends.
+template <class KeyT>
+__global__ void __launch_bounds__(kExtendWarps * 32)
+walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint32_t* __restrict__ seg_link,
+                 const uint32_t* __restrict__ seg_reach, const uint32_t* __restrict__ first,
+                 const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
+                 uint32_t* __restrict__ comp_right, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
+	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
+	const uint32_t seg = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
+	if (seg >= v.n_seg) return;
 	const int lane = threadIdx.x & 31;
-	const int L = sd.L;
-	const uint32_t hi = seg_head[seg];
+	const bool is_first = first[seg] != 0;
+	const uint32_t comp = first_excl[seg] - (is_first ? 0u : 1u);
+	if (!seg_link[seg] && lane == 0) comp_right[comp] = seg_reach[seg];
+	if (!is_first) return;
+	const uint32_t hi = v.seg_head[seg];
+	const uint32_t h = v.hid[hi];
+	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
+	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, lane};
+	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
+	bool linked, exhausted;
+	const int64_t c = -w.walk(0, -1, L, -1, &linked, kWarpProbeBudget, &exhausted);
+	if (lane == 0) comp_rep[comp] = hi;
+	if (exhausted) {
+		if (lane == 0) {
+			const uint32_t at = atomicAdd(defer_count, 1u);
+			defer[at] = make_uint2(seg, (uint32_t)(int32_t)c);
+		}
+		return;
+	}
+	if (lane == 0) {
+		comp_left[comp] = (uint32_t)(x0 + c);
+	}
+}
+
+// ---- long walks -------------------------------------------------------------------------------------
+// A diagonal shared by few sequences has few hits but can match for hundreds of kbp (the sequences agree
+// wherever the others carry a SNP), so a handful of walks are 10^3-10^4 probes long: as one warp each they
+// would be the critical path of the whole call.  Walks that exhaust their warp budget are finished here by
+// a 32-warp CTA: every round the warps probe 32 x 128 consecutive windows at once, each summarises its 128
+// bits (first match, end of the chain that starts there, last match) and thread 0 stitches the summaries.
+constexpr int kLongWarps = 32;
+constexpr int kLongSpan = kLongWarps * 128;
+
+template <class KeyT>
+__device__ int64_t cta_walk(WarpHit<KeyT>& w, int64_t k0, int dir, int L, int64_t stop_dist, bool* linked, int4* s_sum,
+                            int64_t* s_result) {
+	const int warp = threadIdx.x >> 5;
+	int64_t walked = 0;
+	while (true) {
+		uint64_t m_lo, m_hi;
+		w.probe(k0 + dir * (walked + 128 * warp), dir, m_lo, m_hi);
+		// summary of this warp's 128 windows (distances 1..128 from its own base)
+		int first = 0, chain_end = 0, last = 0;
+		if (m_lo | m_hi) {
+			first = m_lo ? __ffsll((long long)m_lo) : 64 + __ffsll((long long)m_hi);
+			last = m_hi ? 128 - __clzll(m_hi) : 64 - __clzll(m_lo);
+			chain_end = first;
+			while (true) {
+				const int limit = chain_end + L < 128 ? chain_end + L : 128;
+				const int best = WarpHit<KeyT>::highest_set_in(m_lo, m_hi, chain_end, limit);
+				if (!best) break;
+				chain_end = best;
+			}
+		}
+		if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			int64_t cur = 0;  // last confirmed match, as a distance from this round's base
+			int state = 0;    // 0 = ran through the whole span, 1 = chain ended, 2 = linked
+			for (int i = 0; i < kLongWarps && state == 0; ++i) {
+				if (stop_dist >= 0 && stop_dist <= walked + cur + L) state = 2;
+				const int4 sm = s_sum[i];
+				if (state || !sm.x) continue;
+				if (128 * i + sm.x - cur > L) {
+					state = 1;
+				} else {
+					cur = 128 * i + sm.y;
+					if (stop_dist >= 0 && stop_dist <= walked + cur + L) state = 2;
+					else if (sm.y != sm.z) state = 1;  // a gap > L inside this warp's windows
+				}
+			}
+			if (state == 0 && stop_dist >= 0 && stop_dist <= walked + cur + L) state = 2;
+			if (state == 0 && kLongSpan - cur >= L) state = 1;  // a full L-window without a match
+			s_result[0] = cur;
+			s_result[1] = state;
+		}
+		__syncthreads();
+		walked += s_result[0];
+		const int64_t state = s_result[1];
+		__syncthreads();
+		if (state) {
+			*linked = state == 2;
+			return walked;
+		}
+	}
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(kLongWarps * 32, 1)
+long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ defer,
+                       const uint32_t* __restrict__ defer_count, uint32_t* __restrict__ seg_link,
+                       uint32_t* __restrict__ seg_reach) {
+	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
+	__shared__ int4 s_sum[kLongWarps];
+	__shared__ int64_t s_result[2];
+	const uint32_t n_defer = *defer_count;
+	for (uint32_t i = blockIdx.x; i < n_defer; i += gridDim.x) {
+		const uint32_t seg = defer[i].x;
+		int64_t c = (int32_t)defer[i].y;
+		const uint32_t hi = v.seg_head[seg];
+		const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
+		const uint32_t h = v.hid[hi];
+		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
+		WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
+		const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
+		const int64_t next_at = has_next ? (int64_t)(v.hkey[end] & a.pos_mask) - x0 : 0;
+		bool linked;
+		c += cta_walk<KeyT>(w, c, +1, L, has_next ? next_at - c : -1, &linked, s_sum, s_result);
+		if (threadIdx.x == 0) {
+			seg_link[seg] = linked ? 1u : 0u;
+			seg_reach[seg] = (uint32_t)(x0 + c);
+		}
+	}
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(kLongWarps * 32, 1)
+long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ defer,
+                      const uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ first_excl,
+                      uint32_t* __restrict__ comp_left) {
+	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
+	__shared__ int4 s_sum[kLongWarps];
+	__shared__ int64_t s_result[2];
+	const uint32_t n_defer = *defer_count;
+	for (uint32_t i = blockIdx.x; i < n_defer; i += gridDim.x) {
+		const uint32_t seg = defer[i].x;  // always the first segment of its component
+		int64_t c = (int32_t)defer[i].y;
+		const uint32_t hi = v.seg_head[seg];
+		const uint32_t h = v.hid[hi];
+		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
+		WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
+		bool linked;
+		c -= cta_walk<KeyT>(w, c, -1, L, -1, &linked, s_sum, s_result);
+		if (threadIdx.x == 0) comp_left[first_excl[seg]] = (uint32_t)(x0 + c);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ 6. emit
+__global__ void emit_size_kernel(const uint32_t* __restrict__ comp_rep, const uint32_t* __restrict__ hid,
+                                 const uint16_t* __restrict__ hit_len, uint32_t n_comp, int mode, int n_seqs,
+                                 uint32_t* __restrict__ rec_size) {
+	const uint32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (comp >= n_comp) return;
+	const uint32_t len = hit_len[hid[comp_rep[comp]]] & ~kFirstStrandBit;
+	rec_size[comp] = 2u + (mode == MEMS_MODE_REPEAT ? len : (uint32_t)n_seqs);
+}
+
+template <class KeyT>
+__global__ void emit_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
+                            const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len,
+                            const uint32_t* __restrict__ comp_rep, const uint32_t* __restrict__ comp_left,
+                            const uint32_t* __restrict__ comp_right, const uint32_t* __restrict__ rec_off, uint32_t n_comp,
+                            int64_t* __restrict__ flat) {
+	const uint32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (comp >= n_comp) return;
+	const uint32_t hi = comp_rep[comp];
 	const uint32_t h = hid[hi];
 	const uint32_t s = hit_start[h];
 	const uint32_t len = hit_len[h] & ~kFirstStrandBit;
 	const uint32_t sf = (hit_len[h] & kFirstStrandBit) ? 1u : 0u;
 	const int64_t x0 = (int64_t)(hkey[hi] & a.pos_mask);
-	const int d = lane + 1;  // lanes 0..L-1 probe distances 1..L
-
-	// ---- left
-	int64_t kl = 0;
-	bool absorbed = false;
-	const bool prev_same = (flags[hi] & kFlagSameDiag) != 0;
-	const int64_t absorb_at = prev_same ? (int64_t)(hkey[hi - 1] & a.pos_mask) - x0 + L : 0;
-	while (true) {
-		bool ok = d <= L && window_matches<KeyT>(a, sd, s, len, sf, kl - d);
-		uint32_t b = __ballot_sync(0xffffffffu, ok);
-		if (!b) break;
-		kl -= 32 - __clz(b);
-		if (prev_same && kl <= absorb_at) {
-			absorbed = true;
-			break;
-		}
-	}
-	// ---- right
-	int64_t c = 0;
-	if (!absorbed) {
-		uint32_t cur = seg;
-		uint32_t end = cur + 1 < n_seg ? seg_head[cur + 1] : n_hits;
-		c = (int64_t)(hkey[end - 1] & a.pos_mask) - x0;
-		while (true) {
-			if (cur + 1 < n_seg) {
-				const uint32_t nh = seg_head[cur + 1];
-				if ((flags[nh] & kFlagSameDiag) && (int64_t)(hkey[nh] & a.pos_mask) - x0 <= c + L) {
-					// the next segment of this diagonal starts within reach: everything up to its last hit is connected
-					++cur;
-					end = cur + 1 < n_seg ? seg_head[cur + 1] : n_hits;
-					const int64_t t = (int64_t)(hkey[end - 1] & a.pos_mask) - x0;
-					if (t > c) c = t;
-					continue;
-				}
-			}
-			bool ok = d <= L && window_matches<KeyT>(a, sd, s, len, sf, c + d);
-			uint32_t b = __ballot_sync(0xffffffffu, ok);
-			if (!b) break;
-			c += 32 - __clz(b);
-		}
-	}
-	if (lane == 0) {
-		seg_kl[seg] = (int32_t)kl;
-		seg_kr[seg] = (int32_t)c;
-		seg_emit[seg] = absorbed ? 0u : 1u;
-	}
-}
-
-// ------------------------------------------------------------------------------------------------ 6. emit
-__global__ void emit_size_kernel(const uint32_t* __restrict__ seg_emit, const uint32_t* __restrict__ seg_head,
-                                 const uint32_t* __restrict__ hid, const uint16_t* __restrict__ hit_len, uint32_t n_seg,
-                                 int mode, int n_seqs, uint32_t* __restrict__ rec_size) {
-	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
-	if (seg >= n_seg) return;
-	uint32_t sz = 0;
-	if (seg_emit[seg]) {
-		const uint32_t len = hit_len[hid[seg_head[seg]]] & ~kFirstStrandBit;
-		sz = 2u + (mode == MEMS_MODE_REPEAT ? len : (uint32_t)n_seqs);
-	}
-	rec_size[seg] = sz;
-}
-
-template <class KeyT>
-__global__ void emit_kernel(MatchArgs a, int L, const uint32_t* __restrict__ seg_emit, const uint32_t* __restrict__ seg_head,
-                            const uint32_t* __restrict__ hid, const uint32_t* __restrict__ hit_start,
-                            const uint16_t* __restrict__ hit_len, const int32_t* __restrict__ seg_kl,
-                            const int32_t* __restrict__ seg_kr, const uint32_t* __restrict__ rec_off, uint32_t n_seg,
-                            int64_t* __restrict__ flat) {
-	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
-	if (seg >= n_seg || !seg_emit[seg]) return;
-	const uint32_t h = hid[seg_head[seg]];
-	const uint32_t s = hit_start[h];
-	const uint32_t len = hit_len[h] & ~kFirstStrandBit;
-	const uint32_t sf = (hit_len[h] & kFirstStrandBit) ? 1u : 0u;
-	const int64_t kl = seg_kl[seg], kr = seg_kr[seg];
-	int64_t* rec = flat + rec_off[seg];
+	const int64_t kl = (int64_t)comp_left[comp] - x0, kr = (int64_t)comp_right[comp] - x0;
+	int64_t* rec = flat + rec_off[comp];
 	const uint32_t seqcount = a.mode == MEMS_MODE_REPEAT ? len : (uint32_t)a.n_seqs;
 	rec[0] = seqcount;
 	rec[1] = kr - kl + L;
@@ -429,17 +719,15 @@ __global__ void hit_len_widen_kernel(const uint16_t* __restrict__ hit_len, uint3
 	if (h < n_hits) out[h] = hit_len[h] & ~kFirstStrandBit;
 }
 
-// record index of every hit: sorted entry -> segment -> the emitted component it belongs to
+// record (= component) index of every hit: sorted entry -> segment -> component
 __global__ void hit_record_kernel(const uint32_t* __restrict__ hid, const uint32_t* __restrict__ is_head,
-                                  const uint32_t* __restrict__ seg_of, const uint32_t* __restrict__ emit_excl,
-                                  const uint32_t* __restrict__ seg_emit, uint32_t n_hits, uint32_t* __restrict__ rec_of_hit) {
+                                  const uint32_t* __restrict__ seg_of, const uint32_t* __restrict__ first,
+                                  const uint32_t* __restrict__ first_excl, uint32_t n_hits, uint32_t* __restrict__ rec_of_hit) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_hits) return;
 	// seg_of is an exclusive scan of is_head: a head's own segment is seg_of[i], a follower's is seg_of[i]-1
 	const uint32_t seg = is_head[i] ? seg_of[i] : seg_of[i] - 1;
-	// an absorbed segment belongs to the closest emitted segment before it
-	const uint32_t rec = emit_excl[seg] + (seg_emit[seg] ? 1u : 0u) - 1u;
-	rec_of_hit[hid[i]] = rec;
+	rec_of_hit[hid[i]] = first_excl[seg] - (first[seg] ? 0u : 1u);
 }
 
 // ================================================================================================ host side
@@ -552,6 +840,7 @@ size_t bucket_lower_bound(const std::vector<Entry*>& v, const Entry& x) {
 
 }  // namespace
 
+
 template <class KeyT>
 static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
 	Ctx* c = b.ctx.get();
@@ -571,12 +860,13 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.mode = mode;
 	a.packed = b.packed.p;
 	a.meta = b.d_meta.p;
+	const KeyT* key_pos = reinterpret_cast<const KeyT*>(b.keys_by_pos.p);
 
 	// ---- 1. run scan -> hits in key order
 	const uint32_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
 	DevBuf<uint16_t> run_info(c, n);
-	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 4);
-	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 4 * sizeof(uint32_t), c->stream));
+	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 8);
+	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(uint32_t), c->stream));
 	{
 		KernelScope ks(c, "run_scan", (double)n * (sizeof(KeyT) + 2.0));
 		run_scan_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, run_info.p, block_hits.p, scalars.p + 0);
@@ -623,11 +913,12 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	{
 		KernelScope ks(c, "segment_flag");
 		segment_flag_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, L, hkey, hid, hit_start.p, hit_len.p, n_hits,
-		                                                             flags.p, is_head.p);
+		                                                             flags.p, is_head.p, scalars.p + 4);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, is_head.p, seg_of.p, n_hits, scalars.p + 2);
 	const uint32_t n_seg = d2h_u32(c, scalars.p + 2);
+	out.n_segments = n_seg;
 	DevBuf<uint32_t> seg_head(c, n_seg);
 	{
 		KernelScope ks(c, "segment_compact");
@@ -635,64 +926,114 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		MEMS_CUDA(cudaGetLastError());
 	}
 
-	// ---- 5. extend
-	DevBuf<int32_t> seg_kl(c, n_seg), seg_kr(c, n_seg);
-	DevBuf<uint32_t> seg_emit(c, n_seg), rec_size(c, n_seg), rec_off(c, n_seg);
+	// ---- 5. extend: right walks link segments into components, left walks finish each component
+	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg};
+	DevBuf<uint32_t> seg_link(c, n_seg), seg_reach(c, n_seg), first(c, n_seg), first_excl(c, n_seg);
+	DevBuf<uint2> defer(c, n_seg);
+	uint32_t* defer_count = scalars.p + 6;  // [6] right walks, [7] left walks handed to whole CTAs
+	const uint32_t long_grid = (uint32_t)c->sm_count;
+	const uint32_t walk_blocks = (n_seg + kExtendWarps - 1) / kExtendWarps, seg_blocks = (n_seg + 255) / 256;
 	{
-		KernelScope ks(c, "extend");
-		extend_kernel<KeyT><<<(n_seg + kExtendWarps - 1) / kExtendWarps, kExtendWarps * 32, 0, c->stream>>>(
-		    a, b.sd, hkey, hid, hit_start.p, hit_len.p, n_hits, flags.p, seg_head.p, n_seg, seg_kl.p, seg_kr.p, seg_emit.p);
+		KernelScope ks(c, "walk_right");
+		walk_right_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(a, key_pos, L, v, seg_link.p, seg_reach.p,
+		                                                                          defer.p, defer_count);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	{
+		KernelScope ks(c, "long_walk_right");
+		long_walk_right_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, key_pos, L, v, defer.p, defer_count,
+		                                                                           seg_link.p, seg_reach.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	{
+		KernelScope ks(c, "chain_first");
+		chain_first_kernel<<<seg_blocks, 256, 0, c->stream>>>(seg_link.p, n_seg, first.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+#ifdef MEMS_WALK_STATS
+	{
+		unsigned long long st[16];
+		MEMS_CUDA(cudaMemcpyFromSymbol(st, g_walk_stats, sizeof st));
+		fprintf(stderr, "walk_right: n_seg=%u probes=%llu max=%llu hist:", n_seg, st[0], st[1]);
+		for (int i = 2; i < 16; ++i) fprintf(stderr, " %llu", st[i]);
+		fprintf(stderr, "\n");
+		memset(st, 0, sizeof st);
+		MEMS_CUDA(cudaMemcpyToSymbol(g_walk_stats, st, sizeof st));
+	}
+#endif
+	exclusive_scan_u32(c, first.p, first_excl.p, n_seg, scalars.p + 3);
+	uint32_t h_tail[2];  // [n_comp, diagonal-hash collision seen]
+	MEMS_CUDA(cudaMemcpyAsync(h_tail, scalars.p + 3, sizeof h_tail, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	const uint32_t n_comp = h_tail[0];
+	const bool collision_seen = h_tail[1] != 0;
+	DevBuf<uint32_t> comp_rep(c, n_comp), comp_left(c, n_comp), comp_right(c, n_comp), rec_size(c, n_comp), rec_off(c, n_comp);
+	{
+		KernelScope ks(c, "walk_left");
+		walk_left_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(
+		    a, key_pos, L, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, defer.p,
+		    defer_count + 1);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	{
+		KernelScope ks(c, "long_walk_left");
+		long_walk_left_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, key_pos, L, v, defer.p, defer_count + 1,
+		                                                                          first_excl.p, comp_left.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 
 	// ---- 6. emit
-	const uint32_t seg_blocks = (n_seg + 255) / 256;
+	const uint32_t comp_blocks = (n_comp + 255) / 256;
 	{
 		KernelScope ks(c, "emit_size");
-		emit_size_kernel<<<seg_blocks, 256, 0, c->stream>>>(seg_emit.p, seg_head.p, hid, hit_len.p, n_seg, mode, b.n_seqs,
-		                                                    rec_size.p);
+		emit_size_kernel<<<comp_blocks, 256, 0, c->stream>>>(comp_rep.p, hid, hit_len.p, n_comp, mode, b.n_seqs, rec_size.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	exclusive_scan_u32(c, rec_size.p, rec_off.p, n_seg, scalars.p + 3);
-	const uint32_t n_flat = d2h_u32(c, scalars.p + 3);
+	exclusive_scan_u32(c, rec_size.p, rec_off.p, n_comp, scalars.p + 5);
+	const uint32_t n_flat = d2h_u32(c, scalars.p + 5);
 	DevBuf<int64_t> d_flat(c, n_flat);
 	{
 		KernelScope ks(c, "emit");
-		emit_kernel<KeyT><<<seg_blocks, 256, 0, c->stream>>>(a, L, seg_emit.p, seg_head.p, hid, hit_start.p, hit_len.p,
-		                                                     seg_kl.p, seg_kr.p, rec_off.p, n_seg, d_flat.p);
+		emit_kernel<KeyT><<<comp_blocks, 256, 0, c->stream>>>(a, L, hkey, hid, hit_start.p, hit_len.p, comp_rep.p,
+		                                                      comp_left.p, comp_right.p, rec_off.p, n_comp, d_flat.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	std::vector<int64_t> raw(n_flat);
 	MEMS_CUDA(cudaMemcpyAsync(raw.data(), d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
 
-	if (order == MEMS_ORDER_CANONICAL) {
+	if (order != MEMS_ORDER_REFERENCE) {
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
-		// distinct matches in canonical order; duplicates only arise when a diagonal-hash collision kept a
-		// segment from seeing its predecessor
-		std::vector<Rec> recs = split_records(raw);
-		std::sort(recs.begin(), recs.end(), rec_less);
-		recs.erase(std::unique(recs.begin(), recs.end(), rec_equal), recs.end());
-		out.flat.reserve(raw.size());
-		for (const Rec& r2 : recs) out.flat.insert(out.flat.end(), r2.p, r2.p + r2.size());
-		out.n_matches = recs.size();
+		// Components are distinct by construction unless two diagonals shared a hash bucket: a foreign entry
+		// between two hits of one diagonal hides them from each other and both may report the same component.
+		// Only then (or when a sorted list is asked for) are the records sorted / de-duplicated on the host.
+		if (order == MEMS_ORDER_CANONICAL || collision_seen) {
+			std::vector<Rec> recs = split_records(raw);
+			std::sort(recs.begin(), recs.end(), rec_less);
+			recs.erase(std::unique(recs.begin(), recs.end(), rec_equal), recs.end());
+			out.flat.reserve(raw.size());
+			for (const Rec& r2 : recs) out.flat.insert(out.flat.end(), r2.p, r2.p + r2.size());
+			out.n_matches = recs.size();
+		} else {
+			out.flat.swap(raw);
+			out.n_matches = n_comp;
+		}
 		out.mem_count = out.n_matches;
 		out.collisions = out.n_hits - out.n_matches;
 		return;
 	}
 
 	// ---- ORDER_REFERENCE: replay the reference's hash table over (hit, extended match) on the host
-	DevBuf<uint32_t> emit_excl(c, n_seg), rec_of_hit(c, n_hits), len32(c, n_hits), mem_off(c, n_hits);
-	exclusive_scan_u32(c, seg_emit.p, emit_excl.p, n_seg, nullptr);
+	DevBuf<uint32_t> rec_of_hit(c, n_hits), len32(c, n_hits), mem_off(c, n_hits);
 	{
 		KernelScope ks(c, "hit_record");
-		hit_record_kernel<<<hit_blocks, 256, 0, c->stream>>>(hid, is_head.p, seg_of.p, emit_excl.p, seg_emit.p, n_hits,
+		hit_record_kernel<<<hit_blocks, 256, 0, c->stream>>>(hid, is_head.p, seg_of.p, first.p, first_excl.p, n_hits,
 		                                                     rec_of_hit.p);
 		MEMS_CUDA(cudaGetLastError());
 		hit_len_widen_kernel<<<hit_blocks, 256, 0, c->stream>>>(hit_len.p, n_hits, len32.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	exclusive_scan_u32(c, len32.p, mem_off.p, n_hits, scalars.p + 3);
-	const uint32_t n_mem = d2h_u32(c, scalars.p + 3);
+	exclusive_scan_u32(c, len32.p, mem_off.p, n_hits, scalars.p + 5);
+	const uint32_t n_mem = d2h_u32(c, scalars.p + 5);
 	DevBuf<uint32_t> mem_val(c, n_mem);
 	DevBuf<uint8_t> mem_strand(c, n_mem);
 	{
@@ -709,7 +1050,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	MEMS_CUDA(cudaMemcpyAsync(h_strand.data(), mem_strand.p, (size_t)n_mem, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 
-	// emitted records in segment order: record r starts at raw[rec_start[r]]
+	// emitted records in component order: record r starts at raw[rec_start[r]]
 	std::vector<size_t> rec_start;
 	for (size_t i = 0; i < raw.size(); i += (size_t)raw[i] + 2) rec_start.push_back(i);
 
@@ -763,7 +1104,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
 	if (mode == MEMS_MODE_PAIRWISE) throw Error(MEMS_ERR_UNSUPPORTED, "PairwiseMatchFinder policy is not built yet");
-	if (b.n_seqs > 64) throw Error(MEMS_ERR_UNSUPPORTED, "more than 64 sequences in one match-finding call");
+	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
 	if (b.key64)
 		find_matches_typed<uint64_t>(b, mode, order, table_size, out);
 	else

@@ -201,7 +201,7 @@ __global__ void scan_bins_kernel(const uint32_t* __restrict__ hist, uint32_t* __
 }
 
 int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], uint64_t n, const SortPlan& plan,
-                     uint32_t* d_hist, const char* prof_name) {
+                     uint32_t* d_hist, const char* prof_name, const void* first_keys_in) {
 	if (n == 0) return 0;
 	if (n > radix_max_items()) throw Error(4, "radix sort: more than 2^30-1 items in one device sort");
 	const uint32_t n_tiles = (uint32_t)((n + kTile - 1) / kTile);
@@ -233,11 +233,11 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 		KernelScope ks(c, prof_name, 2.0 * (double)n * (double)(key_bytes + 4));
 		if (key64)
 			onesweep_kernel<uint64_t><<<n_tiles, kSortThreads, smem, c->stream>>>(
-			    (const uint64_t*)d_keys[cur], d_vals[cur], (uint64_t*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n,
+			    (const uint64_t*)(q == 0 && first_keys_in ? first_keys_in : d_keys[cur]), d_vals[cur], (uint64_t*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n,
 			    plan.shift[q], mask, bin_base.p + q * kRadix, st, ticket);
 		else
 			onesweep_kernel<uint32_t><<<n_tiles, kSortThreads, smem, c->stream>>>(
-			    (const uint32_t*)d_keys[cur], d_vals[cur], (uint32_t*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n,
+			    (const uint32_t*)(q == 0 && first_keys_in ? first_keys_in : d_keys[cur]), d_vals[cur], (uint32_t*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n,
 			    plan.shift[q], mask, bin_base.p + q * kRadix, st, ticket);
 		MEMS_CUDA(cudaGetLastError());
 		cur ^= 1;

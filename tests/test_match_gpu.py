@@ -89,10 +89,10 @@ def test_singles_then_find_equals_batch(ctx, orc):
     smls = [ctx.create_sml(g, seed) for g in gs]
     flat, _ = ctx.find_matches(smls, mode=mems.MODE_MEMHASH)
     want, _ = orc.find_matches(0, gs, seed)
-    assert mems.flat_to_matches(flat) == canonical(want)
+    assert sorted(mems.flat_to_matches(flat)) == canonical(want)  # ORDER_ANY: distinct, device order
     # a subset, in another order, of a batch
     b = ctx.create_smls(gs, seed)
-    flat, _ = ctx.find_matches([b[2], b[0]], mode=mems.MODE_MEMHASH)
+    flat, _ = ctx.find_matches([b[2], b[0]], mode=mems.MODE_MEMHASH, order=mems.ORDER_CANONICAL)
     want, _ = orc.find_matches(0, [gs[2], gs[0]], seed)
     assert mems.flat_to_matches(flat) == canonical(want)
 
@@ -125,3 +125,22 @@ def test_medium_size_vs_oracle(ctx, orc):
     got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
     assert got == canonical(want)
     assert info["n_hits"] == winfo["hits"]
+
+
+def test_long_walks_between_sparse_hits(ctx, orc):
+    """Few hits, long matching diagonal: the extension walks exceed a warp's probe budget and are finished
+    by the CTA-wide walker, including the case where a long walk has to link two distant hit groups."""
+    seed = mems.get_seed(15)
+    rng = np.random.default_rng(99)
+    T = synth.random_genome(30_000, rng)
+    M1, M2 = synth.random_genome(60, rng), synth.random_genome(60, rng)
+    # every window inside a copy of T is repeated (no hit); only windows touching M1/M2 are unique
+    for X in (np.concatenate([T, M1, T]), np.concatenate([T, M1, T, M2, T])):
+        for other in (X, synth.revcomp(X)):
+            want, winfo = orc.find_matches(0, [X, other], seed)
+            got, info = gpu_matches(ctx, [X, other], seed, mems.MODE_MEMHASH)
+            assert got == canonical(want)
+            assert info["n_hits"] == winfo["hits"]
+            assert any(m[1] == len(X) for m in got)  # the full-length diagonal is found
+            got_ref, _ = gpu_matches(ctx, [X, other], seed, mems.MODE_MEMHASH, mems.ORDER_REFERENCE)
+            assert got_ref == want
