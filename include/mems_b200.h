@@ -128,6 +128,8 @@ int mems_matches_info(mems_matches_t m, mems_matches_info_t* out);
 /* Flat records [SeqCount, Length, Start(0) .. Start(SeqCount-1)] per match; starts are 1-based,
  * negative = reverse strand, 0 = NO_MATCH (AbstractMatch.h:27, UngappedLocalAlignment.h:201-206). */
 int mems_matches_copy(mems_matches_t m, int64_t* flat_out);
+/* The same records in place (n_flat int64 values), valid until mems_matches_destroy: no copy. */
+const int64_t* mems_matches_data(mems_matches_t m);
 void mems_matches_destroy(mems_matches_t m);
 
 /* ---- measurement ---- */

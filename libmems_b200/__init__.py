@@ -52,7 +52,7 @@ EXPORTS = [
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_destroy",
+    "mems_sml_packed", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
 ]
 
@@ -95,6 +95,8 @@ def load():
                                       ctypes.POINTER(_vp)]
     lib.mems_matches_info.argtypes = [_vp, ctypes.POINTER(MatchesInfo)]
     lib.mems_matches_copy.argtypes = [_vp, _vp]
+    lib.mems_matches_data.argtypes = [_vp]
+    lib.mems_matches_data.restype = ctypes.POINTER(ctypes.c_int64)
     lib.mems_matches_destroy.argtypes = [_vp]
     lib.mems_profile_enable.argtypes = [_vp, ctypes.c_int]
     lib.mems_profile_reset.argtypes = [_vp]
@@ -132,6 +134,26 @@ def _host_ptr(seq):
     b = bytes(seq)
     buf = ctypes.create_string_buffer(b, len(b)) if len(b) else ctypes.create_string_buffer(1)
     return ctypes.addressof(buf), len(b), buf
+
+
+class _MatchHandle:
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def __del__(self):
+        try:
+            self.lib.mems_matches_destroy(self.h)
+        except Exception:
+            pass
+
+
+class _OwnedArray(np.ndarray):
+    """ndarray view that keeps the owning match handle alive."""
+    _keep = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._keep = getattr(obj, "_keep", None)
 
 
 class Context:
@@ -190,15 +212,16 @@ class Context:
         params = MatchParams(mode, order, table_size, 0)
         h = _vp()
         self._check(self.lib.mems_find_matches(self.h, n, arr, ctypes.byref(params), ctypes.byref(h)))
-        try:
-            info = MatchesInfo()
-            self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
-            flat = np.zeros(max(int(info.n_flat), 1), np.int64)
-            self._check(self.lib.mems_matches_copy(h, flat.ctypes.data))
-        finally:
-            self.lib.mems_matches_destroy(h)
-        flat = flat[:int(info.n_flat)]
+        keep = _MatchHandle(self.lib, h)
+        info = MatchesInfo()
+        self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
         d = {k: int(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        if info.n_flat == 0:
+            return np.zeros(0, np.int64), d
+        # zero-copy view of the library's (page-locked) result buffer; it lives as long as the array does
+        view = np.ctypeslib.as_array(self.lib.mems_matches_data(h), shape=(int(info.n_flat),))
+        flat = view.view(_OwnedArray)
+        flat._keep = keep
         return flat, d
 
     # -- measurement ----------------------------------------------------------------------------------

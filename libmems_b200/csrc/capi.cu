@@ -273,10 +273,12 @@ int mems_matches_info(mems_matches_t m, mems_matches_info_t* out) {
 }
 
 int mems_matches_copy(mems_matches_t m, int64_t* flat_out) {
-	if (!m || (!flat_out && !m->r.flat.empty())) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
-	if (!m->r.flat.empty()) memcpy(flat_out, m->r.flat.data(), m->r.flat.size() * sizeof(int64_t));
+	if (!m || (!flat_out && m->r.flat.size())) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	if (m->r.flat.size()) memcpy(flat_out, m->r.flat.data(), m->r.flat.size() * sizeof(int64_t));
 	return MEMS_OK;
 }
+
+const int64_t* mems_matches_data(mems_matches_t m) { return m ? m->r.flat.data() : nullptr; }
 
 void mems_matches_destroy(mems_matches_t m) { delete m; }
 

@@ -69,6 +69,10 @@ struct Ctx {
 
 	void* alloc(size_t bytes);  // stream-ordered
 	void free(void* p);
+	// page-locked host staging buffers for results (D2H at full PCIe rate), recycled across calls
+	std::vector<std::pair<void*, size_t>> pinned_free;
+	void* pinned_get(size_t bytes, size_t* capacity);
+	void pinned_put(void* p, size_t capacity);
 	cudaEvent_t get_event();
 	void prof_begin(const char* name, double bytes);
 	void prof_end(const char* name);
@@ -188,8 +192,25 @@ struct SeqRef {
 std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const std::vector<SeqRef>& seqs);
 
 // ---- kernels_match.cu ----
+// [SeqCount, Length, starts...] records on the host: either a page-locked buffer borrowed from the context
+// (filled straight by the D2H copy) or, when the host re-ordered the records, a plain vector.
+struct FlatRecords {
+	std::shared_ptr<Ctx> owner;
+	int64_t* pinned = nullptr;
+	size_t pinned_cap = 0, pinned_n = 0;
+	std::vector<int64_t> vec;
+	const int64_t* data() const { return pinned ? pinned : vec.data(); }
+	size_t size() const { return pinned ? pinned_n : vec.size(); }
+	void release() {
+		if (pinned) owner->pinned_put(pinned, pinned_cap);
+		pinned = nullptr;
+		pinned_n = 0;
+	}
+	~FlatRecords() { release(); }
+};
+
 struct MatchResult {
-	std::vector<int64_t> flat;  // [SeqCount, Length, starts...] per match
+	FlatRecords flat;
 	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0, n_segments = 0;
 	uint32_t seq_count = 0, seed_length = 0;
 };

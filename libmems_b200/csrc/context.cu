@@ -16,6 +16,32 @@ void Ctx::free(void* p) {
 	if (p) cudaFreeAsync(p, stream);
 }
 
+void* Ctx::pinned_get(size_t bytes, size_t* capacity) {
+	size_t best = pinned_free.size();
+	for (size_t i = 0; i < pinned_free.size(); ++i)
+		if (pinned_free[i].second >= bytes && (best == pinned_free.size() || pinned_free[i].second < pinned_free[best].second))
+			best = i;
+	if (best != pinned_free.size()) {
+		void* p = pinned_free[best].first;
+		*capacity = pinned_free[best].second;
+		pinned_free.erase(pinned_free.begin() + best);
+		return p;
+	}
+	size_t cap = (bytes + (1u << 20)) & ~(size_t)((1u << 20) - 1);  // round up to 1 MiB
+	void* p = nullptr;
+	MEMS_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+	*capacity = cap;
+	return p;
+}
+
+void Ctx::pinned_put(void* p, size_t capacity) {
+	if (pinned_free.size() >= 8) {  // keep the pool small
+		cudaFreeHost(p);
+		return;
+	}
+	pinned_free.push_back({p, capacity});
+}
+
 cudaEvent_t Ctx::get_event() {
 	if (!free_events.empty()) {
 		cudaEvent_t e = free_events.back();
@@ -68,6 +94,7 @@ Ctx::~Ctx() {
 			cudaEventDestroy(pr.second);
 		}
 	for (auto e : free_events) cudaEventDestroy(e);
+	for (auto& pb : pinned_free) cudaFreeHost(pb.first);
 	if (own_stream && stream) cudaStreamDestroy(stream);
 }
 

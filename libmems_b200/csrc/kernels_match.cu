@@ -269,9 +269,16 @@ segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const
 }
 
 __global__ void segment_compact_kernel(const uint32_t* __restrict__ is_head, const uint32_t* __restrict__ seg_of,
-                                       uint32_t n_hits, uint32_t* __restrict__ seg_head) {
+                                       const uint64_t* __restrict__ hkey, uint32_t pos_mask, uint32_t n_hits,
+                                       uint32_t* __restrict__ seg_head, uint32_t* __restrict__ seg_x,
+                                       uint32_t* __restrict__ seg_id) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n_hits && is_head[i]) seg_head[seg_of[i]] = i;
+	if (i < n_hits && is_head[i]) {
+		const uint32_t seg = seg_of[i];
+		seg_head[seg] = i;
+		seg_x[seg] = (uint32_t)hkey[i] & pos_mask;
+		seg_id[seg] = seg;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ 5. extend
@@ -286,7 +293,7 @@ __global__ void segment_compact_kernel(const uint32_t* __restrict__ is_head, con
 constexpr int kExtendWarps = 4;
 constexpr int kMemberTile = 64;  // members staged in shared memory per warp (MEMS_MAX_SEQS fits at once)
 constexpr uint32_t kReverseBit = 0x80000000u;
-constexpr int kWarpProbeBudget = 16;  // probes (of 128 windows) a single warp spends on one walk before deferring
+constexpr int kWarpProbeBudget = 48;  // probes (of 128 windows) a single warp spends on one walk before deferring
 
 template <class KeyT>
 struct WarpHit {
@@ -294,24 +301,26 @@ struct WarpHit {
 	const KeyT* key_pos;
 	uint32_t* s_mem;  // this warp's kMemberTile slots: (seed_off + pos) | reverse << 31
 	uint32_t s, len, sf;
-	int64_t kmin, kmax;
+	int32_t kmin, kmax;  // valid window offsets (all |k| < 2^31: positions are < 2^30)
 	int lane;
 #ifdef MEMS_WALK_STATS
 	uint32_t n_probes = 0;
 #endif
+	static constexpr int kProbe = 128;
+	typedef unsigned __int128 mask_t;  // bit i = the window at distance i+1 matches
 
-	__device__ uint32_t member_entry(uint32_t j, int64_t& lo, int64_t& hi) const {
+	__device__ uint32_t member_entry(uint32_t j, int32_t& lo, int32_t& hi) const {
 		const uint32_t val = a.vals[j];
 		const uint32_t o = strand_of<KeyT>(a.keys, j) ^ sf;
 		const SeqMeta m = a.meta[val >> a.pos_bits];
-		const int64_t p = val & a.pos_mask, last = (int64_t)m.n_seeds - 1;
+		const int32_t p = (int32_t)(val & a.pos_mask), last = (int32_t)m.n_seeds - 1;
 		lo = o ? p - last : -p;
 		hi = o ? p : last - p;
 		return ((uint32_t)m.seed_off + (uint32_t)p) | (o ? kReverseBit : 0u);
 	}
 	__device__ void load_tile(uint32_t first) {
 		for (uint32_t t = lane; t < kMemberTile && first + t < len; t += 32) {
-			int64_t lo, hi;
+			int32_t lo, hi;
 			s_mem[t] = member_entry(s + first + t, lo, hi);
 		}
 		__syncwarp();
@@ -320,55 +329,58 @@ struct WarpHit {
 		s = hit_s;
 		len = hit_len;
 		sf = first_strand;
-		int64_t lo = INT64_MIN, hi = INT64_MAX;
+		int32_t lo = INT32_MIN, hi = INT32_MAX;
 		for (uint32_t t = lane; t < len; t += 32) {
-			int64_t l2, h2;
+			int32_t l2, h2;
 			member_entry(s + t, l2, h2);
-			lo = l2 > lo ? l2 : lo;
-			hi = h2 < hi ? h2 : hi;
+			lo = max(lo, l2);
+			hi = min(hi, h2);
 		}
-		for (int o = 16; o; o >>= 1) {
-			int64_t l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
-			lo = l2 > lo ? l2 : lo;
-			hi = h2 < hi ? h2 : hi;
-		}
-		kmin = lo;
-		kmax = hi;
+		kmin = __reduce_max_sync(0xffffffffu, lo);
+		kmax = __reduce_min_sync(0xffffffffu, hi);
 		load_tile(0);
 	}
-	__device__ uint64_t tagged(uint32_t e, int64_t k) const {
-		const uint32_t rev = e >> 31;
-		const int64_t idx = (int64_t)(e & ~kReverseBit) + (rev ? -k : k);
-		return (uint64_t)key_pos[idx] ^ (uint64_t)rev;
-	}
-	// Probe the kProbe windows at distances 1..kProbe from k0 in direction dir (+1/-1): lane l tests distances
-	// l+1, l+33, l+65, l+97.  All loads of one member are independent (no early exit inside a lane), so a probe
-	// costs about one memory round trip per member instead of one per member and window.  Returns the match
-	// bits, bit i = distance i+1, identical in every lane.
-	__device__ void probe(int64_t k0, int dir, uint64_t& m_lo, uint64_t& m_hi) {
-		int64_t kk[4];
+	// Probe the windows at distances 1..n_win (<= 128) from k0 in direction dir (+1/-1): lane l tests distances
+	// l+1, l+33, l+65, l+97.  Members are taken four at a time and all 16 loads of a group are issued before
+	// any is compared, so a group costs one memory round trip.  Returns the match bits, identical in every lane.
+	__device__ mask_t probe(int32_t k0, int dir, int n_win) {
+		int32_t kk[4];
 		bool ok[4];
-		uint64_t ref[4];
+		KeyT ref[4];
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
-			kk[j] = k0 + (int64_t)dir * (lane + 32 * j + 1);
-			ok[j] = kk[j] >= kmin && kk[j] <= kmax;
+			kk[j] = k0 + dir * (lane + 32 * j + 1);
+			ok[j] = lane + 32 * j < n_win && kk[j] >= kmin && kk[j] <= kmax;
 			if (!ok[j]) kk[j] = 0;  // window 0 is the hit itself, always valid: keeps the loads in range
 		}
 		for (uint32_t first = 0; first < len; first += kMemberTile) {
 			if (first) load_tile(first);
 			const uint32_t cnt = len - first < kMemberTile ? len - first : kMemberTile;
-			for (uint32_t t = 0; t < cnt; ++t) {
-				const uint32_t e = s_mem[t];
+			for (uint32_t t0 = 0; t0 < cnt; t0 += 4) {
+				KeyT v[4][4];
+				uint32_t rev[4];
 #pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const uint64_t v = tagged(e, kk[j]);
-					if (first == 0 && t == 0) ref[j] = v;
-					else ok[j] = ok[j] && v == ref[j];
+				for (int u = 0; u < 4; ++u) {
+					const uint32_t e = s_mem[t0 + u < cnt ? t0 + u : cnt - 1];  // tail: repeat the last member
+					rev[u] = e >> 31;
+					const uint32_t base = e & ~kReverseBit;
+#pragma unroll
+					for (int j = 0; j < 4; ++j)
+						if (32 * j < n_win) v[u][j] = key_pos[base + (uint32_t)(rev[u] ? -kk[j] : kk[j])];  // warp-uniform guard
 				}
-				// whole-warp early exit, checked every 8 members so the loads in between stay independent
-				if ((t & 7) == 7 && !__any_sync(0xffffffffu, ok[0] | ok[1] | ok[2] | ok[3])) {
-					t = cnt;
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						if (32 * j < n_win) {
+							const KeyT tg = v[u][j] ^ (KeyT)rev[u];  // reverse members flip the strand bit
+							if (first == 0 && t0 == 0 && u == 0) ref[j] = tg;
+							else ok[j] = ok[j] && tg == ref[j];
+						}
+					}
+				}
+				if (cnt > 4 && !__any_sync(0xffffffffu, ok[0] | ok[1] | ok[2] | ok[3])) {  // nothing left to decide
+					t0 = cnt;
 					first = len;
 				}
 			}
@@ -377,16 +389,50 @@ struct WarpHit {
 		if (len > kMemberTile) load_tile(0);
 		const uint32_t b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
 		const uint32_t b2 = __ballot_sync(0xffffffffu, ok[2]), b3 = __ballot_sync(0xffffffffu, ok[3]);
-		m_lo = ((uint64_t)b1 << 32) | b0;
-		m_hi = ((uint64_t)b3 << 32) | b2;
+		return ((mask_t)(((uint64_t)b3 << 32) | b2) << 64) | (mask_t)(((uint64_t)b1 << 32) | b0);
+	}
+	__device__ static int highest_set(mask_t m) {  // 1-based distance of the highest set bit, 0 if none
+		const uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+		return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
+	}
+	__device__ static int lowest_set(mask_t m) {  // 1-based distance of the lowest set bit, 0 if none
+		const uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+		return lo ? __ffsll((long long)lo) : (hi ? 64 + __ffsll((long long)hi) : 0);
+	}
+	// Follow the chain of matches inside one probe, starting from a match at distance `from` (0 = the window
+	// the walk stands on): consecutive matches may be at most L apart.  Bit-parallel: the chain ends right
+	// before the first run of L zero bits, found by AND-ing shifted copies of the zero mask (log steps).
+	// Returns the chain's last match; *ended tells whether that L-gap lies completely inside the n_win
+	// probed windows (the chain is over) or the probe simply ran out (continue from the returned distance).
+	__device__ static int follow(mask_t m, int from, int L, int n_win, bool* ended) {
+		const mask_t valid = n_win >= 128 ? ~(mask_t)0 : (((mask_t)1 << n_win) - 1);
+		mask_t z = ~m & valid;             // zero bits inside the probed range; beyond it nothing is known
+		if (from) z &= ~(((mask_t)1 << from) - 1);  // ignore everything before the starting match
+		// run[i] = z[i] & z[i+1] & ... & z[i+L-1]
+		const mask_t a1 = z, a2 = a1 & (a1 >> 1), a4 = a2 & (a2 >> 2), a8 = a4 & (a4 >> 4), a16 = a8 & (a8 >> 8);
+		mask_t run = ~(mask_t)0;
+		int off = 0;
+		if (L & 16) { run &= a16 >> off; off += 16; }
+		if (L & 8) { run &= a8 >> off; off += 8; }
+		if (L & 4) { run &= a4 >> off; off += 4; }
+		if (L & 2) { run &= a2 >> off; off += 2; }
+		if (L & 1) { run &= a1 >> off; }
+		const int gap_at = lowest_set(run);  // distance of the first window of the first L-gap
+		if (gap_at) {
+			*ended = true;
+			return gap_at - 1 > from ? gap_at - 1 : from;  // the window right before the gap is the chain's last match
+		}
+		*ended = false;
+		const int last = highest_set(m & valid);
+		return last > from ? last : from;
 	}
 	// Walk from window k0 in direction dir over matching windows that start <= L apart, as far as they go
 	// (the closure loop of MatchFinder::ExtendMatch, MatchFinder.h:259-355).  If stop_dist >= 0 the walk ends as
 	// soon as it stands within L of that distance (the next segment of the diagonal) and *linked is set.
 	// Returns the distance walked.  After max_probes probes the walk gives up with *exhausted set: such
 	// walks (a handful per genome set, but up to hundreds of kbp long) are finished by whole CTAs, see cta_walk.
-	__device__ int64_t walk(int64_t k0, int dir, int L, int64_t stop_dist, bool* linked, int max_probes, bool* exhausted) {
-		int64_t walked = 0;
+	__device__ int32_t walk(int32_t k0, int dir, int L, int32_t stop_dist, bool* linked, int max_probes, bool* exhausted) {
+		int32_t walked = 0;
 		*linked = false;
 		*exhausted = false;
 		for (int n = 0;; ++n) {
@@ -398,47 +444,20 @@ struct WarpHit {
 				*exhausted = true;
 				return walked;
 			}
-			uint64_t m_lo, m_hi;
-			probe(k0 + dir * walked, dir, m_lo, m_hi);
+			int n_win = kProbe;  // never probe beyond the stop target
+			if (stop_dist >= 0 && stop_dist - walked < n_win) n_win = stop_dist - walked;
+			const mask_t m = probe(k0 + dir * walked, dir, n_win);
 #ifdef MEMS_WALK_STATS
 			++n_probes;
 #endif
-			int pos = 0;  // distance reached inside this probe
-			while (true) {
-				if (stop_dist >= 0 && stop_dist <= walked + pos + L) {
-					*linked = true;
-					return walked + pos;
-				}
-				const int limit = pos + L < kProbe ? pos + L : kProbe;
-				const int best = highest_set_in(m_lo, m_hi, pos, limit);  // farthest match in (pos, limit]
-				if (best) {
-					pos = best;
-					continue;
-				}
-				if (pos + L <= kProbe) return walked + pos;  // a full L-window without a match: the chain ends here
-				break;  // the rest of the L-window lies beyond this probe
+			bool ended;
+			walked += follow(m, 0, L, n_win, &ended);
+			if (stop_dist >= 0 && stop_dist <= walked + L) {
+				*linked = true;
+				return walked;
 			}
-			walked += pos;
+			if (ended) return walked;
 		}
-	}
-	static constexpr int kProbe = 128;
-	// highest distance d in (a, b] whose bit (d-1) is set, 0 if none; 0 <= a < b <= 128
-	__device__ static int highest_set_in(uint64_t lo, uint64_t hi, int a, int b) {
-		if (b > 64) {
-			const int from = a > 64 ? a - 64 : 0, to = b - 64;  // bits [from, to) of hi
-			uint64_t w = hi;
-			if (to < 64) w &= (1ull << to) - 1ull;
-			w = from < 64 ? (w >> from) << from : 0ull;
-			if (w) return 64 + 64 - __clzll(w);
-		}
-		if (a < 64) {
-			const int to = b < 64 ? b : 64;  // bits [a, to) of lo
-			uint64_t w = lo;
-			if (to < 64) w &= (1ull << to) - 1ull;
-			w = (w >> a) << a;
-			if (w) return 64 - __clzll(w);
-		}
-		return 0;
 	}
 };
 
@@ -454,6 +473,7 @@ struct SegView {
 	const uint8_t* flags;
 	const uint32_t* seg_head;
 	uint32_t n_hits, n_seg;
+	const uint32_t* order;  // segment ids sorted by the first-member position of their first hit
 };
 
 // Right walk of every segment: from its last hit, follow matching windows until either the next segment of
@@ -464,17 +484,18 @@ __global__ void __launch_bounds__(kExtendWarps * 32)
 walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, uint32_t* __restrict__ seg_link,
                   uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
 	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
-	const uint32_t seg = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
-	if (seg >= v.n_seg) return;
+	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
+	if (slot >= v.n_seg) return;
+	const uint32_t seg = v.order[slot];  // segments are visited in order of genome position (L2 locality)
 	const uint32_t hi = v.seg_head[seg];
 	const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
 	const uint32_t h = v.hid[hi];
 	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
 	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
 	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
-	int64_t c = (int64_t)(v.hkey[end - 1] & a.pos_mask) - x0;
+	int32_t c = (int32_t)((int64_t)(v.hkey[end - 1] & a.pos_mask) - x0);
 	const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
-	const int64_t next_at = has_next ? (int64_t)(v.hkey[end] & a.pos_mask) - x0 : 0;
+	const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
 	bool linked, exhausted;
 	c += w.walk(c, +1, L, has_next ? next_at - c : -1, &linked, kWarpProbeBudget, &exhausted);
 	if (exhausted) {  // hand the rest of this walk to a whole CTA (long_walk_kernel)
@@ -512,8 +533,9 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
                  const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
                  uint32_t* __restrict__ comp_right, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
 	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
-	const uint32_t seg = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
-	if (seg >= v.n_seg) return;
+	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
+	if (slot >= v.n_seg) return;
+	const uint32_t seg = v.order[slot];
 	const int lane = threadIdx.x & 31;
 	const bool is_first = first[seg] != 0;
 	const uint32_t comp = first_excl[seg] - (is_first ? 0u : 1u);
@@ -525,7 +547,7 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, lane};
 	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 	bool linked, exhausted;
-	const int64_t c = -w.walk(0, -1, L, -1, &linked, kWarpProbeBudget, &exhausted);
+	const int32_t c = -w.walk(0, -1, L, -1, &linked, kWarpProbeBudget, &exhausted);
 	if (lane == 0) comp_rep[comp] = hi;
 	if (exhausted) {
 		if (lane == 0) {
@@ -549,30 +571,26 @@ constexpr int kLongWarps = 32;
 constexpr int kLongSpan = kLongWarps * 128;
 
 template <class KeyT>
-__device__ int64_t cta_walk(WarpHit<KeyT>& w, int64_t k0, int dir, int L, int64_t stop_dist, bool* linked, int4* s_sum,
-                            int64_t* s_result) {
+__device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_t stop_dist, bool* linked, int4* s_sum,
+                            int32_t* s_result) {
+	typedef typename WarpHit<KeyT>::mask_t mask_t;
 	const int warp = threadIdx.x >> 5;
-	int64_t walked = 0;
+	int32_t walked = 0;
 	while (true) {
-		uint64_t m_lo, m_hi;
-		w.probe(k0 + dir * (walked + 128 * warp), dir, m_lo, m_hi);
-		// summary of this warp's 128 windows (distances 1..128 from its own base)
-		int first = 0, chain_end = 0, last = 0;
-		if (m_lo | m_hi) {
-			first = m_lo ? __ffsll((long long)m_lo) : 64 + __ffsll((long long)m_hi);
-			last = m_hi ? 128 - __clzll(m_hi) : 64 - __clzll(m_lo);
-			chain_end = first;
-			while (true) {
-				const int limit = chain_end + L < 128 ? chain_end + L : 128;
-				const int best = WarpHit<KeyT>::highest_set_in(m_lo, m_hi, chain_end, limit);
-				if (!best) break;
-				chain_end = best;
-			}
+		const mask_t m = w.probe(k0 + dir * (walked + 128 * warp), dir, 128);
+		// summary of this warp's 128 windows (distances 1..128 from its own base): first match, last match of
+		// the chain that starts at the first match, last match overall
+		const int first = WarpHit<KeyT>::lowest_set(m), last = WarpHit<KeyT>::highest_set(m);
+		int chain_end = 0;
+		if (first) {
+			bool ended;
+			chain_end = WarpHit<KeyT>::follow(m, first, L, 128, &ended);
+			if (!ended) chain_end = last;
 		}
 		if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
 		__syncthreads();
 		if (threadIdx.x == 0) {
-			int64_t cur = 0;  // last confirmed match, as a distance from this round's base
+			int32_t cur = 0;  // last confirmed match, as a distance from this round's base
 			int state = 0;    // 0 = ran through the whole span, 1 = chain ended, 2 = linked
 			for (int i = 0; i < kLongWarps && state == 0; ++i) {
 				if (stop_dist >= 0 && stop_dist <= walked + cur + L) state = 2;
@@ -593,7 +611,7 @@ __device__ int64_t cta_walk(WarpHit<KeyT>& w, int64_t k0, int dir, int L, int64_
 		}
 		__syncthreads();
 		walked += s_result[0];
-		const int64_t state = s_result[1];
+		const int state = s_result[1];
 		__syncthreads();
 		if (state) {
 			*linked = state == 2;
@@ -609,11 +627,11 @@ long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, Seg
                        uint32_t* __restrict__ seg_reach) {
 	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
 	__shared__ int4 s_sum[kLongWarps];
-	__shared__ int64_t s_result[2];
+	__shared__ int32_t s_result[2];
 	const uint32_t n_defer = *defer_count;
 	for (uint32_t i = blockIdx.x; i < n_defer; i += gridDim.x) {
 		const uint32_t seg = defer[i].x;
-		int64_t c = (int32_t)defer[i].y;
+		int32_t c = (int32_t)defer[i].y;
 		const uint32_t hi = v.seg_head[seg];
 		const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
 		const uint32_t h = v.hid[hi];
@@ -621,7 +639,7 @@ long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, Seg
 		WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
 		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 		const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
-		const int64_t next_at = has_next ? (int64_t)(v.hkey[end] & a.pos_mask) - x0 : 0;
+		const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
 		bool linked;
 		c += cta_walk<KeyT>(w, c, +1, L, has_next ? next_at - c : -1, &linked, s_sum, s_result);
 		if (threadIdx.x == 0) {
@@ -638,11 +656,11 @@ long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegV
                       uint32_t* __restrict__ comp_left) {
 	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
 	__shared__ int4 s_sum[kLongWarps];
-	__shared__ int64_t s_result[2];
+	__shared__ int32_t s_result[2];
 	const uint32_t n_defer = *defer_count;
 	for (uint32_t i = blockIdx.x; i < n_defer; i += gridDim.x) {
 		const uint32_t seg = defer[i].x;  // always the first segment of its component
-		int64_t c = (int32_t)defer[i].y;
+		int32_t c = (int32_t)defer[i].y;
 		const uint32_t hi = v.seg_head[seg];
 		const uint32_t h = v.hid[hi];
 		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
@@ -747,9 +765,9 @@ struct Rec {
 bool rec_less(const Rec& x, const Rec& y) { return std::lexicographical_compare(x.p, x.p + x.size(), y.p, y.p + y.size()); }
 bool rec_equal(const Rec& x, const Rec& y) { return x.size() == y.size() && std::equal(x.p, x.p + x.size(), y.p); }
 
-std::vector<Rec> split_records(const std::vector<int64_t>& flat) {
+std::vector<Rec> split_records(const int64_t* flat, size_t n) {
 	std::vector<Rec> recs;
-	for (size_t i = 0; i < flat.size(); i += (size_t)flat[i] + 2) recs.push_back({flat.data() + i});
+	for (size_t i = 0; i < n; i += (size_t)flat[i] + 2) recs.push_back({flat + i});
 	return recs;
 }
 
@@ -919,15 +937,28 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	exclusive_scan_u32(c, is_head.p, seg_of.p, n_hits, scalars.p + 2);
 	const uint32_t n_seg = d2h_u32(c, scalars.p + 2);
 	out.n_segments = n_seg;
-	DevBuf<uint32_t> seg_head(c, n_seg);
+	DevBuf<uint32_t> seg_head(c, n_seg), seg_x_a(c, n_seg), seg_x_b(c, n_seg), seg_id_a(c, n_seg), seg_id_b(c, n_seg);
 	{
 		KernelScope ks(c, "segment_compact");
-		segment_compact_kernel<<<hit_blocks, 256, 0, c->stream>>>(is_head.p, seg_of.p, n_hits, seg_head.p);
+		segment_compact_kernel<<<hit_blocks, 256, 0, c->stream>>>(is_head.p, seg_of.p, hkey, a.pos_mask, n_hits, seg_head.p,
+		                                                          seg_x_a.p, seg_id_a.p);
 		MEMS_CUDA(cudaGetLastError());
+	}
+	// Visit segments in order of genome position, not of diagonal hash: the walks of all diagonals that cross
+	// one region then run together and find that region's keys in L2 instead of going to HBM one by one.
+	const uint32_t* seg_order;
+	{
+		SortPlan splan = make_sort_plan(b.pos_bits);
+		DevBuf<uint32_t> shist(c, (size_t)splan.n_passes * 256);
+		launch_histogram(c, false, seg_x_a.p, n_seg, splan, shist.p);
+		void* skp[2] = {seg_x_a.p, seg_x_b.p};
+		uint32_t* svp[2] = {seg_id_a.p, seg_id_b.p};
+		const int sr = radix_sort_pairs(c, false, skp, svp, n_seg, splan, shist.p, "segment_order_pass");
+		seg_order = sr ? seg_id_b.p : seg_id_a.p;
 	}
 
 	// ---- 5. extend: right walks link segments into components, left walks finish each component
-	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg};
+	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg, seg_order};
 	DevBuf<uint32_t> seg_link(c, n_seg), seg_reach(c, n_seg), first(c, n_seg), first_excl(c, n_seg);
 	DevBuf<uint2> defer(c, n_seg);
 	uint32_t* defer_count = scalars.p + 6;  // [6] right walks, [7] left walks handed to whole CTAs
@@ -998,8 +1029,12 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		                                                      comp_left.p, comp_right.p, rec_off.p, n_comp, d_flat.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	std::vector<int64_t> raw(n_flat);
-	MEMS_CUDA(cudaMemcpyAsync(raw.data(), d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+	// D2H straight into a page-locked buffer that the result object keeps (no pageable staging, no copy)
+	out.flat.owner = b.ctx;
+	out.flat.pinned = (int64_t*)c->pinned_get((size_t)n_flat * sizeof(int64_t), &out.flat.pinned_cap);
+	out.flat.pinned_n = n_flat;
+	const int64_t* raw = out.flat.pinned;
+	MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
 
 	if (order != MEMS_ORDER_REFERENCE) {
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
@@ -1007,14 +1042,14 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		// between two hits of one diagonal hides them from each other and both may report the same component.
 		// Only then (or when a sorted list is asked for) are the records sorted / de-duplicated on the host.
 		if (order == MEMS_ORDER_CANONICAL || collision_seen) {
-			std::vector<Rec> recs = split_records(raw);
+			std::vector<Rec> recs = split_records(raw, n_flat);
 			std::sort(recs.begin(), recs.end(), rec_less);
 			recs.erase(std::unique(recs.begin(), recs.end(), rec_equal), recs.end());
-			out.flat.reserve(raw.size());
-			for (const Rec& r2 : recs) out.flat.insert(out.flat.end(), r2.p, r2.p + r2.size());
+			out.flat.vec.reserve(n_flat);
+			for (const Rec& r2 : recs) out.flat.vec.insert(out.flat.vec.end(), r2.p, r2.p + r2.size());
+			out.flat.release();
 			out.n_matches = recs.size();
 		} else {
-			out.flat.swap(raw);
 			out.n_matches = n_comp;
 		}
 		out.mem_count = out.n_matches;
@@ -1052,7 +1087,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 
 	// emitted records in component order: record r starts at raw[rec_start[r]]
 	std::vector<size_t> rec_start;
-	for (size_t i = 0; i < raw.size(); i += (size_t)raw[i] + 2) rec_start.push_back(i);
+	for (size_t i = 0; i < n_flat; i += (size_t)raw[i] + 2) rec_start.push_back(i);
 
 	std::vector<std::vector<Entry*>> table(table_size);
 	std::vector<std::unique_ptr<Entry>> stored;
@@ -1080,7 +1115,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 			continue;
 		}
 		// "ExtendMatch": the extended form of this hit is the component the device computed for it
-		const int64_t* rec = raw.data() + rec_start[h_rec[h]];
+		const int64_t* rec = raw + rec_start[h_rec[h]];
 		auto e = std::make_unique<Entry>();
 		e->seqcount = (uint32_t)rec[0];
 		e->len = rec[1];
@@ -1095,10 +1130,11 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	// MemHash::GetMatchList (MemHash.h:183-203): buckets in order, front to back
 	for (auto& bucket : table)
 		for (Entry* e : bucket) {
-			out.flat.push_back(e->seqcount);
-			out.flat.push_back(e->len);
-			out.flat.insert(out.flat.end(), e->start, e->start + e->seqcount);
+			out.flat.vec.push_back(e->seqcount);
+			out.flat.vec.push_back(e->len);
+			out.flat.vec.insert(out.flat.vec.end(), e->start, e->start + e->seqcount);
 		}
+	out.flat.release();  // the stored entries pointed into the raw buffer until here
 	out.n_matches = out.mem_count;
 }
 

@@ -15,15 +15,15 @@
 //   4. reorder through shared memory so every digit's run leaves the CTA as one contiguous segment.
 // Tiles take their index from an atomic ticket, which guarantees that all predecessors of a running
 // tile are themselves running or finished (forward progress of the look-back).
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mems {
 
 constexpr int kRadix = 256;
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 16;
-constexpr int kTile = kSortThreads * kSortItems;  // 4096 pairs per CTA
+constexpr int kTile = 4096;  // pairs per CTA
 
 constexpr uint32_t kFlagPartial = 0x40000000u;
 constexpr uint32_t kFlagInclusive = 0x80000000u;
@@ -55,18 +55,38 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 	asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <class KeyT>
-__global__ void __launch_bounds__(kSortThreads, 2)
+// THREADS x ITEMS = kTile.  The kernel is bound by the latency of its shared-memory ranking chain, not by
+// HBM (ncu, profiles/r01_*): what buys throughput is resident warps, so the register footprint is kept
+// small — ranks are 16-bit, values are not loaded until the reorder step — and MINB CTAs share an SM.
+// lanes of the warp holding the same 8-bit digit.  MATCH.ANY is a single instruction but occupies its pipe for
+// tens of cycles; eight VOTEs plus a little logic (the digit is <= 8 bits) issue at full rate.
+template <bool BALLOT>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
+	if (!BALLOT) return __match_any_sync(0xffffffffu, d);
+	uint32_t peers = 0xffffffffu;
+#pragma unroll
+	for (int b = 0; b < 8; ++b) {
+		const bool bit = (d >> b) & 1u;
+		const uint32_t m = __ballot_sync(0xffffffffu, bit);
+		peers &= bit ? m : ~m;
+	}
+	return peers;
+}
+
+template <class KeyT, int THREADS, int MINB, bool BALLOT = false>
+__global__ void __launch_bounds__(THREADS, MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t digit_mask,
                 const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+	constexpr int WARPS = THREADS / 32;
+	constexpr int ITEMS = kTile / THREADS;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
 	uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * kTile);
-	__shared__ uint32_t s_warp_cnt[kSortWarps][kRadix];
+	__shared__ uint16_t s_warp_cnt[WARPS][kRadix];  // per-warp digit counts (<= 32*ITEMS), then exclusive over warps
 	__shared__ uint32_t s_digit_excl[kRadix];
 	__shared__ uint32_t s_global_base[kRadix];
-	__shared__ uint32_t s_warp_tot[kSortWarps];
+	__shared__ uint32_t s_warp_tot[8];
 	__shared__ uint32_t s_tile;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -77,33 +97,26 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 	const uint32_t tile_base = tile * (uint32_t)kTile;
 	const uint32_t n_valid = n - tile_base < (uint32_t)kTile ? n - tile_base : (uint32_t)kTile;
 
-	KeyT key[kSortItems];
-	uint32_t val[kSortItems];
-	uint16_t rank[kSortItems];
-	const uint32_t warp_base = warp * (32 * kSortItems);
+	KeyT key[ITEMS];
+	uint16_t rank[ITEMS];
+	const uint32_t warp_base = warp * (32 * ITEMS);
 #pragma unroll
-	for (int i = 0; i < kSortItems; ++i) {
-		uint32_t local = warp_base + i * 32 + lane;
-		if (local < n_valid) {
-			key[i] = keys_in[tile_base + local];
-			val[i] = vals_in[tile_base + local];
-		} else {
-			key[i] = ~(KeyT)0;
-			val[i] = 0;
-		}
+	for (int i = 0; i < ITEMS; ++i) {
+		const uint32_t local = warp_base + i * 32 + lane;
+		key[i] = local < n_valid ? keys_in[tile_base + local] : ~(KeyT)0;
 	}
 	// ---- rank inside the warp, in memory order
 	const uint32_t lanemask_lt = (1u << lane) - 1u;
 #pragma unroll
-	for (int i = 0; i < kSortItems; ++i) {
-		uint32_t local = warp_base + i * 32 + lane;
-		uint32_t d = local < n_valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
-		uint32_t peers = __match_any_sync(0xffffffffu, d);
-		int leader = __ffs(peers) - 1;
+	for (int i = 0; i < ITEMS; ++i) {
+		const uint32_t local = warp_base + i * 32 + lane;
+		const uint32_t d = local < n_valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
+		const uint32_t peers = digit_peers<BALLOT>(d);
+		const int leader = __ffs(peers) - 1;
 		uint32_t base = 0;
 		if (lane == leader) {
 			base = s_warp_cnt[warp][d];
-			s_warp_cnt[warp][d] = base + __popc(peers);
+			s_warp_cnt[warp][d] = (uint16_t)(base + __popc(peers));
 		}
 		base = __shfl_sync(0xffffffffu, base, leader);
 		rank[i] = (uint16_t)(base + __popc(peers & lanemask_lt));
@@ -111,34 +124,35 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 	}
 	__syncthreads();
 	// ---- thread d owns digit d: exclusive scan over warps, tile count, look-back
-	{
-		const int d = tid;
+	uint32_t count = 0;
+	if (tid < kRadix) {
 		uint32_t sum = 0;
 #pragma unroll
-		for (int w = 0; w < kSortWarps; ++w) {
-			uint32_t c = s_warp_cnt[w][d];
-			s_warp_cnt[w][d] = sum;
+		for (int w = 0; w < WARPS; ++w) {
+			const uint32_t c = s_warp_cnt[w][tid];
+			s_warp_cnt[w][tid] = (uint16_t)sum;
 			sum += c;
 		}
 		// padding items of the last tile were ranked as digit 255, after every real item
-		uint32_t count = sum - (d == kRadix - 1 ? (uint32_t)kTile - n_valid : 0u);
-		// exclusive scan of count over the 256 digits
+		count = sum - (tid == kRadix - 1 ? (uint32_t)kTile - n_valid : 0u);
 		uint32_t incl = count;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
 			if (lane >= o) incl += t;
 		}
 		if (lane == 31) s_warp_tot[warp] = incl;
-		__syncthreads();
+		s_digit_excl[tid] = incl - count;  // exclusive inside this warp's 32 digits; warp offsets added below
+	}
+	__syncthreads();
+	if (tid < kRadix) {
 		uint32_t woff = 0;
 #pragma unroll
-		for (int w = 0; w < kSortWarps; ++w)
+		for (int w = 0; w < kRadix / 32; ++w)
 			if (w < warp) woff += s_warp_tot[w];
-		const uint32_t digit_excl = woff + incl - count;
-
+		const uint32_t digit_excl = s_digit_excl[tid] + woff;
 		uint32_t excl = 0;
-		uint32_t* my_status = status + (size_t)tile * kRadix + d;
+		uint32_t* my_status = status + (size_t)tile * kRadix + tid;
 		if (tile == 0) {
 			st_volatile_u32(my_status, count | kFlagInclusive);
 		} else {
@@ -155,27 +169,28 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 			}
 			st_volatile_u32(my_status, (excl + count) | kFlagInclusive);
 		}
-		s_digit_excl[d] = digit_excl;
-		s_global_base[d] = bin_base[d] + excl - digit_excl;  // + tile-local sorted index = global index
+		s_digit_excl[tid] = digit_excl;
+		s_global_base[tid] = bin_base[tid] + excl - digit_excl;  // + tile-local sorted index = global index
 	}
 	__syncthreads();
-	// ---- reorder through shared memory
+	// ---- reorder through shared memory (values are loaded only now: one register live per value)
 #pragma unroll
-	for (int i = 0; i < kSortItems; ++i) {
-		uint32_t local = warp_base + i * 32 + lane;
-		uint32_t d = local < n_valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
-		uint32_t pos = s_digit_excl[d] + s_warp_cnt[warp][d] + rank[i];
+	for (int i = 0; i < ITEMS; ++i) {
+		const uint32_t local = warp_base + i * 32 + lane;
+		const bool valid = local < n_valid;
+		const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
+		const uint32_t pos = s_digit_excl[d] + s_warp_cnt[warp][d] + rank[i];
 		s_keys[pos] = key[i];
-		s_vals[pos] = val[i];
+		s_vals[pos] = valid ? vals_in[tile_base + local] : 0u;
 	}
 	__syncthreads();
 #pragma unroll
-	for (int k = 0; k < kSortItems; ++k) {
-		uint32_t idx = k * kSortThreads + tid;
+	for (int k = 0; k < ITEMS; ++k) {
+		const uint32_t idx = k * THREADS + tid;
 		if (idx < n_valid) {
-			KeyT kk = s_keys[idx];
-			uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
-			uint32_t g = s_global_base[d] + idx;
+			const KeyT kk = s_keys[idx];
+			const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
+			const uint32_t g = s_global_base[d] + idx;
 			keys_out[g] = kk;
 			vals_out[g] = s_vals[idx];
 		}
@@ -200,6 +215,12 @@ __global__ void scan_bins_kernel(const uint32_t* __restrict__ hist, uint32_t* __
 	bin_base[blockIdx.x * kRadix + tid] = woff + incl - c;
 }
 
+template <class K>
+static const K* first_arg_of(void (*)(const K*, const uint32_t*, K*, uint32_t*, uint32_t, int, uint32_t, const uint32_t*, uint32_t*,
+                                      uint32_t*)) {
+	return nullptr;
+}
+
 int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], uint64_t n, const SortPlan& plan,
                      uint32_t* d_hist, const char* prof_name, const void* first_keys_in) {
 	if (n == 0) return 0;
@@ -217,29 +238,36 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 	}
 	const size_t key_bytes = key64 ? 8 : 4;
 	const size_t smem = (key_bytes + 4) * kTile;
-	static bool attr_set = false;
-	if (!attr_set) {
-		MEMS_CUDA(cudaFuncSetAttribute(onesweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                               (int)(12 * kTile)));
-		MEMS_CUDA(cudaFuncSetAttribute(onesweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                               (int)(8 * kTile)));
-		attr_set = true;
+	// launch configuration (measured on B200, tools/sort_bench.py): 256 threads x 16 pairs, 5 CTAs per SM for
+	// 32-bit keys and 4 for 64-bit keys; MEMS_SORT_VARIANT selects the alternatives for experiments
+	static int variant = -1;
+	if (variant < 0) {
+		const char* e = getenv("MEMS_SORT_VARIANT");
+		variant = e ? atoi(e) : 0;
 	}
-	int cur = 0;
-	for (int q = 0; q < P; ++q) {
+	auto launch = [&](auto kern, int threads, int q, int cur) {
+		MEMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		uint32_t* st = status.p + status_words * q;
 		uint32_t* ticket = status.p + status_words * P + q;
 		const uint32_t mask = (1u << plan.bits[q]) - 1u;
-		KernelScope ks(c, prof_name, 2.0 * (double)n * (double)(key_bytes + 4));
-		if (key64)
-			onesweep_kernel<uint64_t><<<n_tiles, kSortThreads, smem, c->stream>>>(
-			    (const uint64_t*)(q == 0 && first_keys_in ? first_keys_in : d_keys[cur]), d_vals[cur], (uint64_t*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n,
-			    plan.shift[q], mask, bin_base.p + q * kRadix, st, ticket);
-		else
-			onesweep_kernel<uint32_t><<<n_tiles, kSortThreads, smem, c->stream>>>(
-			    (const uint32_t*)(q == 0 && first_keys_in ? first_keys_in : d_keys[cur]), d_vals[cur], (uint32_t*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n,
-			    plan.shift[q], mask, bin_base.p + q * kRadix, st, ticket);
+		using K = std::remove_const_t<std::remove_pointer_t<decltype(first_arg_of(kern))>>;
+		kern<<<n_tiles, threads, smem, c->stream>>>((const K*)(q == 0 && first_keys_in ? first_keys_in : d_keys[cur]), d_vals[cur],
+		                                            (K*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n, plan.shift[q], mask,
+		                                            bin_base.p + q * kRadix, st, ticket);
 		MEMS_CUDA(cudaGetLastError());
+	};
+	int cur = 0;
+	for (int q = 0; q < P; ++q) {
+		KernelScope ks(c, prof_name, 2.0 * (double)n * (double)(key_bytes + 4));
+		if (key64) {
+			if (variant == 1) launch(onesweep_kernel<uint64_t, 512, 3, true>, 512, q, cur);
+			else if (variant == 2) launch(onesweep_kernel<uint64_t, 256, 3, true>, 256, q, cur);
+			else launch(onesweep_kernel<uint64_t, 256, 4, true>, 256, q, cur);
+		} else {
+			if (variant == 1) launch(onesweep_kernel<uint32_t, 512, 3, true>, 512, q, cur);
+			else if (variant == 2) launch(onesweep_kernel<uint32_t, 256, 4, true>, 256, q, cur);
+			else launch(onesweep_kernel<uint32_t, 256, 5, true>, 256, q, cur);
+		}
 		cur ^= 1;
 	}
 	return cur;
