@@ -1,0 +1,81 @@
+// libMems/MatchList.h façade — GenericMatchList<Match*> with seq_table / sml_table (MatchList.h:33-116)
+// and CreateMemorySMLs (MatchList.h:408-435), which here builds all lists as ONE device batch.
+#pragma once
+#include <cmath>
+#include <ostream>
+#include <string>
+#include <vector>
+
+#include "libMems/Match.h"
+#include "libMems/SortedMerList.h"
+
+namespace mems {
+
+template <class Sequence = genome::gnSequence>
+class GenericMatchList : public std::vector<Match*> {
+public:
+	std::vector<std::string> sml_filename, seq_filename;
+	std::vector<SortedMerList*> sml_table;
+	std::vector<Sequence*> seq_table;
+
+	static unsigned GetDefaultMerSize(const std::vector<Sequence*>& seq_table) {  // MatchList.h:352-357
+		uint64_t total = 0;
+		for (auto* s : seq_table) total += s->length();
+		return getDefaultSeedWeight(seq_table.empty() ? 0 : total / seq_table.size());
+	}
+	void CreateMemorySMLs(unsigned mer_size, std::ostream* log_stream, int seed_rank = 0) {
+		if (mer_size == 0) {
+			mer_size = GetDefaultMerSize(seq_table);
+			if (log_stream) (*log_stream) << "Using " << mer_size << "-mers for initial seeds\n";
+		}
+		const uint64_t seed = (uint64_t)getSeed((int)mer_size, seed_rank);
+		const size_t n = seq_table.size();
+		std::vector<std::vector<char>> bufs(n);
+		std::vector<const char*> ptrs(n);
+		std::vector<uint64_t> lens(n);
+		for (size_t i = 0; i < n; ++i) {
+			lens[i] = seq_table[i]->length();
+			bufs[i].resize(lens[i] ? lens[i] : 1);
+			if (lens[i]) seq_table[i]->ToArray(bufs[i].data(), lens[i]);
+			ptrs[i] = bufs[i].data();
+		}
+		if (log_stream) (*log_stream) << "Creating sorted mer lists\n";
+		std::vector<mems_sml_t> handles(n);
+		Context::check(mems_sml_create_batch(Context::get(), (int)n, ptrs.data(), lens.data(), seed, handles.data()));
+		for (size_t i = 0; i < n; ++i) {
+			DNAMemorySML* sml = new DNAMemorySML();
+			sml->adopt(handles[i]);
+			sml_table.push_back(sml);
+		}
+	}
+	void Clear() {  // MatchList.h:438-457
+		for (auto* s : seq_table) delete s;
+		for (auto* s : sml_table) delete s;
+		for (auto* m : *this) m->Free();
+		seq_table.clear();
+		sml_table.clear();
+		this->clear();
+		seq_filename.clear();
+		sml_filename.clear();
+	}
+	void MultiplicityFilter(unsigned mult) {  // MatchList.h:637-650
+		size_t cur = 0;
+		for (size_t i = 0; i < this->size(); ++i) {
+			if ((*this)[i]->Multiplicity() == mult) (*this)[cur++] = (*this)[i];
+			else (*this)[i]->Free();
+		}
+		this->resize(cur);
+	}
+	void LengthFilter(uint64_t length) {  // MatchList.h:652-664
+		size_t cur = 0;
+		for (size_t i = 0; i < this->size(); ++i) {
+			if ((*this)[i]->Length() >= length) (*this)[cur++] = (*this)[i];
+			else (*this)[i]->Free();
+		}
+		this->resize(cur);
+	}
+};
+
+typedef GenericMatchList<> MatchList;
+
+}  // namespace mems

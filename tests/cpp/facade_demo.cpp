@@ -1,0 +1,41 @@
+// facade_demo.cpp — the anchoring call sequence of the reference's callers (MatchList::CreateMemorySMLs +
+// MemHash::FindMatches, e.g. ProgressiveAligner.cpp:636-653) written against the façade headers.
+// Usage: facade_demo <memhash|repeat> <seed_weight> <raw-sequence-file>...   prints "len\tstart0\tstart1..." lines.
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <string>
+
+#include "libMems/MemHash.h"
+
+using namespace mems;
+
+int main(int argc, char** argv) {
+	if (argc < 4) return 2;
+	const std::string mode = argv[1];
+	const unsigned weight = (unsigned)atoi(argv[2]);
+	try {
+		MatchList ml;
+		for (int i = 3; i < argc; ++i) {
+			std::ifstream f(argv[i], std::ios::binary);
+			std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+			ml.seq_table.push_back(new genome::gnSequence(s));
+			ml.seq_filename.push_back(argv[i]);
+		}
+		ml.CreateMemorySMLs(weight, &std::cerr);
+		std::cerr << "seed " << std::hex << ml.sml_table[0]->Seed() << std::dec << " length " << ml.sml_table[0]->SeedLength()
+		          << " sml[0] = {" << (*ml.sml_table[0])[0].position << ", " << (*ml.sml_table[0])[0].mer << "}\n";
+		MemHash* mh = mode == "repeat" ? new RepeatHash() : new MemHash();
+		mh->SetOutputOrder(MEMS_ORDER_REFERENCE);
+		mh->FindMatches(ml);
+		std::cerr << "MemCount " << mh->MemCount() << " MemCollisionCount " << mh->MemCollisionCount() << "\n";
+		for (Match* m : ml) std::cout << *m << "\n";
+		mh->Clear();
+		delete mh;
+		ml.Clear();
+	} catch (const MemsException& e) {
+		std::cerr << "error " << e.code << ": " << e.what() << "\n";
+		return 1;
+	}
+	return 0;
+}
