@@ -132,6 +132,27 @@ int mems_matches_copy(mems_matches_t m, int64_t* flat_out);
 const int64_t* mems_matches_data(mems_matches_t m);
 void mems_matches_destroy(mems_matches_t m);
 
+/* ---- sharded match finding: one process per GPU, NCCL over NVLink ----
+ * Every rank extracts a contiguous block of the sequences; seed space is range-partitioned (owners balanced by
+ * the global key histogram) and one all-to-all delivers each seed range to its owner, which finds that range's
+ * hits; hits are re-partitioned by diagonal so that extension is disjoint across ranks.  Design precedent in the
+ * reference: ParallelMemHash's seed-range chunks (ParallelMemHash.cpp:42-121, never built). */
+typedef struct mems_comm* mems_comm_t;
+/* rank 0 creates the 128-byte NCCL id and hands it to the other ranks by any host channel */
+int mems_comm_unique_id(char* id_out /* 128 bytes */);
+int mems_comm_create(mems_ctx_t ctx, const char* id /* 128 bytes */, int rank, int world, mems_comm_t* out);
+void mems_comm_destroy(mems_comm_t comm);
+/* the block of sequences [first, first+count) rank `rank` must supply (host arithmetic) */
+int mems_shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count);
+/* owner rank of each of the 256 top-key-digit buckets given their global counts (host arithmetic) */
+int mems_shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256);
+/* Collective: all ranks call it with the same n_seqs / lens / seed / params; seqs[g] must be valid for the
+ * sequences of this rank's block (others may be NULL).  MEMS_MODE_MEMHASH, ORDER_ANY or ORDER_CANONICAL.
+ * *out holds THIS rank's share of the distinct matches; the union over ranks is the MatchList. */
+int mems_find_matches_sharded(mems_ctx_t ctx, mems_comm_t comm, int n_seqs, const char* const* seqs,
+                              const uint64_t* lens, uint64_t seed, const mems_match_params_t* params,
+                              mems_matches_t* out);
+
 /* ---- measurement ---- */
 /* With profiling on, every kernel launch is bracketed by CUDA events on the context's stream. */
 int mems_profile_enable(mems_ctx_t ctx, int on);

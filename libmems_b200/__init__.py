@@ -53,7 +53,8 @@ EXPORTS = [
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
     "mems_sml_packed", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
-    "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
+    "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
+    "mems_shard_bucket_owners", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
 ]
 
 _lib = None
@@ -98,6 +99,14 @@ def load():
     lib.mems_matches_data.argtypes = [_vp]
     lib.mems_matches_data.restype = ctypes.POINTER(ctypes.c_int64)
     lib.mems_matches_destroy.argtypes = [_vp]
+    lib.mems_comm_unique_id.argtypes = [_vp]
+    lib.mems_comm_create.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]
+    lib.mems_comm_destroy.argtypes = [_vp]
+    lib.mems_shard_sequence_range.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                              ctypes.POINTER(ctypes.c_int)]
+    lib.mems_shard_bucket_owners.argtypes = [_vp, ctypes.c_int, _vp]
+    lib.mems_find_matches_sharded.argtypes = [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _u64,
+                                              ctypes.POINTER(MatchParams), ctypes.POINTER(_vp)]
     lib.mems_profile_enable.argtypes = [_vp, ctypes.c_int]
     lib.mems_profile_reset.argtypes = [_vp]
     lib.mems_profile_get.argtypes = [_vp, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
@@ -122,6 +131,34 @@ def get_seed_weight(seed):
 
 def get_default_seed_weight(avg_len):
     return int(load().mems_get_default_seed_weight(int(avg_len)))
+
+
+def shard_sequence_range(n_seqs, rank, world):
+    """(first, count): the contiguous block of sequences a rank extracts when the path is sharded."""
+    f, c = ctypes.c_int(), ctypes.c_int()
+    rc = load().mems_shard_sequence_range(n_seqs, rank, world, ctypes.byref(f), ctypes.byref(c))
+    if rc:
+        raise MemsError(rc, "bad shard arguments")
+    return f.value, c.value
+
+
+def shard_bucket_owners(hist256, world):
+    """Owner rank of each of the 256 top-key-digit buckets, balanced by the global histogram."""
+    h = np.ascontiguousarray(hist256, dtype=np.uint64)
+    assert h.size == 256
+    out = np.zeros(256, np.uint8)
+    rc = load().mems_shard_bucket_owners(h.ctypes.data, world, out.ctypes.data)
+    if rc:
+        raise MemsError(rc, "bad shard arguments")
+    return out
+
+
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    rc = load().mems_comm_unique_id(ctypes.addressof(buf))
+    if rc:
+        raise MemsError(rc, load().mems_last_error(None).decode())
+    return buf.raw
 
 
 def _host_ptr(seq):
@@ -224,6 +261,35 @@ class Context:
         flat._keep = keep
         return flat, d
 
+    # -- sharded (one process per GPU) ----------------------------------------------------------------
+    def create_comm(self, unique_id, rank, world):
+        h = _vp()
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        self._check(self.lib.mems_comm_create(self.h, ctypes.addressof(buf), rank, world, ctypes.byref(h)))
+        return Communicator(self, h, rank, world)
+
+    def find_matches_sharded(self, comm, seqs, lens, seed, mode=MODE_MEMHASH, order=ORDER_ANY):
+        """Collective.  seqs: list over ALL sequences; entries outside this rank's block may be None.
+        Returns this rank's share of the matches (flat, info)."""
+        n = len(lens)
+        parts = [(_host_ptr(s) if s is not None else (0, 0, None)) for s in seqs]
+        ptrs = (_vp * n)(*[p[0] for p in parts])
+        ls = (_u64 * n)(*[int(x) for x in lens])
+        params = MatchParams(mode, order, 0, 0)
+        h = _vp()
+        self._check(self.lib.mems_find_matches_sharded(self.h, comm.h, n, ptrs, ls, seed, ctypes.byref(params),
+                                                       ctypes.byref(h)))
+        keep = _MatchHandle(self.lib, h)
+        info = MatchesInfo()
+        self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
+        d = {k: int(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        if info.n_flat == 0:
+            return np.zeros(0, np.int64), d
+        view = np.ctypeslib.as_array(self.lib.mems_matches_data(h), shape=(int(info.n_flat),))
+        flat = view.view(_OwnedArray)
+        flat._keep = keep
+        return flat, d
+
     # -- measurement ----------------------------------------------------------------------------------
     def profile_enable(self, on=True):
         self._check(self.lib.mems_profile_enable(self.h, 1 if on else 0))
@@ -240,6 +306,24 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.mems_launch_count(self.h))
+
+
+class Communicator:
+    """NCCL communicator of the sharded path (one per process / GPU)."""
+
+    def __init__(self, ctx, handle, rank, world):
+        self.ctx, self.h, self.rank, self.world = ctx, handle, rank, world
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.mems_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def flat_to_matches(flat):

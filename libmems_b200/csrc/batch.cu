@@ -14,13 +14,14 @@
 
 namespace mems {
 
-static int bits_for(uint64_t max_value) {  // bits needed to store values 0..max_value
+int bits_for(uint64_t max_value) {  // bits needed to store values 0..max_value
 	int b = 1;
 	while (b < 64 && (max_value >> b)) ++b;
 	return b;
 }
 
-static void layout_batch(Batch& b, const std::vector<uint64_t>& lens) {
+static void layout_batch(Batch& b, const std::vector<uint64_t>& lens, uint32_t tag0 = 0, int force_pos_bits = 0,
+                         int force_seq_bits = 0) {
 	b.n_seqs = (int)lens.size();
 	b.meta.resize(b.n_seqs);
 	uint64_t byte_off = 0, word_off = 0, seed_off = 0;
@@ -34,6 +35,8 @@ static void layout_batch(Batch& b, const std::vector<uint64_t>& lens) {
 		m.byte_off = byte_off;
 		m.word_off = word_off;
 		m.seed_off = seed_off;
+		m.tag = tag0 + (uint32_t)g;
+		m.pad_ = 0;
 		byte_off += (lens[g] + 15) / 16 * 16;
 		word_off += ((lens[g] + 15) / 16 + 2 + 3) / 4 * 4;  // keep every sequence 16-byte aligned
 		seed_off += m.n_seeds;
@@ -42,6 +45,8 @@ static void layout_batch(Batch& b, const std::vector<uint64_t>& lens) {
 	b.n_total = seed_off;
 	b.pos_bits = bits_for(max_seeds ? max_seeds - 1 : 0);
 	b.seq_bits = b.n_seqs > 1 ? bits_for((uint64_t)b.n_seqs - 1) : 0;
+	if (force_pos_bits) b.pos_bits = force_pos_bits;
+	if (force_seq_bits) b.seq_bits = force_seq_bits;
 	if (b.pos_bits + b.seq_bits > 32)
 		throw Error(MEMS_ERR_UNSUPPORTED,
 		            "sequence count x longest sequence does not fit the 32-bit (sequence, position) tag; "
@@ -77,15 +82,16 @@ static void extract_and_sort(Batch& b) {
 	}
 }
 
-std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
-                                              const uint64_t* lens, uint64_t seed) {
-	if (n_seqs < 1) throw Error(MEMS_ERR_INVALID, "need at least one sequence");
+std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
+                                                const uint64_t* lens, uint64_t seed, uint32_t tag0, int pos_bits,
+                                                int seq_bits) {
 	auto b = std::make_shared<Batch>();
 	b->ctx = ctx;
 	b->sd = make_seed_desc(seed);
 	Ctx* c = ctx.get();
 	MEMS_CUDA(cudaSetDevice(c->device));
-	layout_batch(*b, std::vector<uint64_t>(lens, lens + n_seqs));
+	layout_batch(*b, std::vector<uint64_t>(lens, lens + n_seqs), tag0, pos_bits, seq_bits);
+	if (n_seqs == 0) return b;
 	const SeqMeta& last = b->meta.back();
 	const uint64_t total_bytes = last.byte_off + ((uint64_t)last.n_bases + 15) / 16 * 16;
 	const uint64_t total_words = last.word_off + (((uint64_t)last.n_bases + 15) / 16 + 2 + 3) / 4 * 4;
@@ -101,13 +107,20 @@ std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_se
 			// cudaMemcpyDefault: seqs[g] may be pageable or pinned host memory, or already a device pointer
 			MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyDefault, c->stream));
 	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
-	extract_and_sort(*b);
 	uint32_t gap = 0;
 	MEMS_CUDA(cudaMemcpyAsync(&gap, gap_flag.p, sizeof gap, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 	if (gap)
 		throw Error(MEMS_ERR_GAP, "Gap in genome sequence: input sequences must be unaligned and ungapped "
 		                          "(SortedMerList.cpp:433-437)");
+	return b;
+}
+
+std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
+                                              const uint64_t* lens, uint64_t seed) {
+	if (n_seqs < 1) throw Error(MEMS_ERR_INVALID, "need at least one sequence");
+	auto b = prepare_batch_from_ascii(ctx, n_seqs, seqs, lens, seed, 0, 0, 0);
+	extract_and_sort(*b);
 	return b;
 }
 

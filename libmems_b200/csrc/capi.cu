@@ -282,6 +282,59 @@ const int64_t* mems_matches_data(mems_matches_t m) { return m ? m->r.flat.data()
 
 void mems_matches_destroy(mems_matches_t m) { delete m; }
 
+// ------------------------------------------------------------------------------------------------ sharded
+struct mems_comm {
+	Comm* c;
+};
+
+int mems_comm_unique_id(char* id_out) {
+	if (!id_out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	return guarded(nullptr, [&] { comm_unique_id(id_out); });
+}
+
+int mems_comm_create(mems_ctx_t ctx, const char* id, int rank, int world, mems_comm_t* out) {
+	if (!ctx || !id || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	return guarded(ctx->c.get(), [&] { *out = new mems_comm{comm_create(ctx->c, id, rank, world)}; });
+}
+
+void mems_comm_destroy(mems_comm_t comm) {
+	if (!comm) return;
+	comm_destroy(comm->c);
+	delete comm;
+}
+
+int mems_shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count) {
+	if (!first || !count || world < 1 || rank < 0 || rank >= world || n_seqs < 0) return fail(nullptr, MEMS_ERR_INVALID, "bad arguments");
+	shard_sequence_range(n_seqs, rank, world, first, count);
+	return MEMS_OK;
+}
+
+int mems_shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256) {
+	if (!hist256 || !owner256 || world < 1 || world > 256) return fail(nullptr, MEMS_ERR_INVALID, "bad arguments");
+	shard_bucket_owners(hist256, world, owner256);
+	return MEMS_OK;
+}
+
+int mems_find_matches_sharded(mems_ctx_t ctx, mems_comm_t comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
+                              uint64_t seed, const mems_match_params_t* params, mems_matches_t* out) {
+	if (!ctx) return fail(nullptr, MEMS_ERR_INVALID, "null context");
+	Ctx* c = ctx->c.get();
+	if (!comm || !seqs || !lens || !out) return fail(c, MEMS_ERR_INVALID, "bad arguments");
+	return guarded(c, [&] {
+		mems_match_params_t p;
+		memset(&p, 0, sizeof p);
+		if (params) p = *params;
+		auto* m = new mems_matches();
+		try {
+			find_matches_sharded(ctx->c, comm->c, n_seqs, seqs, lens, seed, p.mode, p.order, m->r);
+		} catch (...) {
+			delete m;
+			throw;
+		}
+		*out = m;
+	});
+}
+
 // ------------------------------------------------------------------------------------------------ measurement
 int mems_profile_enable(mems_ctx_t ctx, int on) {
 	if (!ctx) return fail(nullptr, MEMS_ERR_INVALID, "null context");

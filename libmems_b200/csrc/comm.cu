@@ -1,0 +1,155 @@
+// comm.cu — the exchange steps of the sharded path over NCCL (NVLink 5 / NVSwitch between the B200s of a node).
+// libnccl is bound at run time with dlopen: inside a torch process that is the NCCL torch already loaded, in a
+// plain C++ host the system libnccl.so.2.  Only four collectives are needed: a small all-reduce (digit
+// histogram), a small all-gather (count matrix), all-to-all-v built from grouped ncclSend/ncclRecv (seed records
+// by key range, hits by diagonal), and an all-gather-v built from grouped broadcasts (position-ordered keys).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "mems_b200.h"
+
+namespace mems {
+
+namespace {
+struct NcclApi {
+	void* lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi& nccl() {
+	static NcclApi api;
+	if (api.lib) return api;
+	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the copy torch (or the host) already loaded
+	if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) throw Error(MEMS_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define MEMS_NCCL_SYM(name)                                                                    \
+	api.name = reinterpret_cast<decltype(api.name)>(dlsym(h, "nccl" #name));                  \
+	if (!api.name) throw Error(MEMS_ERR_NCCL, "libnccl lacks nccl" #name);
+	MEMS_NCCL_SYM(GetUniqueId)
+	MEMS_NCCL_SYM(CommInitRank)
+	MEMS_NCCL_SYM(CommDestroy)
+	MEMS_NCCL_SYM(GroupStart)
+	MEMS_NCCL_SYM(GroupEnd)
+	MEMS_NCCL_SYM(Send)
+	MEMS_NCCL_SYM(Recv)
+	MEMS_NCCL_SYM(AllReduce)
+	MEMS_NCCL_SYM(AllGather)
+	MEMS_NCCL_SYM(Broadcast)
+	MEMS_NCCL_SYM(GetErrorString)
+#undef MEMS_NCCL_SYM
+	api.lib = h;
+	return api;
+}
+
+void check(ncclResult_t r, const char* what) {
+	if (r != ncclSuccess) throw Error(MEMS_ERR_NCCL, std::string(what) + ": " + nccl().GetErrorString(r));
+}
+}  // namespace
+
+struct Comm {
+	std::shared_ptr<Ctx> ctx;
+	ncclComm_t comm = nullptr;
+	int rank = 0, world = 1;
+	~Comm() {
+		if (comm) nccl().CommDestroy(comm);
+	}
+};
+
+int Comm_rank(const Comm* c) { return c->rank; }
+int Comm_world(const Comm* c) { return c->world; }
+
+void comm_unique_id(char* id128) {
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+	memcpy(id128, &id, 128);
+}
+
+Comm* comm_create(std::shared_ptr<Ctx> ctx, const char* id128, int rank, int world) {
+	if (world < 1 || rank < 0 || rank >= world) throw Error(MEMS_ERR_INVALID, "bad rank / world size");
+	MEMS_CUDA(cudaSetDevice(ctx->device));
+	auto* c = new Comm();
+	c->ctx = ctx;
+	c->rank = rank;
+	c->world = world;
+	ncclUniqueId id;
+	memcpy(&id, id128, 128);
+	try {
+		check(nccl().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
+	} catch (...) {
+		delete c;
+		throw;
+	}
+	return c;
+}
+
+void comm_destroy(Comm* c) { delete c; }
+
+// in-place sum of n u64 counters that live in device memory
+void comm_all_reduce_u64(Comm* c, uint64_t* d_buf, size_t n) {
+	if (c->world == 1) return;
+	check(nccl().AllReduce(d_buf, d_buf, n, ncclUint64, ncclSum, c->comm, c->ctx->stream), "ncclAllReduce");
+}
+
+// every rank contributes n u64 values; d_recv receives world * n (rank-major)
+void comm_all_gather_u64(Comm* c, const uint64_t* d_send, uint64_t* d_recv, size_t n) {
+	if (c->world == 1) {
+		MEMS_CUDA(cudaMemcpyAsync(d_recv, d_send, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->ctx->stream));
+		return;
+	}
+	check(nccl().AllGather(d_send, d_recv, n, ncclUint64, c->comm, c->ctx->stream), "ncclAllGather");
+}
+
+// all-to-all with per-peer element counts; buffers are laid out peer-major (offsets = prefix sums of the counts)
+void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts, void* d_recv, const uint64_t* recv_counts,
+                       size_t elem_bytes) {
+	const char* s = static_cast<const char*>(d_send);
+	char* r = static_cast<char*>(d_recv);
+	if (c->world == 1) {
+		if (send_counts[0])
+			MEMS_CUDA(cudaMemcpyAsync(r, s, send_counts[0] * elem_bytes, cudaMemcpyDeviceToDevice, c->ctx->stream));
+		return;
+	}
+	check(nccl().GroupStart(), "ncclGroupStart");
+	size_t so = 0, ro = 0;
+	for (int p = 0; p < c->world; ++p) {
+		if (send_counts[p]) check(nccl().Send(s + so, send_counts[p] * elem_bytes, ncclChar, p, c->comm, c->ctx->stream), "ncclSend");
+		if (recv_counts[p]) check(nccl().Recv(r + ro, recv_counts[p] * elem_bytes, ncclChar, p, c->comm, c->ctx->stream), "ncclRecv");
+		so += send_counts[p] * elem_bytes;
+		ro += recv_counts[p] * elem_bytes;
+	}
+	check(nccl().GroupEnd(), "ncclGroupEnd");
+}
+
+// all-gather with per-rank byte counts: rank p's bytes land at d_recv + offsets[p] on every rank
+void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t* byte_counts, const uint64_t* byte_offsets) {
+	char* r = static_cast<char*>(d_recv);
+	if (c->world == 1) {
+		if (byte_counts[0])
+			MEMS_CUDA(cudaMemcpyAsync(r + byte_offsets[0], d_send, byte_counts[0], cudaMemcpyDeviceToDevice, c->ctx->stream));
+		return;
+	}
+	check(nccl().GroupStart(), "ncclGroupStart");
+	for (int p = 0; p < c->world; ++p)
+		if (byte_counts[p])
+			check(nccl().Broadcast(p == c->rank ? d_send : nullptr, r + byte_offsets[p], byte_counts[p], ncclChar, p, c->comm,
+			                       c->ctx->stream),
+			      "ncclBroadcast");
+	check(nccl().GroupEnd(), "ncclGroupEnd");
+}
+
+}  // namespace mems

@@ -33,6 +33,8 @@ struct SeqMeta {
 	uint64_t seed_off;  // first index inside the batch's union key/value arrays
 	uint32_t n_bases;
 	uint32_t n_seeds;   // SMLLength: n_bases - L + 1, or 0
+	uint32_t tag;       // sequence id written into the values (index in the batch; global id when sharded)
+	uint32_t pad_;
 };
 
 struct Error : std::runtime_error {
@@ -185,11 +187,36 @@ struct Batch {
 };
 std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
                                               const uint64_t* lens, uint64_t seed);
+// layout + H2D + pack only (no keys yet).  tag0 = id of the first sequence; pos_bits/seq_bits > 0 override the
+// batch-local choice (sharded runs use the global ones).
+std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
+                                                const uint64_t* lens, uint64_t seed, uint32_t tag0, int pos_bits,
+                                                int seq_bits);
+int bits_for(uint64_t max_value);
 struct SeqRef {
 	const Batch* batch;
 	int index;
 };
 std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const std::vector<SeqRef>& seqs);
+
+// ---- comm.cu ---- (NCCL exchange steps of the sharded path)
+struct Comm;
+void comm_unique_id(char* id128);
+Comm* comm_create(std::shared_ptr<Ctx> ctx, const char* id128, int rank, int world);
+void comm_destroy(Comm* c);
+int Comm_rank(const Comm* c);
+int Comm_world(const Comm* c);
+void comm_all_reduce_u64(Comm* c, uint64_t* d_buf, size_t n);
+void comm_all_gather_u64(Comm* c, const uint64_t* d_send, uint64_t* d_recv, size_t n);
+void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts, void* d_recv, const uint64_t* recv_counts,
+                       size_t elem_bytes);
+void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t* byte_counts, const uint64_t* byte_offsets);
+
+// ---- sharding plan (host arithmetic, identical on every rank) ----
+// contiguous block of sequences a rank extracts: [first, first + count)
+void shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count);
+// owner rank of each of the 256 top-digit buckets, balanced by the global bucket histogram, contiguous ranges
+void shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256);
 
 // ---- kernels_match.cu ----
 // [SeqCount, Length, starts...] records on the host: either a page-locked buffer borrowed from the context
@@ -215,5 +242,7 @@ struct MatchResult {
 	uint32_t seq_count = 0, seed_length = 0;
 };
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out);
+void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
+                          uint64_t seed, int mode, int order, MatchResult& out);
 
 }  // namespace mems

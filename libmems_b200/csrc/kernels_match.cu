@@ -859,32 +859,22 @@ size_t bucket_lower_bound(const std::vector<Entry*>& v, const Entry& x) {
 }  // namespace
 
 
+// hits of one sorted union, in key order
+struct HitSet {
+	DevBuf<uint32_t> start;  // first union entry of the hit
+	DevBuf<uint16_t> len;    // entries in the hit (bit 15 is set later: strand of the first member)
+	uint32_t n = 0;
+	uint32_t max_run = 0;
+};
+
+// ---- stage A: equal-seed runs of a sorted union -> hits in key order
 template <class KeyT>
-static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
-	Ctx* c = b.ctx.get();
-	const uint32_t n = (uint32_t)b.n_total;
-	const int L = b.sd.L;
-	out.seq_count = (uint32_t)b.n_seqs;
-	out.seed_length = (uint32_t)L;
-	if (n < 2) return;
-
-	MatchArgs a;
-	a.keys = b.keys.p;
-	a.vals = b.vals.p;
-	a.n = n;
-	a.pos_bits = b.pos_bits;
-	a.pos_mask = b.pos_mask();
-	a.n_seqs = b.n_seqs;
-	a.mode = mode;
-	a.packed = b.packed.p;
-	a.meta = b.d_meta.p;
-	const KeyT* key_pos = reinterpret_cast<const KeyT*>(b.keys_by_pos.p);
-
-	// ---- 1. run scan -> hits in key order
+static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
+	const uint32_t n = a.n;
 	const uint32_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
 	DevBuf<uint16_t> run_info(c, n);
-	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 8);
-	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(uint32_t), c->stream));
+	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 2);
+	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(uint32_t), c->stream));
 	{
 		KernelScope ks(c, "run_scan", (double)n * (sizeof(KeyT) + 2.0));
 		run_scan_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, run_info.p, block_hits.p, scalars.p + 0);
@@ -894,18 +884,29 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	uint32_t h_scal[2];
 	MEMS_CUDA(cudaMemcpyAsync(h_scal, scalars.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
-	out.max_run = h_scal[0];
-	const uint32_t n_hits = h_scal[1];
-	out.n_hits = n_hits;
-	if (n_hits == 0) return;
-	DevBuf<uint32_t> hit_start(c, n_hits);
-	DevBuf<uint16_t> hit_len(c, n_hits);
+	hits.max_run = h_scal[0];
+	hits.n = h_scal[1];
+	if (hits.n == 0) return;
+	hits.start = DevBuf<uint32_t>(c, hits.n);
+	hits.len = DevBuf<uint16_t>(c, hits.n);
 	{
 		KernelScope ks(c, "hit_compact", (double)n * 2.0);
-		hit_compact_kernel<<<n_blocks, kScanBlock, 0, c->stream>>>(run_info.p, n, block_hits.p, hit_start.p, hit_len.p);
+		hit_compact_kernel<<<n_blocks, kScanBlock, 0, c->stream>>>(run_info.p, n, block_hits.p, hits.start.p, hits.len.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	run_info.reset();
+}
+
+// ---- stage B: hits (members readable through a.keys / a.vals) -> extended, distinct matches
+template <class KeyT>
+static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT* key_pos, int L, HitSet& hits, int order,
+                        uint32_t table_size, MatchResult& out) {
+	Ctx* c = ctx.get();
+	const int mode = a.mode;
+	const uint32_t n_hits = hits.n;
+	DevBuf<uint32_t>& hit_start = hits.start;
+	DevBuf<uint16_t>& hit_len = hits.len;
+	DevBuf<uint32_t> scalars(c, 8);
+	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(uint32_t), c->stream));
 
 	// ---- 2. describe + 3. sort by (diagonal hash, first-member position)
 	SortPlan plan = make_sort_plan(64);
@@ -948,7 +949,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	// one region then run together and find that region's keys in L2 instead of going to HBM one by one.
 	const uint32_t* seg_order;
 	{
-		SortPlan splan = make_sort_plan(b.pos_bits);
+		SortPlan splan = make_sort_plan(a.pos_bits);
 		DevBuf<uint32_t> shist(c, (size_t)splan.n_passes * 256);
 		launch_histogram(c, false, seg_x_a.p, n_seg, splan, shist.p);
 		void* skp[2] = {seg_x_a.p, seg_x_b.p};
@@ -1017,7 +1018,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	const uint32_t comp_blocks = (n_comp + 255) / 256;
 	{
 		KernelScope ks(c, "emit_size");
-		emit_size_kernel<<<comp_blocks, 256, 0, c->stream>>>(comp_rep.p, hid, hit_len.p, n_comp, mode, b.n_seqs, rec_size.p);
+		emit_size_kernel<<<comp_blocks, 256, 0, c->stream>>>(comp_rep.p, hid, hit_len.p, n_comp, mode, a.n_seqs, rec_size.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, rec_size.p, rec_off.p, n_comp, scalars.p + 5);
@@ -1030,7 +1031,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		MEMS_CUDA(cudaGetLastError());
 	}
 	// D2H straight into a page-locked buffer that the result object keeps (no pageable staging, no copy)
-	out.flat.owner = b.ctx;
+	out.flat.owner = ctx;
 	out.flat.pinned = (int64_t*)c->pinned_get((size_t)n_flat * sizeof(int64_t), &out.flat.pinned_cap);
 	out.flat.pinned_n = n_flat;
 	const int64_t* raw = out.flat.pinned;
@@ -1095,14 +1096,14 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	for (uint32_t h = 0; h < n_hits; ++h) {
 		const uint32_t m0 = h_off[h], m1 = h + 1 < n_hits ? h_off[h + 1] : n_mem;
 		Entry probe;
-		probe.seqcount = mode == MEMS_MODE_REPEAT ? (m1 - m0) : (uint32_t)b.n_seqs;
+		probe.seqcount = mode == MEMS_MODE_REPEAT ? (m1 - m0) : (uint32_t)a.n_seqs;
 		probe.len = L;
 		probe.mersize = L;
 		probe_start.assign(probe.seqcount, 0);
 		const uint32_t sf = h_strand[m0];
 		for (uint32_t j = m0; j < m1; ++j) {
-			const uint32_t slot = mode == MEMS_MODE_REPEAT ? (j - m0) : (h_val[j] >> b.pos_bits);
-			const int64_t st = (int64_t)(h_val[j] & b.pos_mask()) + 1;
+			const uint32_t slot = mode == MEMS_MODE_REPEAT ? (j - m0) : (h_val[j] >> a.pos_bits);
+			const int64_t st = (int64_t)(h_val[j] & a.pos_mask) + 1;
 			probe_start[slot] = (h_strand[j] != sf) ? -st : st;  // SetDirection, MemHash.cpp:189-203
 		}
 		probe.start = probe_start.data();
@@ -1138,6 +1139,30 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	out.n_matches = out.mem_count;
 }
 
+template <class KeyT>
+static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
+	Ctx* c = b.ctx.get();
+	out.seq_count = (uint32_t)b.n_seqs;
+	out.seed_length = (uint32_t)b.sd.L;
+	if (b.n_total < 2) return;
+	MatchArgs a;
+	a.keys = b.keys.p;
+	a.vals = b.vals.p;
+	a.n = (uint32_t)b.n_total;
+	a.pos_bits = b.pos_bits;
+	a.pos_mask = b.pos_mask();
+	a.n_seqs = b.n_seqs;
+	a.mode = mode;
+	a.packed = b.packed.p;
+	a.meta = b.d_meta.p;
+	HitSet hits;
+	find_hits<KeyT>(c, a, hits);
+	out.max_run = hits.max_run;
+	out.n_hits = hits.n;
+	if (hits.n == 0) return;
+	extend_hits<KeyT>(b.ctx, a, reinterpret_cast<const KeyT*>(b.keys_by_pos.p), b.sd.L, hits, order, table_size, out);
+}
+
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
 	if (mode == MEMS_MODE_PAIRWISE) throw Error(MEMS_ERR_UNSUPPORTED, "PairwiseMatchFinder policy is not built yet");
 	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
@@ -1145,6 +1170,333 @@ void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, M
 		find_matches_typed<uint64_t>(b, mode, order, table_size, out);
 	else
 		find_matches_typed<uint32_t>(b, mode, order, table_size, out);
+}
+
+// ================================================================================================ sharded (multi-GPU)
+// One process per GPU.  The path shards in two exchanges (ParallelMemHash.cpp:42-121 is the
+// reference's own, never-built, seed-range chunking):
+//   * every rank packs + extracts a contiguous block of the sequences;
+//   * seed space is range-partitioned on the top 8 key bits with owners balanced by the global histogram
+//     (canonical keys are skewed ~15:1 across the key space), so one all-to-all delivers every occurrence
+//     of a seed range to one GPU, which sorts it and finds the hits of its range;
+//   * hits are then re-partitioned by the hash of their DIAGONAL (second, much smaller all-to-all), so that
+//     all hits of a diagonal meet on one GPU: segments, walks and components are disjoint across ranks — no
+//     duplicated extension work and nothing to de-duplicate between ranks;
+//   * the position-ordered keys of all sequences are all-gathered (window tests read arbitrary sequences).
+// Each rank returns its share of the (distinct) matches.
+void shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count) {
+	const int base = n_seqs / world, extra = n_seqs % world;
+	*first = rank * base + (rank < extra ? rank : extra);
+	*count = base + (rank < extra ? 1 : 0);
+}
+
+void shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256) {
+	uint64_t total = 0;
+	for (int b = 0; b < 256; ++b) total += hist256[b];
+	uint64_t acc = 0;
+	int r = 0;
+	if (total == 0) world = 1;  // nothing to balance: everything stays with rank 0
+	for (int b = 0; b < 256; ++b) {
+		// bucket b goes to the rank whose share [r*total/world, (r+1)*total/world) holds the bucket's midpoint
+		const uint64_t mid = acc + hist256[b] / 2;
+		while (r + 1 < world && mid >= (uint64_t)((__uint128_t)total * (uint64_t)(r + 1) / (uint64_t)world)) ++r;
+		owner256[b] = (uint8_t)r;
+		acc += hist256[b];
+	}
+}
+
+template <class KeyT>
+__global__ void scatter_members_kernel(MatchArgs a, const uint32_t* __restrict__ hid, const uint32_t* __restrict__ hit_start,
+                                       const uint16_t* __restrict__ hit_len, const uint32_t* __restrict__ mem_off, uint32_t n_hits,
+                                       uint32_t* __restrict__ out_len, uint32_t* __restrict__ out_val, uint8_t* __restrict__ out_strand) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // hit i in diagonal-hash order
+	if (i >= n_hits) return;
+	const uint32_t h = hid[i], s = hit_start[h], len = hit_len[h] & ~kFirstStrandBit;
+	out_len[i] = len;
+	uint32_t at = mem_off[i];
+	for (uint32_t j = s; j < s + len; ++j, ++at) {  // union order: strand 0 members first, each part ascending
+		out_val[at] = a.vals[j];
+		out_strand[at] = (uint8_t)strand_of<KeyT>(a.keys, j);
+	}
+}
+
+__global__ void sorted_len_kernel(const uint32_t* __restrict__ hid, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
+                                  uint32_t* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_hits) out[i] = hit_len[hid[i]] & ~kFirstStrandBit;
+}
+
+// first index of the sorted hit keys that belongs to rank d (range partition on the top 32 hash bits)
+__global__ void hit_bounds_kernel(const uint64_t* __restrict__ hkey, uint32_t n_hits, int world, uint32_t* __restrict__ bound) {
+	const int d = threadIdx.x;
+	if (d > world) return;
+	if (d == world) {
+		bound[d] = n_hits;
+		return;
+	}
+	const uint64_t t = ((((uint64_t)d << 32) + (uint64_t)world - 1) / (uint64_t)world) << 32;  // ceil(d * 2^32 / world) << 32
+	uint32_t lo = 0, hi = n_hits;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) / 2;
+		if (hkey[mid] < t) lo = mid + 1;
+		else hi = mid;
+	}
+	bound[d] = lo;
+}
+
+template <class KeyT>
+__global__ void received_hits_kernel(const uint32_t* __restrict__ len32, const uint8_t* __restrict__ strand, uint32_t n_hits,
+                                     uint32_t n_mem, uint16_t* __restrict__ hit_len, KeyT* __restrict__ keys) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_hits) hit_len[i] = (uint16_t)len32[i];
+	if (i < n_mem) keys[i] = (KeyT)strand[i];  // the kernels downstream read only the strand bit of a member's key
+}
+
+template <class KeyT>
+static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, const SeedDesc& sd, int n_seqs,
+                                       const char* const* seqs, const uint64_t* lens, uint64_t seed, int mode, int order,
+                                       MatchResult& out) {
+	Ctx* c = ctx.get();
+	const int W = Comm_world(comm), R = Comm_rank(comm);
+	const size_t K = sizeof(KeyT);
+	// ---- global layout (identical on every rank)
+	std::vector<SeqMeta> gmeta(n_seqs);
+	uint64_t seed_off = 0;
+	uint32_t max_seeds = 0;
+	for (int g = 0; g < n_seqs; ++g) {
+		if (lens[g] > 0xffffffffull) throw Error(MEMS_ERR_UNSUPPORTED, "sequence longer than 2^32-1 bases");
+		SeqMeta& m = gmeta[g];
+		memset(&m, 0, sizeof m);
+		m.n_bases = (uint32_t)lens[g];
+		m.n_seeds = lens[g] >= (uint64_t)sd.L ? (uint32_t)(lens[g] - sd.L + 1) : 0u;
+		m.seed_off = seed_off;
+		m.tag = (uint32_t)g;
+		seed_off += m.n_seeds;
+		max_seeds = std::max(max_seeds, m.n_seeds);
+	}
+	const uint64_t s_total = seed_off;
+	const int pos_bits = bits_for(max_seeds ? max_seeds - 1 : 0);
+	const int seq_bits = n_seqs > 1 ? bits_for((uint64_t)n_seqs - 1) : 0;
+	if (pos_bits + seq_bits > 32) throw Error(MEMS_ERR_UNSUPPORTED, "sequence count x longest sequence exceeds the 32-bit tag");
+	if (s_total >= (1ull << 31)) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^31-1 seed positions in total");
+	out.seq_count = (uint32_t)n_seqs;
+	out.seed_length = (uint32_t)sd.L;
+
+	// ---- 1. this rank's block of sequences: pack, extract, top-digit histogram
+	int first, count;
+	shard_sequence_range(n_seqs, R, W, &first, &count);
+	for (int g = first; g < first + count; ++g)
+		if (lens[g] && !seqs[g]) throw Error(MEMS_ERR_INVALID, "a sequence of this rank's block is missing");
+	auto local = prepare_batch_from_ascii(ctx, count, seqs + first, lens + first, seed, (uint32_t)first, pos_bits, seq_bits ? seq_bits : 0);
+	const uint64_t n_loc = local->n_total;
+	SortPlan top;  // one digit: the top 8 key bits
+	top.n_passes = 1;
+	top.bits[0] = sd.key_bits < 8 ? sd.key_bits : 8;
+	top.shift[0] = sd.key_bits - top.bits[0];
+	DevBuf<uint8_t> keys_loc(c, n_loc * K), keys_part(c, n_loc * K);
+	DevBuf<uint32_t> vals_loc(c, n_loc), vals_part(c, n_loc), hist_top(c, 256);
+	MEMS_CUDA(cudaMemsetAsync(hist_top.p, 0, 256 * sizeof(uint32_t), c->stream));
+	if (n_loc)
+		launch_extract(c, local->packed.p, local->d_meta.p, local->meta.data(), count, sd, pos_bits, K == 8, keys_loc.p,
+		               vals_loc.p, hist_top.p, 1, top.shift, top.bits);
+	uint32_t h_hist32[256];
+	MEMS_CUDA(cudaMemcpyAsync(h_hist32, hist_top.p, sizeof h_hist32, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	uint64_t h_hist[256];
+	for (int b = 0; b < 256; ++b) h_hist[b] = h_hist32[b];
+	DevBuf<uint64_t> d_u64(c, 256 + (size_t)4 * W * W + 4 * W);
+	MEMS_CUDA(cudaMemcpyAsync(d_u64.p, h_hist, sizeof h_hist, cudaMemcpyHostToDevice, c->stream));
+	comm_all_reduce_u64(comm, d_u64.p, 256);
+	uint64_t g_hist[256];
+	MEMS_CUDA(cudaMemcpyAsync(g_hist, d_u64.p, sizeof g_hist, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+
+	// ---- 2. owners of the key ranges; partition the local records by top digit (stable counting pass)
+	uint8_t owner[256];
+	shard_bucket_owners(g_hist, W, owner);
+	std::vector<uint64_t> send_counts(W, 0), recv_counts(W, 0);
+	for (int b = 0; b < 256; ++b) send_counts[owner[b]] += h_hist32[b];
+	{
+		void* kp[2] = {keys_loc.p, keys_part.p};
+		uint32_t* vp[2] = {vals_loc.p, vals_part.p};
+		radix_sort_pairs(c, K == 8, kp, vp, n_loc, top, hist_top.p, "shard_partition_pass");
+	}
+	// ---- 3. exchange: counts, then the records of every key range to its owner
+	auto exchange_counts = [&](const std::vector<uint64_t>& mine, std::vector<uint64_t>& theirs) {
+		uint64_t* d_send = d_u64.p + 256;
+		uint64_t* d_all = d_send + W;
+		MEMS_CUDA(cudaMemcpyAsync(d_send, mine.data(), W * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+		comm_all_gather_u64(comm, d_send, d_all, W);
+		std::vector<uint64_t> all((size_t)W * W);
+		MEMS_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		for (int p = 0; p < W; ++p) theirs[p] = all[(size_t)p * W + R];  // what rank p sends to me
+	};
+	exchange_counts(send_counts, recv_counts);
+	uint64_t n_recv = 0;
+	for (int p = 0; p < W; ++p) n_recv += recv_counts[p];
+	if (n_recv > radix_max_items()) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30-1 seed records on one rank");
+	DevBuf<uint8_t> rk_a(c, n_recv * K), rk_b(c, n_recv * K);
+	DevBuf<uint32_t> rv_a(c, n_recv), rv_b(c, n_recv);
+	{
+		KernelScope ks(c, "nccl_all_to_all_records", (double)n_loc * (K + 4));
+		comm_all_to_all_v(comm, keys_part.p, send_counts.data(), rk_a.p, recv_counts.data(), K);
+		comm_all_to_all_v(comm, vals_part.p, send_counts.data(), rv_a.p, recv_counts.data(), 4);
+	}
+	keys_part.reset();
+	vals_part.reset();
+	vals_loc.reset();
+	// ---- 4. position-ordered keys of ALL sequences on every rank (window tests read any sequence)
+	DevBuf<uint8_t> key_pos_all(c, s_total * K);
+	{
+		std::vector<uint64_t> bytes(W), offs(W);
+		for (int p = 0; p < W; ++p) {
+			int f, n;
+			shard_sequence_range(n_seqs, p, W, &f, &n);
+			uint64_t cnt = 0;
+			for (int g = f; g < f + n; ++g) cnt += gmeta[g].n_seeds;
+			bytes[p] = cnt * K;
+			offs[p] = (n ? gmeta[f].seed_off : 0) * K;
+		}
+		KernelScope ks(c, "nccl_all_gather_keys", (double)s_total * K);
+		comm_all_gather_v(comm, keys_loc.p, key_pos_all.p, bytes.data(), offs.data());
+	}
+	keys_loc.reset();
+	DevBuf<SeqMeta> d_gmeta(c, n_seqs);
+	MEMS_CUDA(cudaMemcpyAsync(d_gmeta.p, gmeta.data(), sizeof(SeqMeta) * n_seqs, cudaMemcpyHostToDevice, c->stream));
+
+	// ---- 5. sort the received range; hits of this rank's seed range
+	const void* u_keys = rk_a.p;
+	const uint32_t* u_vals = rv_a.p;
+	if (n_recv) {
+		SortPlan plan = make_sort_plan(sd.key_bits);
+		DevBuf<uint32_t> hist(c, (size_t)plan.n_passes * 256);
+		launch_histogram(c, K == 8, rk_a.p, n_recv, plan, hist.p);
+		void* kp[2] = {rk_a.p, rk_b.p};
+		uint32_t* vp[2] = {rv_a.p, rv_b.p};
+		const int r = radix_sort_pairs(c, K == 8, kp, vp, n_recv, plan, hist.p, "radix_pass");
+		u_keys = kp[r];
+		u_vals = vp[r];
+	}
+	MatchArgs a1;
+	a1.keys = u_keys;
+	a1.vals = u_vals;
+	a1.n = (uint32_t)n_recv;
+	a1.pos_bits = pos_bits;
+	a1.pos_mask = pos_bits >= 32 ? 0xffffffffu : ((1u << pos_bits) - 1u);
+	a1.n_seqs = n_seqs;
+	a1.mode = mode;
+	a1.packed = nullptr;
+	a1.meta = d_gmeta.p;
+	HitSet hits1;
+	if (n_recv >= 2) find_hits<KeyT>(c, a1, hits1);
+	out.max_run = hits1.max_run;
+
+	// ---- 6. describe + sort the hits by diagonal hash; ranges of the hash space go to their owner rank
+	const uint32_t n1 = hits1.n;
+	SortPlan hplan = make_sort_plan(64);
+	DevBuf<uint64_t> hk_a(c, n1), hk_b(c, n1);
+	DevBuf<uint32_t> hid_a(c, n1), hid_b(c, n1), slen(c, n1), moff(c, n1), bound(c, W + 1), scal(c, 2);
+	const uint64_t* hkey = hk_a.p;
+	const uint32_t* hid = hid_a.p;
+	uint32_t n_mem1 = 0;
+	std::vector<uint32_t> h_bound(W + 1, 0), h_mbound(W + 1, 0);
+	if (n1) {
+		DevBuf<uint32_t> hist(c, (size_t)hplan.n_passes * 256);
+		MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)hplan.n_passes * 256 * sizeof(uint32_t), c->stream));
+		const uint32_t hb = (n1 + 255) / 256;
+		{
+			KernelScope ks(c, "hit_describe");
+			hit_describe_kernel<KeyT><<<hb, 256, 0, c->stream>>>(a1, hits1.start.p, hits1.len.p, n1, hk_a.p, hid_a.p, hist.p, hplan);
+			MEMS_CUDA(cudaGetLastError());
+		}
+		void* kp[2] = {hk_a.p, hk_b.p};
+		uint32_t* vp[2] = {hid_a.p, hid_b.p};
+		const int r = radix_sort_pairs(c, true, kp, vp, n1, hplan, hist.p, "hit_sort_pass");
+		hkey = r ? hk_b.p : hk_a.p;
+		hid = r ? hid_b.p : hid_a.p;
+		KernelScope ks(c, "shard_hits");
+		sorted_len_kernel<<<hb, 256, 0, c->stream>>>(hid, hits1.len.p, n1, slen.p);
+		MEMS_CUDA(cudaGetLastError());
+		exclusive_scan_u32(c, slen.p, moff.p, n1, scal.p);
+		hit_bounds_kernel<<<1, 32 * ((W + 32) / 32), 0, c->stream>>>(hkey, n1, W, bound.p);
+		MEMS_CUDA(cudaGetLastError());
+		MEMS_CUDA(cudaMemcpyAsync(&n_mem1, scal.p, 4, cudaMemcpyDeviceToHost, c->stream));
+		MEMS_CUDA(cudaMemcpyAsync(h_bound.data(), bound.p, (W + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		std::vector<uint32_t> h_moff(W + 1, n_mem1);
+		for (int d = 0; d < W; ++d)
+			if (h_bound[d] < n1) MEMS_CUDA(cudaMemcpyAsync(&h_moff[d], moff.p + h_bound[d], 4, cudaMemcpyDeviceToHost, c->stream));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		h_mbound = h_moff;
+	}
+	DevBuf<uint32_t> s_mval(c, n_mem1);
+	DevBuf<uint8_t> s_mstr(c, n_mem1);
+	if (n1) {
+		KernelScope ks(c, "shard_hits");
+		scatter_members_kernel<KeyT><<<(n1 + 255) / 256, 256, 0, c->stream>>>(a1, hid, hits1.start.p, hits1.len.p, moff.p, n1,
+		                                                                        slen.p, s_mval.p, s_mstr.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	std::vector<uint64_t> hs(W), hr(W), ms(W), mr(W);
+	for (int d = 0; d < W; ++d) {
+		hs[d] = h_bound[d + 1] - h_bound[d];
+		ms[d] = h_mbound[d + 1] - h_mbound[d];
+	}
+	exchange_counts(hs, hr);
+	exchange_counts(ms, mr);
+	uint64_t n2 = 0, n_mem2 = 0;
+	for (int p = 0; p < W; ++p) {
+		n2 += hr[p];
+		n_mem2 += mr[p];
+	}
+	if (n_mem2 >= (1ull << 31)) throw Error(MEMS_ERR_UNSUPPORTED, "too many hit members on one rank");
+	DevBuf<uint32_t> r_len(c, n2), r_mval(c, n_mem2);
+	DevBuf<uint8_t> r_mstr(c, n_mem2);
+	{
+		KernelScope ks(c, "nccl_all_to_all_hits", (double)n1 * 4 + (double)n_mem1 * 5);
+		comm_all_to_all_v(comm, slen.p, hs.data(), r_len.p, hr.data(), 4);
+		comm_all_to_all_v(comm, s_mval.p, ms.data(), r_mval.p, mr.data(), 4);
+		comm_all_to_all_v(comm, s_mstr.p, ms.data(), r_mstr.p, mr.data(), 1);
+	}
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers below go out of scope
+	// ---- 7. this rank's diagonals: segments, walks, components
+	out.n_hits = n2;
+	if (n2 == 0) return;
+	HitSet hits2;
+	hits2.n = (uint32_t)n2;
+	hits2.start = DevBuf<uint32_t>(c, n2);
+	hits2.len = DevBuf<uint16_t>(c, n2);
+	DevBuf<KeyT> keys2(c, n_mem2);
+	exclusive_scan_u32(c, r_len.p, hits2.start.p, n2, nullptr);
+	{
+		KernelScope ks(c, "shard_hits");
+		const uint32_t nmax = (uint32_t)std::max<uint64_t>(n2, n_mem2);
+		received_hits_kernel<KeyT><<<(nmax + 255) / 256, 256, 0, c->stream>>>(r_len.p, r_mstr.p, (uint32_t)n2, (uint32_t)n_mem2,
+		                                                                        hits2.len.p, keys2.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	MatchArgs a2 = a1;
+	a2.keys = keys2.p;
+	a2.vals = r_mval.p;
+	a2.n = (uint32_t)n_mem2;
+	extend_hits<KeyT>(ctx, a2, reinterpret_cast<const KeyT*>(key_pos_all.p), sd.L, hits2, order, 40000u, out);
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
+                          uint64_t seed, int mode, int order, MatchResult& out) {
+	if (mode != MEMS_MODE_MEMHASH)
+		throw Error(MEMS_ERR_UNSUPPORTED, "only MemHash is sharded (RepeatHash needs the reference's table order: run it on one GPU)");
+	if (order == MEMS_ORDER_REFERENCE)
+		throw Error(MEMS_ERR_UNSUPPORTED, "the reference's table order needs all hits in one place; use ORDER_ANY or ORDER_CANONICAL when sharded");
+	if (n_seqs < 1 || n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "1..MEMS_MAX_SEQS sequences");
+	MEMS_CUDA(cudaSetDevice(ctx->device));
+	const SeedDesc sd = make_seed_desc(seed);
+	if (sd.key_bits > 32)
+		find_matches_sharded_typed<uint64_t>(ctx, comm, sd, n_seqs, seqs, lens, seed, mode, order, out);
+	else
+		find_matches_sharded_typed<uint32_t>(ctx, comm, sd, n_seqs, seqs, lens, seed, mode, order, out);
 }
 
 }  // namespace mems

@@ -106,7 +106,7 @@ extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ 
 		s_words[i] = wi < n_words ? src[wi] : 0u;
 	}
 	__syncthreads();
-	const uint32_t seq_tag = (uint32_t)blockIdx.y << pos_bits;
+	const uint32_t seq_tag = m.tag << pos_bits;
 #pragma unroll
 	for (int k = 0; k < kExtractItems; ++k) {
 		uint32_t local = k * kExtractThreads + threadIdx.x;  // striped: a warp writes 32 consecutive keys
