@@ -11,8 +11,10 @@ palindromic spaced seed (progressiveMauve default), 1 GPU.
 value  : Mbp/s with the ASCII genomes already resident in HBM when the timed region starts.
 e2e    : Mbp/s through the public C-ABI call with pinned HOST buffers (H2D of the genomes and D2H of the
          MatchList inside the timed region).
-N > 1  : launched by torchrun, one rank per GPU.  This round every rank anchors its own independent
-         genome set (weak scaling, no data-path collective); the seed-range all-to-all is not built yet.
+N > 1  : launched by torchrun, one rank per GPU, SHARDED path (mems_find_matches_sharded): every rank extracts
+         a block of the genomes, one NCCL all-to-all moves each seed range to its owner, a second one moves hits
+         to the owner of their diagonal.  Weak scaling: the genome count stays 8 and every genome is N times
+         longer (N = 1 is exactly the single-GPU workload), so each GPU carries a constant 40 Mbp.
 --impl reference : times the UNMODIFIED reference (oracle/_ref, single-threaded MemorySML + MemHash) on
          the host cores over a bounded sample of the same workload.
 """
@@ -177,19 +179,39 @@ def main():
     n_genomes, length, weight, mode, desc = WORKLOADS[name]
     seed = mems.get_seed(weight)
     match_mode = mems.MODE_REPEAT if mode == "repeat" else mems.MODE_MEMHASH
-    gs = make_genomes(name, n_genomes, length, seed=2 + rank)  # every rank anchors its own genome set
-    mbp_rank = sum(len(g) for g in gs) / 1e6
-    host = [torch.from_numpy(g).pin_memory() for g in gs]
-    dev = [h.cuda(non_blocking=False) for h in host]
     stream = torch.cuda.Stream()
     ctx = mems.Context(local_rank, stream=stream.cuda_stream)
+    if world == 1:
+        gs = make_genomes(name, n_genomes, length, seed=2)
+        mbp_total = sum(len(g) for g in gs) / 1e6
+        host = [torch.from_numpy(g).pin_memory() for g in gs]
+        dev = [h.cuda(non_blocking=False) for h in host]
 
-    def step(bufs):
-        smls = ctx.create_smls([(b.data_ptr(), b.numel()) for b in bufs], seed)
-        flat, info = ctx.find_matches(smls, mode=match_mode)
-        for s in smls:
-            s.close()
-        return flat, info
+        def step(bufs):
+            smls = ctx.create_smls([(b.data_ptr(), b.numel()) for b in bufs], seed)
+            flat, info = ctx.find_matches(smls, mode=match_mode)
+            for s in smls:
+                s.close()
+            return flat, info
+    else:
+        # sharded: same 8-genome family, every genome `world` times longer; this rank holds only its block
+        if mode == "repeat":
+            raise SystemExit("RepeatHash runs on one GPU (replicas only); use --gpus 1")
+        length = length * world
+        gs = make_genomes(name, n_genomes, length, seed=2)  # identical on every rank (seeded generator)
+        lens = [len(g) for g in gs]
+        mbp_total = sum(lens) / 1e6
+        first, count = mems.shard_sequence_range(n_genomes, rank, world)
+        host = [torch.from_numpy(g).pin_memory() if first <= i < first + count else None for i, g in enumerate(gs)]
+        dev = [h.cuda(non_blocking=False) if h is not None else None for h in host]
+        del gs
+        uid = [mems.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=torch.device("cuda", local_rank))
+        comm = ctx.create_comm(uid[0], rank, world)
+
+        def step(bufs):
+            seqs = [(b.data_ptr(), b.numel()) if b is not None else None for b in bufs]
+            return ctx.find_matches_sharded(comm, seqs, lens, seed, mode=match_mode)
 
     def barrier():
         if world > 1:
@@ -231,6 +253,11 @@ def main():
         step(host)
     ms_e2e, flat_h, info_h = timed(host, args.steps)
     clocks = sampler.stop()
+    n_matches_total, n_hits_total, d2h_total = info["n_matches"], info["n_hits"], len(flat_h) * 8 + 64
+    if world > 1:
+        t = torch.tensor([n_matches_total, n_hits_total, d2h_total], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        n_matches_total, n_hits_total, d2h_total = (int(x) for x in t.tolist())
 
     if rank == 0:
         peaks = {}
@@ -255,27 +282,29 @@ def main():
                     "launches": roof["launches"], "avg_launch_ms": roof["ms"] / max(roof["launches"], 1),
                     "dominant_kernel_by_time": top[0], "kernel_ms_per_step": total_ms / args.steps,
                     "profiled_ms_per_step": ms_prof / args.steps}
-        mbp_total = mbp_rank * world
         line = {
             "metric": "genome Mbp/s (SML build + MemHash match find)",
             "value": mbp_total * args.steps / (ms_dev / 1e3), "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32" if 2 * weight + 1 <= 32 else "u64", "data": "synthetic",
             "config": {"workload": desc, "genomes": n_genomes, "genome_length": length, "seed_weight": weight,
-                       "seed_pattern": hex(seed), "multi_gpu": "independent genome sets per rank" if world > 1 else "n/a",
-                       "l2": "per-step working set (%.0f MB of seed records) exceeds the 126 MB L2" %
-                             (sum(len(g) for g in gs) * (8 if 2 * weight + 1 <= 32 else 12) / 1e6)},
+                       "seed_pattern": hex(seed), "multi_gpu": ("sharded: genome blocks per rank, seed-range all-to-all + diagonal all-to-all over NCCL; "
+                                     "weak scaling by genome length") if world > 1 else "n/a",
+                       "l2": "per-step working set (%.0f MB of seed records per GPU) exceeds the 126 MB L2" %
+                             (mbp_total / world * (8 if 2 * weight + 1 <= 32 else 12))},
             "e2e": {"value": mbp_total * args.steps / (ms_e2e / 1e3), "unit": "Mbp/s",
                     "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(sum(len(g) for g in gs)),
-                    "d2h_bytes_per_step": int(len(flat_h) * 8 + 64)},
-            "gpu_launches": launches, "matches_per_step": info["n_matches"], "hits_per_step": info["n_hits"],
-            "matches_per_s": info["n_matches"] * world * args.steps / (ms_dev / 1e3),
+                    "h2d_bytes_per_step": int(mbp_total * 1e6),
+                    "d2h_bytes_per_step": int(d2h_total)},
+            "gpu_launches": launches, "matches_per_step": n_matches_total, "hits_per_step": n_hits_total,
+            "matches_per_s": n_matches_total * args.steps / (ms_dev / 1e3),
             "roofline": roofline, "kernels": kernels, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(name)
         print(json.dumps(line))
+    if world > 1:
+        comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
