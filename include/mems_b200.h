@@ -99,6 +99,10 @@ int mems_sml_find_mer(mems_sml_t sml, uint64_t query_mer, int* found, uint64_t* 
  * ceil(2n/32)+2 words, pad words zero). words_out may be NULL to query *n_words only. */
 int mems_sml_packed(mems_sml_t sml, uint32_t* words_out, uint64_t* n_words);
 
+/* SeedOccurrenceList::construct (SeedOccurrenceList.h:21-92): out[p] for every base position p (Length()
+ * floats) = multiplicity of the seed at p, averaged over the seeds that contain p. */
+int mems_sml_seed_occurrence(mems_sml_t sml, float* out);
+
 /* ---- match finding ---- */
 typedef struct {
 	int mode;          /* MEMS_MODE_* */

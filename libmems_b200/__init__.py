@@ -52,7 +52,7 @@ EXPORTS = [
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
+    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
 ]
@@ -92,6 +92,7 @@ def load():
     lib.mems_sml_seed_mers.argtypes = [_vp, _vp, _u64, _vp, _vp]
     lib.mems_sml_find_mer.argtypes = [_vp, _u64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_u64)]
     lib.mems_sml_packed.argtypes = [_vp, _vp, ctypes.POINTER(_u64)]
+    lib.mems_sml_seed_occurrence.argtypes = [_vp, _vp]
     lib.mems_find_matches.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(MatchParams),
                                       ctypes.POINTER(_vp)]
     lib.mems_matches_info.argtypes = [_vp, ctypes.POINTER(MatchesInfo)]
@@ -383,6 +384,12 @@ class SortedMerList:
         idx = _u64()
         self.ctx._check(self.ctx.lib.mems_sml_find_mer(self.h, mer, ctypes.byref(found), ctypes.byref(idx)))
         return bool(found.value), int(idx.value)
+
+    def seed_occurrence(self):
+        """SeedOccurrenceList::construct: smoothed per-position seed multiplicity (float32, one per base)."""
+        out = np.zeros(max(self.info["length"], 1), np.float32)
+        self.ctx._check(self.ctx.lib.mems_sml_seed_occurrence(self.h, out.ctypes.data))
+        return out[:self.info["length"]]
 
     def packed(self):
         n = _u64()

@@ -217,6 +217,24 @@ int mems_sml_packed(mems_sml_t sml, uint32_t* words_out, uint64_t* n_words) {
 	});
 }
 
+int mems_sml_seed_occurrence(mems_sml_t sml, float* out) {
+	if (!sml || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	Batch& b = *sml->batch;
+	Ctx* c = b.ctx.get();
+	return guarded(c, [&] {
+		MEMS_CUDA(cudaSetDevice(c->device));
+		const SeqMeta& m = b.meta[sml->index];
+		if (m.n_bases == 0) return;
+		const uint32_t* pos = b.sorted_positions() + m.seed_off;
+		const size_t K = b.key64 ? 8 : 4;
+		DevBuf<float> d_out(c, m.n_bases);
+		launch_seed_occurrence(c, pos, b.pos_mask(), b.keys_by_pos.p + m.seed_off * K, b.key64, m.n_seeds, m.n_bases, b.sd.L,
+		                       d_out.p);
+		MEMS_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)m.n_bases * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	});
+}
+
 // ------------------------------------------------------------------------------------------------ matches
 int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls, const mems_match_params_t* params,
                       mems_matches_t* out) {

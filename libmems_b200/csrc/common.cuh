@@ -143,6 +143,11 @@ void launch_sml_read(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const 
 void launch_find_mer(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const uint32_t* d_positions, uint32_t pos_mask,
                      uint64_t n, uint64_t query_mer, uint64_t* d_result);
 
+// SeedOccurrenceList::construct for one sequence; d_positions = its sorted list (tagged), d_key_pos = its slice of
+// the position-ordered keys; writes n_bases floats
+void launch_seed_occurrence(Ctx* c, const uint32_t* d_positions, uint32_t pos_mask, const void* d_key_pos, bool key64,
+                            uint32_t n_seeds, uint32_t n_bases, int L, float* d_out);
+
 // ---- radix_sort.cu ----
 struct SortPlan {
 	int n_passes;

@@ -896,6 +896,113 @@ static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ pairwise policy
+// PairwiseMatchFinder::EnumerateMatches (PairwiseMatchFinder.cpp:37-71): of an equal-seed run keep the
+// sequences that hold the seed exactly once (others may hold it any number of times) and hash every pair
+// (i < j in sequence order) as a two-member hit.  Pairs are not contiguous in the union, so their members
+// are written out as a synthetic union of two-entry "runs" (strand-0 member first, like a real run), which
+// the extension stage reads exactly like the real one.
+template <class KeyT>
+__device__ uint64_t unique_sequences(const MatchArgs& a, uint32_t i, uint32_t* run_len) {
+	const uint64_t mk = masked_of<KeyT>(a.keys, i);
+	uint64_t once = 0, more = 0;
+	uint32_t j = i;
+	while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && j - i <= kRunCap) {
+		const uint64_t bit = 1ull << (a.vals[j] >> a.pos_bits);
+		more |= once & bit;
+		once |= bit;
+		++j;
+	}
+	*run_len = j - i;
+	return j - i > kRunCap ? 0ull : (once & ~more);
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(kScanBlock)
+pair_count_kernel(MatchArgs a, uint32_t* __restrict__ pair_count, uint32_t* __restrict__ max_run) {
+	const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+	uint32_t cnt = 0, run = 0;
+	if (i < a.n) {
+		const uint64_t mk = masked_of<KeyT>(a.keys, i);
+		const bool head = i == 0 || masked_of<KeyT>(a.keys, i - 1) != mk;
+		if (head && i + 1 < a.n && masked_of<KeyT>(a.keys, i + 1) == mk) {
+			const uint32_t u = __popcll(unique_sequences<KeyT>(a, i, &run));
+			cnt = u * (u - 1) / 2;
+		}
+		pair_count[i] = cnt;
+	}
+	run = __reduce_max_sync(0xffffffffu, run);
+	if ((threadIdx.x & 31) == 0 && run > 1) atomicMax(max_run, run);
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(kScanBlock)
+pair_emit_kernel(MatchArgs a, const uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ pair_off,
+                 uint32_t* __restrict__ out_vals, KeyT* __restrict__ out_keys) {
+	const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+	if (i >= a.n || pair_count[i] == 0) return;
+	uint32_t run;
+	const uint64_t uniq = unique_sequences<KeyT>(a, i, &run);
+	uint32_t at = 2 * pair_off[i];
+	// sequences in ascending order; a sequence's (single) entry is found by scanning the run
+	for (uint64_t ra = uniq; ra; ra &= ra - 1) {
+		const uint32_t ga = __ffsll((long long)ra) - 1;
+		uint32_t ja = i;
+		while ((a.vals[ja] >> a.pos_bits) != ga) ++ja;
+		for (uint64_t rb = ra & (ra - 1); rb; rb &= rb - 1) {
+			const uint32_t gb = __ffsll((long long)rb) - 1;
+			uint32_t jb = i;
+			while ((a.vals[jb] >> a.pos_bits) != gb) ++jb;
+			const uint32_t lo = ja < jb ? ja : jb, hi = ja < jb ? jb : ja;  // union order: strand 0 first, then (seq,pos)
+			out_vals[at] = a.vals[lo];
+			out_keys[at] = (KeyT)strand_of<KeyT>(a.keys, lo);
+			out_vals[at + 1] = a.vals[hi];
+			out_keys[at + 1] = (KeyT)strand_of<KeyT>(a.keys, hi);
+			at += 2;
+		}
+	}
+}
+
+__global__ void pair_hits_kernel(uint32_t n_hits, uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h < n_hits) {
+		hit_start[h] = 2 * h;
+		hit_len[h] = 2;
+	}
+}
+
+// stage A for the pairwise policy: hits + the synthetic union their members live in
+template <class KeyT>
+static void find_pair_hits(Ctx* c, const MatchArgs& a, HitSet& hits, DevBuf<uint32_t>& pvals, DevBuf<KeyT>& pkeys) {
+	const uint32_t n = a.n, n_blocks = (n + kScanBlock - 1) / kScanBlock;
+	DevBuf<uint32_t> cnt(c, n), off(c, n), scalars(c, 2);
+	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(uint32_t), c->stream));
+	{
+		KernelScope ks(c, "pair_scan", (double)n * (sizeof(KeyT) + 4.0));
+		pair_count_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, cnt.p, scalars.p + 0);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	exclusive_scan_u32(c, cnt.p, off.p, n, scalars.p + 1);
+	uint32_t h_scal[2];
+	MEMS_CUDA(cudaMemcpyAsync(h_scal, scalars.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	hits.max_run = h_scal[0];
+	hits.n = h_scal[1];
+	if (hits.n == 0) return;
+	if (hits.n >= (1u << 30)) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30 pairwise hits");
+	pvals = DevBuf<uint32_t>(c, 2 * (size_t)hits.n);
+	pkeys = DevBuf<KeyT>(c, 2 * (size_t)hits.n);
+	hits.start = DevBuf<uint32_t>(c, hits.n);
+	hits.len = DevBuf<uint16_t>(c, hits.n);
+	{
+		KernelScope ks(c, "pair_emit");
+		pair_emit_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, cnt.p, off.p, pvals.p, pkeys.p);
+		MEMS_CUDA(cudaGetLastError());
+		pair_hits_kernel<<<(hits.n + 255) / 256, 256, 0, c->stream>>>(hits.n, hits.start.p, hits.len.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+}
+
 // ---- stage B: hits (members readable through a.keys / a.vals) -> extended, distinct matches
 template <class KeyT>
 static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT* key_pos, int L, HitSet& hits, int order,
@@ -1156,7 +1263,16 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.packed = b.packed.p;
 	a.meta = b.d_meta.p;
 	HitSet hits;
-	find_hits<KeyT>(c, a, hits);
+	DevBuf<uint32_t> pvals;
+	DevBuf<KeyT> pkeys;
+	if (mode == MEMS_MODE_PAIRWISE) {
+		find_pair_hits<KeyT>(c, a, hits, pvals, pkeys);
+		a.keys = pkeys.p;  // from here on a hit's members are the two entries of its pair
+		a.vals = pvals.p;
+		a.n = 2 * hits.n;
+	} else {
+		find_hits<KeyT>(c, a, hits);
+	}
 	out.max_run = hits.max_run;
 	out.n_hits = hits.n;
 	if (hits.n == 0) return;
@@ -1164,7 +1280,6 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 }
 
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
-	if (mode == MEMS_MODE_PAIRWISE) throw Error(MEMS_ERR_UNSUPPORTED, "PairwiseMatchFinder policy is not built yet");
 	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
 	if (b.key64)
 		find_matches_typed<uint64_t>(b, mode, order, table_size, out);

@@ -235,3 +235,93 @@ void launch_sml_read(Ctx* c, const uint32_t* d_words, const SeedDesc& sd, const 
 }
 
 }  // namespace mems
+
+// ------------------------------------------------------------------------------------------------ seed occurrence
+// SeedOccurrenceList::construct (SeedOccurrenceList.h:21-92): for every base position the number of times the
+// seed starting there occurs in the sequence (the length of its equal-masked-key run in the sorted list),
+// positions past the last seed count 1, then each value becomes the mean over the L seeds that contain the
+// position (window sum / L in double, stored as float; the first L-1 positions see "1" for seeds before the start).
+namespace mems {
+
+template <class KeyT>
+__global__ void occ_heads_kernel(const uint32_t* __restrict__ positions, uint32_t pos_mask, const KeyT* __restrict__ key_pos,
+                                 uint32_t n, uint32_t* __restrict__ is_head) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const KeyT k = key_pos[positions[i] & pos_mask] >> 1;
+	is_head[i] = (i == 0 || (KeyT)(key_pos[positions[i - 1] & pos_mask] >> 1) != k) ? 1u : 0u;
+}
+
+__global__ void occ_run_starts_kernel(const uint32_t* __restrict__ is_head, const uint32_t* __restrict__ run_of, uint32_t n,
+                                      uint32_t* __restrict__ run_start) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && is_head[i]) run_start[run_of[i]] = i;
+}
+
+__global__ void occ_counts_kernel(const uint32_t* __restrict__ positions, uint32_t pos_mask, const uint32_t* __restrict__ is_head,
+                                  const uint32_t* __restrict__ run_of, const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                                  uint32_t n, uint32_t* __restrict__ count) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t r = is_head[i] ? run_of[i] : run_of[i] - 1;  // run_of is an exclusive scan of is_head
+	const uint32_t end = r + 1 < n_runs ? run_start[r + 1] : n;
+	count[positions[i] & pos_mask] = end - run_start[r];
+}
+
+__global__ void occ_smooth_kernel(const uint32_t* __restrict__ count, uint32_t n_bases, uint32_t n_seeds, int L,
+                                  float* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bases) return;
+	// raw value of position j: its run length, 1 past the last seed (and for "positions" before the start)
+	auto raw = [&](int64_t j) -> uint64_t {
+		if (j < 0) return 1;
+		const uint32_t tail_from = n_seeds > 1 ? n_seeds : 1;
+		return (uint32_t)j >= tail_from ? 1u : (uint64_t)count[j];
+	};
+	float v;
+	if (i + 1 < n_bases) {
+		uint64_t sum = 0;
+		for (int64_t j = (int64_t)i - L + 1; j <= (int64_t)i; ++j) sum += raw(j);
+		v = (float)((double)sum / (double)L);
+	} else {
+		v = (float)raw(i);  // the reference's loop never smooths the last position
+	}
+	out[i] = v == 0.f ? 1.f : v;
+}
+
+void launch_seed_occurrence(Ctx* c, const uint32_t* d_positions, uint32_t pos_mask, const void* d_key_pos, bool key64,
+                            uint32_t n_seeds, uint32_t n_bases, int L, float* d_out) {
+	if (n_bases == 0) return;
+	DevBuf<uint32_t> count(c, n_bases);
+	MEMS_CUDA(cudaMemsetAsync(count.p, 0, (size_t)n_bases * sizeof(uint32_t), c->stream));
+	if (n_seeds) {
+		DevBuf<uint32_t> is_head(c, n_seeds), run_of(c, n_seeds), total(c, 1);
+		const unsigned blocks = (n_seeds + 255) / 256;
+		KernelScope ks(c, "seed_occurrence");
+		if (key64)
+			occ_heads_kernel<uint64_t><<<blocks, 256, 0, c->stream>>>(d_positions, pos_mask, (const uint64_t*)d_key_pos, n_seeds, is_head.p);
+		else
+			occ_heads_kernel<uint32_t><<<blocks, 256, 0, c->stream>>>(d_positions, pos_mask, (const uint32_t*)d_key_pos, n_seeds, is_head.p);
+		MEMS_CUDA(cudaGetLastError());
+		exclusive_scan_u32(c, is_head.p, run_of.p, n_seeds, total.p);
+		uint32_t n_runs = 0;
+		MEMS_CUDA(cudaMemcpyAsync(&n_runs, total.p, 4, cudaMemcpyDeviceToHost, c->stream));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		DevBuf<uint32_t> run_start(c, n_runs);
+		occ_run_starts_kernel<<<blocks, 256, 0, c->stream>>>(is_head.p, run_of.p, n_seeds, run_start.p);
+		MEMS_CUDA(cudaGetLastError());
+		occ_counts_kernel<<<blocks, 256, 0, c->stream>>>(d_positions, pos_mask, is_head.p, run_of.p, run_start.p, n_runs, n_seeds,
+		                                                 count.p);
+		MEMS_CUDA(cudaGetLastError());
+		occ_smooth_kernel<<<(n_bases + 255) / 256, 256, 0, c->stream>>>(count.p, n_bases, n_seeds, L, d_out);
+		MEMS_CUDA(cudaGetLastError());
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // scratch buffers die with this scope
+	} else {
+		KernelScope ks(c, "seed_occurrence");
+		occ_smooth_kernel<<<(n_bases + 255) / 256, 256, 0, c->stream>>>(count.p, n_bases, 0, L, d_out);
+		MEMS_CUDA(cudaGetLastError());
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	}
+}
+
+}  // namespace mems

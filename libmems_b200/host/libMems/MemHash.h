@@ -98,6 +98,11 @@ protected:
 	int order;
 };
 
+class PairwiseMatchFinder : public MemHash {  // PairwiseMatchFinder.h:24-40
+protected:
+	int mode() const override { return MEMS_MODE_PAIRWISE; }
+};
+
 class RepeatHash : public MemHash {  // RepeatHash.h:24-46
 protected:
 	int mode() const override { return MEMS_MODE_REPEAT; }

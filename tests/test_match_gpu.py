@@ -40,8 +40,6 @@ def canonical(matches):
 
 def test_golden_matchlists(ctx):
     for case in json.load(open(os.path.join(GOLD, "matchlists.json"))):
-        if case["mode"] == mems.MODE_PAIRWISE:
-            continue
         seqs = [s.encode() for s in case["seqs"]]
         want = [tuple(m) for m in case["matches"]]
         got, info = gpu_matches(ctx, seqs, case["seed"], case["mode"], mems.ORDER_REFERENCE)
@@ -144,3 +142,21 @@ def test_long_walks_between_sparse_hits(ctx, orc):
             assert any(m[1] == len(X) for m in got)  # the full-length diagonal is found
             got_ref, _ = gpu_matches(ctx, [X, other], seed, mems.MODE_MEMHASH, mems.ORDER_REFERENCE)
             assert got_ref == want
+
+
+@pytest.mark.parametrize("it", range(6))
+def test_pairwise_vs_oracle(ctx, orc, it):
+    """PairwiseMatchFinder policy: every pair of sequences that hold a seed exactly once."""
+    rng = np.random.default_rng(7000 + it)
+    seed = mems.get_seed(int(rng.integers(7, 22)))
+    gs = synth.genome_family(int(rng.integers(2, 7)), int(rng.integers(500, 40000)), seed=900 + it,
+                             n_indels=3, max_indel=20)
+    if it % 2:
+        gs.append(np.concatenate([gs[1], gs[1]]))  # holds every seed twice: excluded, must not block the other pairs
+    want, winfo = orc.find_matches(2, gs, seed)
+    got, info = gpu_matches(ctx, gs, seed, mems.MODE_PAIRWISE)
+    assert got == canonical(want)
+    assert info["n_hits"] == winfo["hits"]
+    got_ref, info_ref = gpu_matches(ctx, gs, seed, mems.MODE_PAIRWISE, mems.ORDER_REFERENCE)
+    assert got_ref == want
+    assert info_ref["collisions"] == winfo["collisions"]

@@ -130,3 +130,15 @@ def test_large_sort_properties(ctx):
         sample = np.random.default_rng(1).integers(0, n, size=4096)
         _, dna = sml.seed_mers(pos[sample])
         assert np.array_equal(dna, mers[sample])
+
+
+def test_seed_occurrence(ctx, orc):
+    """SeedOccurrenceList::construct (per-position seed multiplicity, smoothed) — bit-exact floats."""
+    seed = mems.get_seed(11)
+    g = synth.repeat_genome(20000, seed=5, families=4, copies=6, min_len=50, max_len=300)
+    other = synth.genome_family(1, 7000, seed=6)[0]
+    smls = ctx.create_smls([g, other, np.frombuffer(b"ACGTACGTAC", dtype=np.uint8)], seed)
+    for s, q in zip(smls, [g, other, b"ACGTACGTAC"]):
+        assert np.array_equal(s.seed_occurrence(), orc.seed_occurrence(q, seed))
+    single = ctx.create_sml(g, mems.get_seed(15))
+    assert np.array_equal(single.seed_occurrence(), orc.seed_occurrence(g, mems.get_seed(15)))
