@@ -2,7 +2,9 @@
 // and CreateMemorySMLs (MatchList.h:408-435), which here builds all lists as ONE device batch.
 #pragma once
 #include <cmath>
+#include <istream>
 #include <ostream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -77,5 +79,68 @@ public:
 };
 
 typedef GenericMatchList<> MatchList;
+
+// .mums match files, format version 3 (ReadList / WriteList, MatchList.h:498-634).  The reference writes each
+// match's heap address as its id; any unique number round-trips, so the match's index + 1 is written here.
+template <class MatchListType>
+void WriteList(const MatchListType& mlist, std::ostream& match_file) {
+	if (mlist.size() == 0) return;
+	const unsigned seq_count = (*mlist.begin())->SeqCount();
+	match_file << "FormatVersion" << '\t' << 3 << "\n";
+	match_file << "SequenceCount" << '\t' << seq_count << "\n";
+	for (unsigned seqI = 0; seqI < seq_count; seqI++) {
+		match_file << "Sequence" << seqI << "File" << '\t';
+		if (mlist.seq_filename.size() > seqI) match_file << mlist.seq_filename[seqI];
+		else match_file << "null";
+		match_file << "\n";
+		match_file << "Sequence" << seqI << "Length" << '\t';
+		if (mlist.seq_table.size() > seqI) match_file << mlist.seq_table[seqI]->length();
+		else match_file << "0";
+		match_file << "\n";
+	}
+	match_file << "MatchCount" << '\t' << mlist.size() << std::endl;
+	uint64_t id = 0;
+	for (const Match* m : mlist) match_file << *m << '\t' << ++id << '\t' << 0 << '\t' << 0 << std::endl;
+}
+
+template <class MatchListType>
+void ReadList(MatchListType& mlist, std::istream& match_file) {
+	std::string tag;
+	unsigned seq_count = 0;
+	match_file >> tag;
+	if (tag != "FormatVersion") throw MemsException(MEMS_ERR_INVALID, "InvalidFileFormat");
+	match_file >> tag;
+	if (tag != "3") throw MemsException(MEMS_ERR_INVALID, "InvalidFileFormat");
+	match_file >> tag;
+	if (tag != "SequenceCount") throw MemsException(MEMS_ERR_INVALID, "InvalidFileFormat");
+	match_file >> seq_count;
+	if (seq_count < 2) throw MemsException(MEMS_ERR_INVALID, "InvalidFileFormat");
+	for (unsigned seqI = 0; seqI < seq_count; seqI++) {
+		match_file >> tag;  // name tag
+		std::getline(match_file, tag);
+		mlist.seq_filename.push_back(tag.empty() ? tag : tag.substr(1));  // skip the tab
+		uint64_t seq_len;
+		match_file >> tag >> seq_len;
+	}
+	uint64_t match_count = 0;
+	match_file >> tag >> match_count;
+	std::string line;
+	std::getline(match_file, line);
+	while (std::getline(match_file, line)) {
+		if (line.empty()) continue;
+		std::istringstream ls(line);
+		uint64_t len;
+		ls >> len;
+		Match* m = new Match(seq_count);
+		m->SetLength(len);
+		for (unsigned seqI = 0; seqI < seq_count; seqI++) {
+			int64_t start;
+			ls >> start;
+			m->SetStart(seqI, start);
+		}
+		mlist.push_back(m);
+	}
+	if (match_count != mlist.size()) throw MemsException(MEMS_ERR_INVALID, "InvalidFileFormat");
+}
 
 }  // namespace mems

@@ -17,6 +17,7 @@
 #include <vector>
 #include <string>
 #include <cstring>
+#include <sstream>
 
 using namespace mems;
 using namespace genome;
@@ -157,6 +158,58 @@ int ref_seed_occurrence(const char* seq, uint64_t n, uint64_t seed, float* out, 
 		*n_out = sml.Length();  // construct() sizes its table to sml.Length()
 		if (out)
 			for (uint64_t i = 0; i < sml.Length(); ++i) out[i] = sol.getFrequency(i);
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	}
+}
+
+// ReadList (MatchList.h:498-587): parse .mums text with the reference's own reader.
+int ref_read_list(const char* text, int64_t** flat_out, uint64_t* n_flat_out, uint64_t* n_matches_out) {
+	try {
+		std::istringstream is(text);
+		MatchList ml;
+		ReadList(ml, is);
+		std::vector<int64_t> flat;
+		for (size_t i = 0; i < ml.size(); ++i) {
+			flat.push_back((int64_t)ml[i]->SeqCount());
+			flat.push_back((int64_t)ml[i]->Length());
+			for (uint s = 0; s < ml[i]->SeqCount(); ++s) flat.push_back((int64_t)ml[i]->Start(s));
+		}
+		*n_matches_out = ml.size();
+		*n_flat_out = flat.size();
+		*flat_out = (int64_t*)malloc(sizeof(int64_t) * (flat.size() ? flat.size() : 1));
+		memcpy(*flat_out, flat.data(), sizeof(int64_t) * flat.size());
+		for (size_t i = 0; i < ml.size(); ++i) ml[i]->Free();
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	} catch (const char* s) {
+		g_err = s;
+		return 2;
+	}
+}
+
+// WriteList (MatchList.h:589-634) of the MemHash result of two or more sequences.
+int ref_write_list(int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed, char** text_out) {
+	try {
+		MatchList ml;
+		for (int g = 0; g < n_seqs; ++g) {
+			ml.seq_table.push_back(new gnSequence(seqs[g], lens[g]));
+			ml.seq_filename.push_back("mem");
+			DNAMemorySML* sml = new DNAMemorySML();
+			sml->Create(*ml.seq_table[g], seed);
+			ml.sml_table.push_back(sml);
+		}
+		MemHash mh;
+		mh.FindMatches(ml);
+		std::ostringstream os;
+		WriteList(ml, os);
+		*text_out = strdup(os.str().c_str());
+		mh.Clear();
+		ml.Clear();
 		return 0;
 	} catch (gnException& e) {
 		g_err = e.code.name + ": " + e.msg;

@@ -172,6 +172,26 @@ class Reference(_Checker):
         info = {"mem_count": counts[0], "collisions": counts[1], "sml_s": times[0], "find_s": times[1]}
         return flat_to_matches(out), info
 
+    def read_list(self, text):
+        """Parse .mums text with the reference's ReadList."""
+        flat = ctypes.POINTER(ctypes.c_int64)()
+        nflat, nm = u64(), u64()
+        if self.lib.ref_read_list(text.encode(), ctypes.byref(flat), ctypes.byref(nflat), ctypes.byref(nm)):
+            raise RuntimeError(self.err())
+        out = np.ctypeslib.as_array(flat, shape=(max(nflat.value, 1),))[:nflat.value].copy()
+        self.lib.ref_free(flat)
+        return flat_to_matches(out)
+
+    def write_list(self, seqs, seed):
+        """MemHash + the reference's WriteList -> .mums text."""
+        bufs = [_as_bytes(s) for s in seqs]
+        arr = (ctypes.c_char_p * len(bufs))(*bufs)
+        lens = (u64 * len(bufs))(*[len(b) for b in bufs])
+        text = ctypes.c_char_p()
+        if self.lib.ref_write_list(len(bufs), arr, lens, u64(seed), ctypes.byref(text)):
+            raise RuntimeError(self.err())
+        return text.value.decode()
+
     def seed_occurrence(self, seq, seed):
         s = _as_bytes(seq)
         out = np.zeros(len(s), np.float32)

@@ -1,9 +1,12 @@
 // facade_demo.cpp — the anchoring call sequence of the reference's callers (MatchList::CreateMemorySMLs +
 // MemHash::FindMatches, e.g. ProgressiveAligner.cpp:636-653) written against the façade headers.
-// Usage: facade_demo <memhash|repeat> <seed_weight> <raw-sequence-file>...   prints "len\tstart0\tstart1..." lines.
+// Usage: facade_demo <memhash|repeat|pairwise|mums> <seed_weight> <raw-sequence-file>...
+//   prints "len\tstart0\tstart1..." lines ("mums": MemHash, then the .mums file WriteList produces, re-read with ReadList)
+//        facade_demo readmums <file.mums>     parses a .mums file and prints its matches
 #include <fstream>
 #include <iostream>
 #include <iterator>
+#include <sstream>
 #include <string>
 
 #include "libMems/MemHash.h"
@@ -11,8 +14,16 @@
 using namespace mems;
 
 int main(int argc, char** argv) {
-	if (argc < 4) return 2;
+	if (argc < 3) return 2;
 	const std::string mode = argv[1];
+	if (mode == "readmums") {
+		std::ifstream f(argv[2]);
+		MatchList ml;
+		ReadList(ml, f);
+		for (Match* m : ml) std::cout << *m << "\n";
+		return 0;
+	}
+	if (argc < 4) return 2;
 	const unsigned weight = (unsigned)atoi(argv[2]);
 	try {
 		MatchList ml;
@@ -25,11 +36,23 @@ int main(int argc, char** argv) {
 		ml.CreateMemorySMLs(weight, &std::cerr);
 		std::cerr << "seed " << std::hex << ml.sml_table[0]->Seed() << std::dec << " length " << ml.sml_table[0]->SeedLength()
 		          << " sml[0] = {" << (*ml.sml_table[0])[0].position << ", " << (*ml.sml_table[0])[0].mer << "}\n";
-		MemHash* mh = mode == "repeat" ? new RepeatHash() : new MemHash();
+		MemHash* mh = mode == "repeat" ? new RepeatHash() : (mode == "pairwise" ? new PairwiseMatchFinder() : new MemHash());
 		mh->SetOutputOrder(MEMS_ORDER_REFERENCE);
 		mh->FindMatches(ml);
 		std::cerr << "MemCount " << mh->MemCount() << " MemCollisionCount " << mh->MemCollisionCount() << "\n";
-		for (Match* m : ml) std::cout << *m << "\n";
+		if (mode == "mums") {
+			std::stringstream file;
+			WriteList(ml, file);
+			std::cout << file.str();
+			MatchList back;
+			ReadList(back, file);
+			if (back.size() != ml.size()) return 3;
+			for (size_t i = 0; i < ml.size(); ++i)
+				if (!(*back[i] == *ml[i])) return 3;
+			for (Match* m : back) m->Free();
+		} else {
+			for (Match* m : ml) std::cout << *m << "\n";
+		}
 		mh->Clear();
 		delete mh;
 		ml.Clear();
