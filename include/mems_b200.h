@@ -109,6 +109,8 @@ typedef struct {
 	int order;         /* MEMS_ORDER_* */
 	uint32_t table_size; /* MemHash::SetTableSize; 0 = DEFAULT_MEM_TABLE_SIZE 40000 (MemHash.h:30) */
 	uint32_t reserved;
+	uint64_t seq_mask;   /* MaskedMemHash::SetMask (MaskedMemHash.h:22-32): with MEMS_MODE_MEMHASH keep only hits whose
+	                        sequence set equals this mask, sequence 0 = most significant of n_smls bits; 0 = no filter */
 } mems_match_params_t;
 
 typedef struct {

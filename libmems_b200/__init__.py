@@ -34,7 +34,7 @@ class SmlInfo(ctypes.Structure):
 
 class MatchParams(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int), ("order", ctypes.c_int), ("table_size", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32)]
+                ("reserved", ctypes.c_uint32), ("seq_mask", _u64)]
 
 
 class MatchesInfo(ctypes.Structure):
@@ -242,12 +242,12 @@ class Context:
         return [SortedMerList(self, _vp(out[i])) for i in range(n)]
 
     # -- match finding --------------------------------------------------------------------------------
-    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0):
+    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0):
         """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches.  Returns (matches, info) where
         matches is a list of tuples (SeqCount, Length, Start(0), ...)."""
         n = len(smls)
         arr = (_vp * n)(*[s.h for s in smls])
-        params = MatchParams(mode, order, table_size, 0)
+        params = MatchParams(mode, order, table_size, 0, seq_mask)
         h = _vp()
         self._check(self.lib.mems_find_matches(self.h, n, arr, ctypes.byref(params), ctypes.byref(h)))
         keep = _MatchHandle(self.lib, h)
@@ -276,7 +276,7 @@ class Context:
         parts = [(_host_ptr(s) if s is not None else (0, 0, None)) for s in seqs]
         ptrs = (_vp * n)(*[p[0] for p in parts])
         ls = (_u64 * n)(*[int(x) for x in lens])
-        params = MatchParams(mode, order, 0, 0)
+        params = MatchParams(mode, order, 0, 0, 0)
         h = _vp()
         self._check(self.lib.mems_find_matches_sharded(self.h, comm.h, n, ptrs, ls, seed, ctypes.byref(params),
                                                        ctypes.byref(h)))

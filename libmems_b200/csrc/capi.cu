@@ -267,7 +267,7 @@ int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls, const 
 		auto* m = new mems_matches();
 		try {
 			find_matches_on_batch(*b, p.mode, p.mode == MEMS_MODE_REPEAT ? MEMS_ORDER_REFERENCE : p.order,
-			                      p.table_size ? p.table_size : 40000u, m->r);
+			                      p.table_size ? p.table_size : 40000u, p.seq_mask, m->r);
 		} catch (...) {
 			delete m;
 			throw;

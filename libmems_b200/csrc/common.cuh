@@ -246,7 +246,7 @@ struct MatchResult {
 	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0, n_segments = 0;
 	uint32_t seq_count = 0, seed_length = 0;
 };
-void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out);
+void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out);
 void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
                           uint64_t seed, int mode, int order, MatchResult& out);
 

@@ -44,6 +44,7 @@ struct MatchArgs {
 	uint32_t pos_mask;
 	int n_seqs;
 	int mode;
+	uint64_t seq_set;  // MaskedMemHash filter: required member set, bit g = sequence g (0 = no filter)
 	const uint32_t* packed;
 	const SeqMeta* meta;
 };
@@ -89,6 +90,7 @@ run_scan_kernel(MatchArgs a, uint16_t* __restrict__ run_info, uint32_t* __restri
 					++len;
 					++j;
 				}
+				if (a.seq_set && seen != a.seq_set) ok = false;  // MaskedMemHash::HashMatch, MaskedMemHash.cpp:50-60
 			} else {
 				uint32_t j = i + 1;
 				while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
@@ -1247,7 +1249,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 }
 
 template <class KeyT>
-static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
+static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out) {
 	Ctx* c = b.ctx.get();
 	out.seq_count = (uint32_t)b.n_seqs;
 	out.seed_length = (uint32_t)b.sd.L;
@@ -1260,6 +1262,10 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.pos_mask = b.pos_mask();
 	a.n_seqs = b.n_seqs;
 	a.mode = mode;
+	// the reference's "match number" puts sequence 0 in the most significant of n_seqs bits; here bit g = sequence g
+	a.seq_set = 0;
+	for (int g = 0; g < b.n_seqs; ++g)
+		if ((seq_mask >> (b.n_seqs - 1 - g)) & 1) a.seq_set |= 1ull << g;
 	a.packed = b.packed.p;
 	a.meta = b.d_meta.p;
 	HitSet hits;
@@ -1279,12 +1285,13 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	extend_hits<KeyT>(b.ctx, a, reinterpret_cast<const KeyT*>(b.keys_by_pos.p), b.sd.L, hits, order, table_size, out);
 }
 
-void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, MatchResult& out) {
+void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out) {
+	if (seq_mask && mode != MEMS_MODE_MEMHASH) throw Error(MEMS_ERR_INVALID, "seq_mask applies to MEMS_MODE_MEMHASH only");
 	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
 	if (b.key64)
-		find_matches_typed<uint64_t>(b, mode, order, table_size, out);
+		find_matches_typed<uint64_t>(b, mode, order, table_size, seq_mask, out);
 	else
-		find_matches_typed<uint32_t>(b, mode, order, table_size, out);
+		find_matches_typed<uint32_t>(b, mode, order, table_size, seq_mask, out);
 }
 
 // ================================================================================================ sharded (multi-GPU)
@@ -1501,6 +1508,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.pos_mask = pos_bits >= 32 ? 0xffffffffu : ((1u << pos_bits) - 1u);
 	a1.n_seqs = n_seqs;
 	a1.mode = mode;
+	a1.seq_set = 0;
 	a1.packed = nullptr;
 	a1.meta = d_gmeta.p;
 	HitSet hits1;

@@ -44,6 +44,7 @@ public:
 		p.mode = mode();
 		p.order = order;
 		p.table_size = table_size;
+		p.seq_mask = seq_mask();
 		mems_matches_t m = nullptr;
 		Context::check(mems_find_matches(Context::get(), (int)h.size(), h.data(), &p, &m));
 		mems_matches_info_t info;
@@ -80,6 +81,7 @@ public:
 
 protected:
 	virtual int mode() const { return MEMS_MODE_MEMHASH; }
+	virtual uint64_t seq_mask() const { return 0; }
 	void reset() {
 		table_size = DEFAULT_MEM_TABLE_SIZE;
 		m_repeat_tolerance = DEFAULT_REPEAT_TOLERANCE;
@@ -96,6 +98,14 @@ protected:
 	uint32_t table_size, m_repeat_tolerance, m_enumeration_tolerance;
 	uint64_t m_mem_count, m_collision_count;
 	int order;
+};
+
+class MaskedMemHash : public MemHash {  // MaskedMemHash.h:21-40
+public:
+	virtual void SetMask(uint64_t m) { mask = m; }
+protected:
+	uint64_t seq_mask() const override { return mask; }
+	uint64_t mask = 0;
 };
 
 class PairwiseMatchFinder : public MemHash {  // PairwiseMatchFinder.h:24-40

@@ -503,6 +503,17 @@ static void hash_match(const finder_t* f, table_t* t, int seqcount, const int* s
 	add_hash_entry(f, t, e);
 }
 
+static uint64_t g_seq_mask = 0; /* MaskedMemHash::SetMask; 0 = no filter (MaskedMemHash.h:22-32) */
+
+int orc_find_matches_masked(int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed,
+                            uint64_t seq_mask, int64_t** flat_out, uint64_t* n_flat_out,
+                            uint64_t* n_matches_out, uint64_t* counts_out) {
+	g_seq_mask = seq_mask;
+	int rc = orc_find_matches(ORC_MODE_MEMHASH, n_seqs, seqs, lens, seed, flat_out, n_flat_out, n_matches_out, counts_out);
+	g_seq_mask = 0;
+	return rc;
+}
+
 int orc_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64_t* lens,
                      uint64_t seed, int64_t** flat_out, uint64_t* n_flat_out,
                      uint64_t* n_matches_out, uint64_t* counts_out) {
@@ -564,6 +575,17 @@ int orc_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 				int ok = 1;
 				for (uint64_t i = s + 1; i < e; ++i)
 					if (occ[i].seq == occ[i - 1].seq) ok = 0;
+				if (ok && g_seq_mask) {
+					/* MaskedMemHash::HashMatch (MaskedMemHash.cpp:38-63): "match number" has sequence 0 in the
+					 * most significant of n_seqs bits; only hits whose number equals the mask are hashed */
+					uint64_t number = 0;
+					for (int g = 0; g < n_seqs; ++g) {
+						number <<= 1;
+						for (uint64_t i = s; i < e; ++i)
+							if ((int)occ[i].seq == g) number |= 1;
+					}
+					if (number != g_seq_mask) ok = 0;
+				}
 				if (ok) {
 					for (uint64_t i = s; i < e; ++i) {
 						slot[i - s] = (int)occ[i].seq;

@@ -9,6 +9,7 @@
 #include "libMems/MemHash.h"
 #include "libMems/RepeatHash.h"
 #include "libMems/PairwiseMatchFinder.h"
+#include "libMems/MaskedMemHash.h"
 #include "libMems/MatchList.h"
 #include "libMems/SeedMasks.h"
 #include "libMems/SeedOccurrenceList.h"
@@ -27,6 +28,7 @@ double now_s() {
 	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 std::string g_err;
+uint64 g_seq_mask = 0;
 }
 
 extern "C" {
@@ -118,6 +120,11 @@ int ref_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 		if (mode == 0) mh = new MemHash();
 		else if (mode == 1) mh = new RepeatHash();
 		else if (mode == 2) mh = new PairwiseMatchFinder();
+		else if (mode == 3) {
+			MaskedMemHash* mm = new MaskedMemHash();
+			mm->SetMask(g_seq_mask);
+			mh = mm;
+		}
 		else { g_err = "bad mode"; return 3; }
 		mh->FindMatches(ml);
 		double t2 = now_s();
@@ -216,6 +223,9 @@ int ref_write_list(int n_seqs, const char* const* seqs, const uint64_t* lens, ui
 		return 1;
 	}
 }
+
+// mask for mode 3 (MaskedMemHash::SetMask, MaskedMemHash.h:32)
+void ref_set_seq_mask(uint64_t mask) { g_seq_mask = mask; }
 
 void ref_free(void* p) { free(p); }
 

@@ -116,6 +116,17 @@ class Oracle(_Checker):
         info = {"mem_count": counts[0], "collisions": counts[1], "hits": counts[2], "max_run": counts[3]}
         return flat_to_matches(out), info
 
+    def find_matches_masked(self, seqs, seed, seq_mask):
+        bufs, arr, lens, flat, nflat, nm = _Checker.find_matches(self, 0, seqs, seed)
+        counts = (u64 * 4)()
+        rc = self.lib.orc_find_matches_masked(len(bufs), arr, lens, u64(seed), u64(seq_mask), ctypes.byref(flat),
+                                              ctypes.byref(nflat), ctypes.byref(nm), counts)
+        if rc:
+            raise RuntimeError(self.err())
+        out = np.ctypeslib.as_array(flat, shape=(max(nflat.value, 1),))[:nflat.value].copy()
+        self.lib.orc_free(flat)
+        return flat_to_matches(out), {"mem_count": counts[0], "collisions": counts[1], "hits": counts[2]}
+
     def seed_occurrence(self, seq, seed):
         s = _as_bytes(seq)
         out = np.zeros(len(s), np.float32)
@@ -171,6 +182,13 @@ class Reference(_Checker):
         self.lib.ref_free(flat)
         info = {"mem_count": counts[0], "collisions": counts[1], "sml_s": times[0], "find_s": times[1]}
         return flat_to_matches(out), info
+
+    def find_matches_masked(self, seqs, seed, seq_mask):
+        self.lib.ref_set_seq_mask(u64(seq_mask))
+        try:
+            return self.find_matches(3, seqs, seed)
+        finally:
+            self.lib.ref_set_seq_mask(u64(0))
 
     def read_list(self, text):
         """Parse .mums text with the reference's ReadList."""

@@ -160,3 +160,15 @@ def test_pairwise_vs_oracle(ctx, orc, it):
     got_ref, info_ref = gpu_matches(ctx, gs, seed, mems.MODE_PAIRWISE, mems.ORDER_REFERENCE)
     assert got_ref == want
     assert info_ref["collisions"] == winfo["collisions"]
+
+
+def test_masked_memhash_vs_oracle(ctx, orc):
+    """MaskedMemHash: only hits whose sequence set equals the mask (sequence 0 = most significant bit)."""
+    gs = synth.genome_family(4, 30000, seed=41, snp_rate=0.03, n_indels=3, max_indel=20)
+    seed = mems.get_seed(11)
+    smls = ctx.create_smls(gs, seed)
+    for mask in (0b1111, 0b1100, 0b0101, 0b1011):
+        want, winfo = orc.find_matches_masked(gs, seed, mask)
+        flat, info = ctx.find_matches(smls, order=mems.ORDER_REFERENCE, seq_mask=mask)
+        assert mems.flat_to_matches(flat) == want, mask
+        assert info["collisions"] == winfo["collisions"] and info["n_hits"] == winfo["hits"]

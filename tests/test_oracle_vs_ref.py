@@ -72,3 +72,14 @@ def test_seed_occurrence(libs):
     g = synth.repeat_genome(5000, seed=5, families=3, copies=4, min_len=50, max_len=200)
     seed = O.get_seed(11)
     assert np.array_equal(O.seed_occurrence(g, seed), R.seed_occurrence(g, seed))
+
+
+def test_masked_memhash(libs):
+    O, R = libs
+    gs = synth.genome_family(4, 6000, seed=41, snp_rate=0.03, n_indels=3, max_indel=20)
+    seed = O.get_seed(11)
+    for mask in (0, 0b1111, 0b1100, 0b0101, 0b1011):
+        mo, io = O.find_matches_masked(gs, seed, mask)
+        mr, ir = R.find_matches_masked(gs, seed, mask)
+        assert mo == mr, mask
+        assert io["collisions"] == ir["collisions"]
