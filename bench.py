@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -237,7 +237,8 @@ def main():
     for _ in range(args.warmup):
         step(dev)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # one poller per node: concurrent nvidia-smi loops contend for the driver and stall the ranks
+        sampler.start()
     # timed region 1: inputs resident in HBM -> `value`
     ctx.profile_reset()
     ms_dev, flat, info = timed(dev, args.steps)
@@ -253,6 +254,12 @@ def main():
         step(host)
     ms_e2e, flat_h, info_h = timed(host, args.steps)
     clocks = sampler.stop()
+    rank_kernel_ms = None
+    if world > 1:
+        # per-kernel device time of every rank (ms per step): shows which rank / kernel sets the max-over-ranks time
+        mine = {k: v["ms"] / args.steps for k, v in prof.items()}
+        rank_kernel_ms = [None] * world
+        dist.all_gather_object(rank_kernel_ms, mine)
     n_matches_total, n_hits_total, d2h_total = info["n_matches"], info["n_hits"], len(flat_h) * 8 + 64
     if world > 1:
         t = torch.tensor([n_matches_total, n_hits_total, d2h_total], device="cuda", dtype=torch.int64)
@@ -300,6 +307,10 @@ def main():
             "matches_per_s": n_matches_total * args.steps / (ms_dev / 1e3),
             "roofline": roofline, "kernels": kernels, "clocks": clocks,
         }
+        if rank_kernel_ms:
+            names = sorted({k for d in rank_kernel_ms for k in d})
+            line["kernel_ms_max_over_ranks"] = {k: max(d.get(k, 0.0) for d in rank_kernel_ms) for k in names}
+            line["kernel_ms_total_per_rank"] = [sum(d.values()) for d in rank_kernel_ms]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(name)
         print(json.dumps(line))

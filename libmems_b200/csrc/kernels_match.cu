@@ -23,6 +23,8 @@
 // Hash collisions between diagonals only split segments (more window tests), never merge them: every
 // merge decision compares the full member lists.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <unordered_map>
@@ -45,6 +47,7 @@ struct MatchArgs {
 	int n_seqs;
 	int mode;
 	uint64_t seq_set;  // MaskedMemHash filter: required member set, bit g = sequence g (0 = no filter)
+	int test_hash_bits;  // 0 = use the full diagonal hash; n > 0 keeps only n bits (tests force bucket collisions with it)
 	const uint32_t* packed;
 	const SeqMeta* meta;
 };
@@ -201,6 +204,7 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 			hash = mix64(hash, ((uint64_t)(val >> a.pos_bits) << 1) | o);
 			hash = mix64(hash, (uint64_t)diag);
 		}
+		if (a.test_hash_bits) hash = (hash & ((1ull << a.test_hash_bits) - 1ull)) << (64 - a.test_hash_bits);
 		const uint64_t key = ((hash >> a.pos_bits) << a.pos_bits) | (uint64_t)x0;
 		hkey[h] = key;
 		hid[h] = h;
@@ -248,7 +252,8 @@ template <class KeyT>
 __global__ void __launch_bounds__(256)
 segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
                     const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
-                    uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head, uint32_t* __restrict__ collision_seen) {
+                    uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head, uint32_t* __restrict__ collision_seen,
+                    uint8_t* __restrict__ suspect) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_hits) return;
 	uint8_t f = kFlagHead;
@@ -262,7 +267,11 @@ segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const
 				const uint64_t gap = (k & a.pos_mask) - (kp & a.pos_mask);
 				if (gap > (uint64_t)L) f |= kFlagHead;
 			} else {
-				atomicOr(collision_seen, 1u);  // two diagonals in one hash bucket (rare): duplicates become possible
+				// two diagonals in one hash bucket (rare): the hits on either side of the foreign entry cannot see each
+				// other, so the components they end up in may be reported twice — mark both for the de-dup
+				atomicOr(collision_seen, 1u);
+				suspect[i] = 1;
+				suspect[i - 1] = 1;
 			}
 		}
 	}
@@ -476,6 +485,7 @@ struct SegView {
 	const uint32_t* seg_head;
 	uint32_t n_hits, n_seg;
 	const uint32_t* order;  // segment ids sorted by the first-member position of their first hit
+	const uint8_t* suspect;  // per sorted hit: next to a foreign diagonal of the same hash bucket
 };
 
 // Right walk of every segment: from its last hit, follow matching windows until either the next segment of
@@ -533,7 +543,8 @@ __global__ void __launch_bounds__(kExtendWarps * 32)
 walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint32_t* __restrict__ seg_link,
                  const uint32_t* __restrict__ seg_reach, const uint32_t* __restrict__ first,
                  const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
-                 uint32_t* __restrict__ comp_right, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
+                 uint32_t* __restrict__ comp_right, uint8_t* __restrict__ comp_suspect, uint2* __restrict__ defer,
+                 uint32_t* __restrict__ defer_count) {
 	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
 	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
 	if (slot >= v.n_seg) return;
@@ -542,6 +553,10 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 	const bool is_first = first[seg] != 0;
 	const uint32_t comp = first_excl[seg] - (is_first ? 0u : 1u);
 	if (!seg_link[seg] && lane == 0) comp_right[comp] = seg_reach[seg];
+	if (lane == 0) {
+		const uint32_t e0 = v.seg_head[seg], e1 = (seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits) - 1;
+		if (v.suspect[e0] | v.suspect[e1]) comp_suspect[comp] = 1;  // only ever set: racing writers agree
+	}
 	if (!is_first) return;
 	const uint32_t hi = v.seg_head[seg];
 	const uint32_t h = v.hid[hi];
@@ -1036,12 +1051,13 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	const uint32_t* hid = r ? hid_b.p : hid_a.p;
 
 	// ---- 4. segments
-	DevBuf<uint8_t> flags(c, n_hits);
+	DevBuf<uint8_t> flags(c, n_hits), suspect(c, n_hits);
 	DevBuf<uint32_t> is_head(c, n_hits), seg_of(c, n_hits);
+	MEMS_CUDA(cudaMemsetAsync(suspect.p, 0, n_hits, c->stream));
 	{
 		KernelScope ks(c, "segment_flag");
 		segment_flag_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, L, hkey, hid, hit_start.p, hit_len.p, n_hits,
-		                                                             flags.p, is_head.p, scalars.p + 4);
+		                                                             flags.p, is_head.p, scalars.p + 4, suspect.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, is_head.p, seg_of.p, n_hits, scalars.p + 2);
@@ -1068,7 +1084,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	}
 
 	// ---- 5. extend: right walks link segments into components, left walks finish each component
-	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg, seg_order};
+	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg, seg_order, suspect.p};
 	DevBuf<uint32_t> seg_link(c, n_seg), seg_reach(c, n_seg), first(c, n_seg), first_excl(c, n_seg);
 	DevBuf<uint2> defer(c, n_seg);
 	uint32_t* defer_count = scalars.p + 6;  // [6] right walks, [7] left walks handed to whole CTAs
@@ -1109,11 +1125,13 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	const uint32_t n_comp = h_tail[0];
 	const bool collision_seen = h_tail[1] != 0;
 	DevBuf<uint32_t> comp_rep(c, n_comp), comp_left(c, n_comp), comp_right(c, n_comp), rec_size(c, n_comp), rec_off(c, n_comp);
+	DevBuf<uint8_t> comp_suspect(c, n_comp);
+	if (collision_seen) MEMS_CUDA(cudaMemsetAsync(comp_suspect.p, 0, n_comp, c->stream));
 	{
 		KernelScope ks(c, "walk_left");
 		walk_left_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(
-		    a, key_pos, L, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, defer.p,
-		    defer_count + 1);
+		    a, key_pos, L, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, comp_suspect.p,
+		    defer.p, defer_count + 1);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
@@ -1150,8 +1168,31 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
 		// Components are distinct by construction unless two diagonals shared a hash bucket: a foreign entry
 		// between two hits of one diagonal hides them from each other and both may report the same component.
-		// Only then (or when a sorted list is asked for) are the records sorted / de-duplicated on the host.
-		if (order == MEMS_ORDER_CANONICAL || collision_seen) {
+		// Every component that can be involved was marked on the device (comp_suspect), so only those few
+		// records are compared; a sorted list (ORDER_CANONICAL) is produced on the host when asked for.
+		std::vector<char> drop;
+		size_t n_drop = 0;
+		if (collision_seen) {
+			std::vector<uint8_t> h_suspect(n_comp);
+			MEMS_CUDA(cudaMemcpyAsync(h_suspect.data(), comp_suspect.p, n_comp, cudaMemcpyDeviceToHost, c->stream));
+			MEMS_CUDA(cudaStreamSynchronize(c->stream));
+			std::vector<std::pair<Rec, uint32_t>> sus;  // (record, component index)
+			size_t at = 0;
+			for (uint32_t k = 0; k < n_comp; ++k) {
+				if (h_suspect[k]) sus.push_back({Rec{raw + at}, k});
+				at += (size_t)raw[at] + 2;
+			}
+			std::sort(sus.begin(), sus.end(), [](const std::pair<Rec, uint32_t>& x, const std::pair<Rec, uint32_t>& y) {
+				return rec_less(x.first, y.first) || (!rec_less(y.first, x.first) && x.second < y.second);
+			});
+			drop.assign(n_comp, 0);
+			for (size_t k = 1; k < sus.size(); ++k)
+				if (rec_equal(sus[k].first, sus[k - 1].first)) {
+					drop[sus[k].second] = 1;
+					++n_drop;
+				}
+		}
+		if (order == MEMS_ORDER_CANONICAL) {
 			std::vector<Rec> recs = split_records(raw, n_flat);
 			std::sort(recs.begin(), recs.end(), rec_less);
 			recs.erase(std::unique(recs.begin(), recs.end(), rec_equal), recs.end());
@@ -1159,6 +1200,16 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 			for (const Rec& r2 : recs) out.flat.vec.insert(out.flat.vec.end(), r2.p, r2.p + r2.size());
 			out.flat.release();
 			out.n_matches = recs.size();
+		} else if (n_drop) {
+			out.flat.vec.reserve(n_flat);
+			size_t at = 0;
+			for (uint32_t k = 0; k < n_comp; ++k) {
+				const size_t sz = (size_t)raw[at] + 2;
+				if (!drop[k]) out.flat.vec.insert(out.flat.vec.end(), raw + at, raw + at + sz);
+				at += sz;
+			}
+			out.flat.release();
+			out.n_matches = n_comp - n_drop;
 		} else {
 			out.n_matches = n_comp;
 		}
@@ -1263,6 +1314,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.n_seqs = b.n_seqs;
 	a.mode = mode;
 	// the reference's "match number" puts sequence 0 in the most significant of n_seqs bits; here bit g = sequence g
+	a.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
 	a.seq_set = 0;
 	for (int g = 0; g < b.n_seqs; ++g)
 		if ((seq_mask >> (b.n_seqs - 1 - g)) & 1) a.seq_set |= 1ull << g;
@@ -1381,6 +1433,16 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	Ctx* c = ctx.get();
 	const int W = Comm_world(comm), R = Comm_rank(comm);
 	const size_t K = sizeof(KeyT);
+	const bool trace = getenv("MEMS_TRACE") != nullptr;
+	auto t_last = std::chrono::steady_clock::now();
+	auto mark = [&](const char* what) {
+		if (!trace) return;
+		cudaStreamSynchronize(c->stream);
+		auto now = std::chrono::steady_clock::now();
+		const double ms = std::chrono::duration<double, std::milli>(now - t_last).count();
+		if (R == 0 || ms > 6.0) fprintf(stderr, "[mems trace r%d] %-28s %8.3f ms\n", R, what, ms);
+		t_last = now;
+	};
 	// ---- global layout (identical on every rank)
 	std::vector<SeqMeta> gmeta(n_seqs);
 	uint64_t seed_off = 0;
@@ -1433,6 +1495,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	MEMS_CUDA(cudaMemcpyAsync(g_hist, d_u64.p, sizeof g_hist, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 
+	mark("pack+extract+histogram");
 	// ---- 2. owners of the key ranges; partition the local records by top digit (stable counting pass)
 	uint8_t owner[256];
 	shard_bucket_owners(g_hist, W, owner);
@@ -1443,6 +1506,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		uint32_t* vp[2] = {vals_loc.p, vals_part.p};
 		radix_sort_pairs(c, K == 8, kp, vp, n_loc, top, hist_top.p, "shard_partition_pass");
 	}
+	mark("partition pass");
 	// ---- 3. exchange: counts, then the records of every key range to its owner
 	auto exchange_counts = [&](const std::vector<uint64_t>& mine, std::vector<uint64_t>& theirs) {
 		uint64_t* d_send = d_u64.p + 256;
@@ -1468,6 +1532,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	keys_part.reset();
 	vals_part.reset();
 	vals_loc.reset();
+	mark("all-to-all records");
 	// ---- 4. position-ordered keys of ALL sequences on every rank (window tests read any sequence)
 	DevBuf<uint8_t> key_pos_all(c, s_total * K);
 	{
@@ -1487,6 +1552,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	DevBuf<SeqMeta> d_gmeta(c, n_seqs);
 	MEMS_CUDA(cudaMemcpyAsync(d_gmeta.p, gmeta.data(), sizeof(SeqMeta) * n_seqs, cudaMemcpyHostToDevice, c->stream));
 
+	mark("all-gather keys");
 	// ---- 5. sort the received range; hits of this rank's seed range
 	const void* u_keys = rk_a.p;
 	const uint32_t* u_vals = rv_a.p;
@@ -1509,12 +1575,14 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.n_seqs = n_seqs;
 	a1.mode = mode;
 	a1.seq_set = 0;
+	a1.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
 	a1.packed = nullptr;
 	a1.meta = d_gmeta.p;
 	HitSet hits1;
 	if (n_recv >= 2) find_hits<KeyT>(c, a1, hits1);
 	out.max_run = hits1.max_run;
 
+	mark("sort + run scan");
 	// ---- 6. describe + sort the hits by diagonal hash; ranges of the hash space go to their owner rank
 	const uint32_t n1 = hits1.n;
 	SortPlan hplan = make_sort_plan(64);
@@ -1561,6 +1629,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		                                                                        slen.p, s_mval.p, s_mstr.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
+	mark("hit describe/sort/pack");
 	std::vector<uint64_t> hs(W), hr(W), ms(W), mr(W);
 	for (int d = 0; d < W; ++d) {
 		hs[d] = h_bound[d + 1] - h_bound[d];
@@ -1583,6 +1652,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		comm_all_to_all_v(comm, s_mstr.p, ms.data(), r_mstr.p, mr.data(), 1);
 	}
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers below go out of scope
+	mark("all-to-all hits");
 	// ---- 7. this rank's diagonals: segments, walks, components
 	out.n_hits = n2;
 	if (n2 == 0) return;
@@ -1605,6 +1675,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a2.n = (uint32_t)n_mem2;
 	extend_hits<KeyT>(ctx, a2, reinterpret_cast<const KeyT*>(key_pos_all.p), sd.L, hits2, order, 40000u, out);
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	mark("extend + emit + D2H");
 }
 
 void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,

@@ -172,3 +172,22 @@ def test_masked_memhash_vs_oracle(ctx, orc):
         flat, info = ctx.find_matches(smls, order=mems.ORDER_REFERENCE, seq_mask=mask)
         assert mems.flat_to_matches(flat) == want, mask
         assert info["collisions"] == winfo["collisions"] and info["n_hits"] == winfo["hits"]
+
+
+def test_diagonal_hash_collisions_are_harmless(orc, monkeypatch):
+    """Force many diagonals into few hash buckets (MEMS_TEST_HASH_BITS): segments get split by foreign entries,
+    some components are found twice, and the de-dup of the marked components must restore the exact MatchList."""
+    seed = mems.get_seed(11)
+    gs = synth.genome_family(5, 40000, seed=51, snp_rate=0.03, n_indels=6, max_indel=30)
+    want, winfo = orc.find_matches(0, gs, seed)
+    for bits in (1, 3, 6):
+        monkeypatch.setenv("MEMS_TEST_HASH_BITS", str(bits))
+        c = gpu_context()
+        smls = c.create_smls(gs, seed)
+        flat, info = c.find_matches(smls)  # ORDER_ANY: device order, distinct
+        got = mems.flat_to_matches(flat)
+        assert len(got) == len(set(got)), bits
+        assert sorted(got) == canonical(want), bits
+        flat, info = c.find_matches(smls, order=mems.ORDER_REFERENCE)
+        assert mems.flat_to_matches(flat) == want, bits
+        c.close()
