@@ -143,13 +143,17 @@ void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t
 			MEMS_CUDA(cudaMemcpyAsync(r + byte_offsets[0], d_send, byte_counts[0], cudaMemcpyDeviceToDevice, c->ctx->stream));
 		return;
 	}
+	// every rank sends its slice to every peer and receives theirs: all NVLink ports busy in both directions
+	// (a ring/tree broadcast per rank reached only ~300 GB/s here)
 	check(nccl().GroupStart(), "ncclGroupStart");
-	for (int p = 0; p < c->world; ++p)
-		if (byte_counts[p])
-			check(nccl().Broadcast(p == c->rank ? d_send : nullptr, r + byte_offsets[p], byte_counts[p], ncclChar, p, c->comm,
-			                       c->ctx->stream),
-			      "ncclBroadcast");
+	for (int p = 0; p < c->world; ++p) {
+		if (p == c->rank) continue;
+		if (byte_counts[c->rank]) check(nccl().Send(d_send, byte_counts[c->rank], ncclChar, p, c->comm, c->ctx->stream), "ncclSend");
+		if (byte_counts[p]) check(nccl().Recv(r + byte_offsets[p], byte_counts[p], ncclChar, p, c->comm, c->ctx->stream), "ncclRecv");
+	}
 	check(nccl().GroupEnd(), "ncclGroupEnd");
+	if (byte_counts[c->rank])
+		MEMS_CUDA(cudaMemcpyAsync(r + byte_offsets[c->rank], d_send, byte_counts[c->rank], cudaMemcpyDeviceToDevice, c->ctx->stream));
 }
 
 }  // namespace mems

@@ -191,3 +191,15 @@ def test_diagonal_hash_collisions_are_harmless(orc, monkeypatch):
         flat, info = c.find_matches(smls, order=mems.ORDER_REFERENCE)
         assert mems.flat_to_matches(flat) == want, bits
         c.close()
+
+
+@pytest.mark.parametrize("w", range(11, 22))
+def test_seed_weight_sweep(ctx, orc, w):
+    """BASELINE config 4 at test size: the requested weights 11..21 map to getSeed(w, 0) — including the
+    "weight 11" row that really is a weight-12 pattern — over a dozen related genomes."""
+    seed = mems.get_seed(w)
+    gs = synth.genome_family(12, 12000, seed=60 + w, n_indels=4, max_indel=25)
+    want, winfo = orc.find_matches(0, gs, seed)
+    got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
+    assert got == canonical(want)
+    assert info["n_hits"] == winfo["hits"]
