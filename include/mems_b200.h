@@ -43,6 +43,7 @@ extern "C" {
 typedef struct mems_ctx* mems_ctx_t;
 typedef struct mems_sml* mems_sml_t;
 typedef struct mems_matches* mems_matches_t;
+typedef struct mems_table* mems_table_t;
 
 /* ---- seed patterns: SeedMasks.h:276-401 (host arithmetic, no device needed) ---- */
 uint64_t mems_get_seed(int weight, int seed_rank);           /* getSeed */
@@ -109,6 +110,10 @@ typedef struct {
 	int order;         /* MEMS_ORDER_* */
 	uint32_t table_size; /* MemHash::SetTableSize; 0 = DEFAULT_MEM_TABLE_SIZE 40000 (MemHash.h:30) */
 	uint32_t reserved;
+	mems_table_t table;  /* NULL, or a persistent MemHash table (mems_table_create): the call then runs in
+	                        MEMS_ORDER_REFERENCE against that table and returns the table's WHOLE content, so several
+	                        FindMatches calls with different seed patterns accumulate exactly like the reference's
+	                        ClearSequences() + FindMatches() loop (ProgressiveAligner.cpp:619-653) */
 	uint64_t seq_mask;   /* MaskedMemHash::SetMask (MaskedMemHash.h:22-32): with MEMS_MODE_MEMHASH keep only hits whose
 	                        sequence set equals this mask, sequence 0 = most significant of n_smls bits; 0 = no filter */
 } mems_match_params_t;
@@ -130,6 +135,10 @@ typedef struct {
  * -> distinct matches. */
 int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls,
                       const mems_match_params_t* params, mems_matches_t* out);
+/* MemHash's mem_table as a persistent object (MemHash::Clear empties it, MemHash.cpp:76-93; ClearSequences keeps it) */
+int mems_table_create(uint32_t table_size /* 0 = 40000 */, mems_table_t* out);
+void mems_table_clear(mems_table_t t);
+void mems_table_destroy(mems_table_t t);
 int mems_matches_info(mems_matches_t m, mems_matches_info_t* out);
 /* Flat records [SeqCount, Length, Start(0) .. Start(SeqCount-1)] per match; starts are 1-based,
  * negative = reverse strand, 0 = NO_MATCH (AbstractMatch.h:27, UngappedLocalAlignment.h:201-206). */

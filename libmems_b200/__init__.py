@@ -34,7 +34,7 @@ class SmlInfo(ctypes.Structure):
 
 class MatchParams(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int), ("order", ctypes.c_int), ("table_size", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32), ("seq_mask", _u64)]
+                ("reserved", ctypes.c_uint32), ("table", _vp), ("seq_mask", _u64)]
 
 
 class MatchesInfo(ctypes.Structure):
@@ -52,7 +52,7 @@ EXPORTS = [
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
+    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
 ]
@@ -95,6 +95,9 @@ def load():
     lib.mems_sml_seed_occurrence.argtypes = [_vp, _vp]
     lib.mems_find_matches.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(MatchParams),
                                       ctypes.POINTER(_vp)]
+    lib.mems_table_create.argtypes = [ctypes.c_uint32, ctypes.POINTER(_vp)]
+    lib.mems_table_clear.argtypes = [_vp]
+    lib.mems_table_destroy.argtypes = [_vp]
     lib.mems_matches_info.argtypes = [_vp, ctypes.POINTER(MatchesInfo)]
     lib.mems_matches_copy.argtypes = [_vp, _vp]
     lib.mems_matches_data.argtypes = [_vp]
@@ -242,12 +245,12 @@ class Context:
         return [SortedMerList(self, _vp(out[i])) for i in range(n)]
 
     # -- match finding --------------------------------------------------------------------------------
-    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0):
+    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0, table=None):
         """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches.  Returns (matches, info) where
         matches is a list of tuples (SeqCount, Length, Start(0), ...)."""
         n = len(smls)
         arr = (_vp * n)(*[s.h for s in smls])
-        params = MatchParams(mode, order, table_size, 0, seq_mask)
+        params = MatchParams(mode, order, table_size, 0, table.h if table is not None else None, seq_mask)
         h = _vp()
         self._check(self.lib.mems_find_matches(self.h, n, arr, ctypes.byref(params), ctypes.byref(h)))
         keep = _MatchHandle(self.lib, h)
@@ -276,7 +279,7 @@ class Context:
         parts = [(_host_ptr(s) if s is not None else (0, 0, None)) for s in seqs]
         ptrs = (_vp * n)(*[p[0] for p in parts])
         ls = (_u64 * n)(*[int(x) for x in lens])
-        params = MatchParams(mode, order, 0, 0, 0)
+        params = MatchParams(mode, order, 0, 0, None, 0)
         h = _vp()
         self._check(self.lib.mems_find_matches_sharded(self.h, comm.h, n, ptrs, ls, seed, ctypes.byref(params),
                                                        ctypes.byref(h)))
@@ -307,6 +310,27 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.mems_launch_count(self.h))
+
+
+class HashTable:
+    """Persistent MemHash table: pass it to find_matches(table=...) to accumulate several seed patterns."""
+
+    def __init__(self, table_size=0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.mems_table_create(table_size, ctypes.byref(h))
+        if rc:
+            raise MemsError(rc, "cannot create table")
+        self.h = h
+
+    def clear(self):
+        self.lib.mems_table_clear(self.h)
+
+    def __del__(self):
+        try:
+            self.lib.mems_table_destroy(self.h)
+        except Exception:
+            pass
 
 
 class Communicator:

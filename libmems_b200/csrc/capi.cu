@@ -18,6 +18,9 @@ struct mems_sml {
 struct mems_matches {
 	MatchResult r;
 };
+struct mems_table {
+	HashTable t;
+};
 
 namespace {
 thread_local std::string tl_error;
@@ -266,8 +269,9 @@ int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls, const 
 		}
 		auto* m = new mems_matches();
 		try {
-			find_matches_on_batch(*b, p.mode, p.mode == MEMS_MODE_REPEAT ? MEMS_ORDER_REFERENCE : p.order,
-			                      p.table_size ? p.table_size : 40000u, p.seq_mask, m->r);
+			if (p.table && p.table->t.size == 0) p.table->t.size = p.table_size ? p.table_size : 40000u;
+			find_matches_on_batch(*b, p.mode, (p.mode == MEMS_MODE_REPEAT || p.table) ? MEMS_ORDER_REFERENCE : p.order,
+			                      p.table_size ? p.table_size : 40000u, p.seq_mask, m->r, p.table ? &p.table->t : nullptr);
 		} catch (...) {
 			delete m;
 			throw;
@@ -275,6 +279,24 @@ int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls, const 
 		*out = m;
 	});
 }
+
+int mems_table_create(uint32_t table_size, mems_table_t* out) {
+	if (!out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	return guarded(nullptr, [&] {
+		auto* t = new mems_table();
+		t->t.size = table_size ? table_size : 40000u;
+		*out = t;
+	});
+}
+
+void mems_table_clear(mems_table_t t) {
+	if (!t) return;
+	const uint32_t size = t->t.size;
+	t->t = HashTable();
+	t->t.size = size;
+}
+
+void mems_table_destroy(mems_table_t t) { delete t; }
 
 int mems_matches_info(mems_matches_t m, mems_matches_info_t* out) {
 	if (!m || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");

@@ -246,7 +246,23 @@ struct MatchResult {
 	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0, n_segments = 0;
 	uint32_t seq_count = 0, seed_length = 0;
 };
-void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out);
+// The reference's MemHash::mem_table replayed on the host (ORDER_REFERENCE): buckets of stored, extended matches.
+// Persistent instances let several FindMatches calls (different seed patterns) accumulate into one table
+// (MemHash::ClearSequences keeps the table, MemHash.cpp:72-74).
+struct TableEntry {
+	uint32_t seqcount;
+	int64_t len, mersize, offset;
+	const int64_t* start;  // seqcount values
+	std::vector<int64_t> own;
+};
+struct HashTable {
+	uint32_t size = 0;
+	std::vector<std::vector<TableEntry*>> buckets;
+	std::vector<std::unique_ptr<TableEntry>> stored;
+	uint64_t mem_count = 0, collisions = 0;
+};
+void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
+                           HashTable* persistent = nullptr);
 void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
                           uint64_t seed, int mode, int order, MatchResult& out);
 

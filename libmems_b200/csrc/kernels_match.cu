@@ -793,12 +793,7 @@ std::vector<Rec> split_records(const int64_t* flat, size_t n) {
 // MatchHashEntry::Contains (MatchHashEntry.cpp:164-200), strict_start_lessthan_ptr (:48-67) and
 // CalculateOffset (:141-160).  Needed because the table's lower_bound over a comparator that is not a
 // strict weak order decides WHICH hits are dropped as collisions and the output order.
-struct Entry {
-	uint32_t seqcount;
-	int64_t len, mersize, offset;
-	const int64_t* start;  // seqcount values
-	std::vector<int64_t> own;
-};
+typedef TableEntry Entry;  // common.cuh
 inline int64_t e_start(const Entry& e, uint32_t i) { return i < e.seqcount ? e.start[i] : 0; }
 inline uint32_t e_first(const Entry& e) {
 	for (uint32_t i = 0; i < e.seqcount; ++i)
@@ -1023,7 +1018,7 @@ static void find_pair_hits(Ctx* c, const MatchArgs& a, HitSet& hits, DevBuf<uint
 // ---- stage B: hits (members readable through a.keys / a.vals) -> extended, distinct matches
 template <class KeyT>
 static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT* key_pos, int L, HitSet& hits, int order,
-                        uint32_t table_size, MatchResult& out) {
+                        uint32_t table_size, MatchResult& out, HashTable* persistent = nullptr) {
 	Ctx* c = ctx.get();
 	const int mode = a.mode;
 	const uint32_t n_hits = hits.n;
@@ -1250,8 +1245,16 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	std::vector<size_t> rec_start;
 	for (size_t i = 0; i < n_flat; i += (size_t)raw[i] + 2) rec_start.push_back(i);
 
-	std::vector<std::vector<Entry*>> table(table_size);
-	std::vector<std::unique_ptr<Entry>> stored;
+	// the table of this call, or the caller's persistent one (several FindMatches calls into one MemHash table)
+	HashTable local_table;
+	HashTable& T = persistent ? *persistent : local_table;
+	if (T.buckets.empty()) {
+		T.size = persistent && persistent->size ? persistent->size : table_size;
+		T.buckets.resize(T.size);
+	}
+	table_size = T.size;
+	std::vector<std::vector<Entry*>>& table = T.buckets;
+	std::vector<std::unique_ptr<Entry>>& stored = T.stored;
 	std::vector<int64_t> probe_start;
 	for (uint32_t h = 0; h < n_hits; ++h) {
 		const uint32_t m0 = h_off[h], m1 = h + 1 < n_hits ? h_off[h + 1] : n_mem;
@@ -1272,7 +1275,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 		std::vector<Entry*>& bucket = table[(size_t)(((probe.offset % ts) + ts) % ts)];
 		size_t at = bucket_lower_bound(bucket, probe);
 		if (at != bucket.size() && !e_compare(*bucket[at], probe) && !e_compare(probe, *bucket[at])) {
-			++out.collisions;
+			++T.collisions;
 			continue;
 		}
 		// "ExtendMatch": the extended form of this hit is the component the device computed for it
@@ -1281,13 +1284,16 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 		e->seqcount = (uint32_t)rec[0];
 		e->len = rec[1];
 		e->mersize = 0;  // stored copies lose m_mersize (MatchHashEntry.cpp:118-126)
-		e->start = rec + 2;
+		e->own.assign(rec + 2, rec + 2 + rec[0]);
+		e->start = e->own.data();
 		e_calc_offset(*e);
 		at = bucket_lower_bound(bucket, *e);
 		bucket.insert(bucket.begin() + at, e.get());
 		stored.push_back(std::move(e));
-		++out.mem_count;
+		++T.mem_count;
 	}
+	out.mem_count = T.mem_count;
+	out.collisions = T.collisions;
 	// MemHash::GetMatchList (MemHash.h:183-203): buckets in order, front to back
 	for (auto& bucket : table)
 		for (Entry* e : bucket) {
@@ -1295,16 +1301,32 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 			out.flat.vec.push_back(e->len);
 			out.flat.vec.insert(out.flat.vec.end(), e->start, e->start + e->seqcount);
 		}
-	out.flat.release();  // the stored entries pointed into the raw buffer until here
-	out.n_matches = out.mem_count;
+	out.flat.release();
+	out.n_matches = stored.size();
+}
+
+static void emit_table(const HashTable& T, MatchResult& out) {
+	for (auto& bucket : T.buckets)
+		for (const TableEntry* e : bucket) {
+			out.flat.vec.push_back(e->seqcount);
+			out.flat.vec.push_back(e->len);
+			out.flat.vec.insert(out.flat.vec.end(), e->start, e->start + e->seqcount);
+		}
+	out.n_matches = T.stored.size();
+	out.mem_count = T.mem_count;
+	out.collisions = T.collisions;
 }
 
 template <class KeyT>
-static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out) {
+static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
+                               HashTable* persistent) {
 	Ctx* c = b.ctx.get();
 	out.seq_count = (uint32_t)b.n_seqs;
 	out.seed_length = (uint32_t)b.sd.L;
-	if (b.n_total < 2) return;
+	if (b.n_total < 2) {
+		if (persistent) emit_table(*persistent, out);
+		return;
+	}
 	MatchArgs a;
 	a.keys = b.keys.p;
 	a.vals = b.vals.p;
@@ -1333,17 +1355,22 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	}
 	out.max_run = hits.max_run;
 	out.n_hits = hits.n;
-	if (hits.n == 0) return;
-	extend_hits<KeyT>(b.ctx, a, reinterpret_cast<const KeyT*>(b.keys_by_pos.p), b.sd.L, hits, order, table_size, out);
+	if (hits.n == 0) {
+		if (persistent) emit_table(*persistent, out);  // nothing new: the result is still the whole table
+		return;
+	}
+	extend_hits<KeyT>(b.ctx, a, reinterpret_cast<const KeyT*>(b.keys_by_pos.p), b.sd.L, hits, order, table_size, out, persistent);
 }
 
-void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out) {
+void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
+                           HashTable* persistent) {
+	if (persistent && order != MEMS_ORDER_REFERENCE) throw Error(MEMS_ERR_INVALID, "a persistent table needs MEMS_ORDER_REFERENCE");
 	if (seq_mask && mode != MEMS_MODE_MEMHASH) throw Error(MEMS_ERR_INVALID, "seq_mask applies to MEMS_MODE_MEMHASH only");
 	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
 	if (b.key64)
-		find_matches_typed<uint64_t>(b, mode, order, table_size, seq_mask, out);
+		find_matches_typed<uint64_t>(b, mode, order, table_size, seq_mask, out, persistent);
 	else
-		find_matches_typed<uint32_t>(b, mode, order, table_size, seq_mask, out);
+		find_matches_typed<uint32_t>(b, mode, order, table_size, seq_mask, out, persistent);
 }
 
 // ================================================================================================ sharded (multi-GPU)

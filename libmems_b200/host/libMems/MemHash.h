@@ -15,11 +15,17 @@ static const uint32_t DEFAULT_ENUMERATION_TOLERANCE = 1;
 
 class MemHash {
 public:
-	MemHash() { reset(); }
-	virtual ~MemHash() { free_stored(); }
+	MemHash() : table(nullptr) { reset(); }
+	virtual ~MemHash() {
+		free_stored();
+		if (table) mems_table_destroy(table);
+	}
+	MemHash(const MemHash&) = delete;
+	MemHash& operator=(const MemHash&) = delete;
 	virtual void Clear() {  // MemHash.cpp:76-93: also drops the stored matches
 		ClearSequences();
 		free_stored();
+		if (table) mems_table_clear(table);
 		reset();
 	}
 	virtual void ClearSequences() { sar_table.clear(); }  // keeps the table: further FindMatches calls accumulate
@@ -45,11 +51,20 @@ public:
 		p.order = order;
 		p.table_size = table_size;
 		p.seq_mask = seq_mask();
+		if (order == MEMS_ORDER_REFERENCE && mode() != MEMS_MODE_REPEAT) {
+			// the reference's table lives across FindMatches calls (several seed patterns accumulate in it)
+			if (!table) Context::check(mems_table_create(table_size, &table));
+			p.table = table;
+		}
 		mems_matches_t m = nullptr;
 		Context::check(mems_find_matches(Context::get(), (int)h.size(), h.data(), &p, &m));
 		mems_matches_info_t info;
 		Context::check(mems_matches_info(m, &info));
 		const int64_t* flat = mems_matches_data(m);
+		if (p.table) {  // the result is the whole table: it replaces what was stored, counters are cumulative
+			free_stored();
+			m_mem_count = m_collision_count = 0;
+		}
 		for (uint64_t i = 0; i < info.n_flat;) {
 			const unsigned k = (unsigned)flat[i];
 			Match* mm = new Match(k);
@@ -98,6 +113,7 @@ protected:
 	uint32_t table_size, m_repeat_tolerance, m_enumeration_tolerance;
 	uint64_t m_mem_count, m_collision_count;
 	int order;
+	mems_table_t table;
 };
 
 class MaskedMemHash : public MemHash {  // MaskedMemHash.h:21-40

@@ -503,6 +503,7 @@ static void hash_match(const finder_t* f, table_t* t, int seqcount, const int* s
 	add_hash_entry(f, t, e);
 }
 
+static table_t* g_accum = NULL; /* open accumulation, see orc_accumulate_begin */
 static uint64_t g_seq_mask = 0; /* MaskedMemHash::SetMask; 0 = no filter (MaskedMemHash.h:22-32) */
 
 int orc_find_matches_masked(int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed,
@@ -549,10 +550,16 @@ int orc_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 		}
 	qsort(occ, total, sizeof(occ_t), occ_cmp);
 
-	table_t t;
-	memset(&t, 0, sizeof t);
-	t.table_size = 40000; /* DEFAULT_MEM_TABLE_SIZE, MemHash.h:30 */
-	t.buckets = (bucket_t*)calloc(t.table_size, sizeof(bucket_t));
+	/* the table lives across calls while an accumulation is open (MemHash::ClearSequences keeps mem_table,
+	 * MemHash.cpp:72-74; several seed patterns then share one table, ProgressiveAligner.cpp:619-653) */
+	table_t t_local;
+	table_t* tp = g_accum ? g_accum : &t_local;
+	if (!g_accum) {
+		memset(tp, 0, sizeof *tp);
+		tp->table_size = 40000; /* DEFAULT_MEM_TABLE_SIZE, MemHash.h:30 */
+		tp->buckets = (bucket_t*)calloc(tp->table_size, sizeof(bucket_t));
+	}
+#define t (*tp)
 	uint64_t max_run = 0;
 
 	int* slot = (int*)malloc(sizeof(int) * 1024);
@@ -638,11 +645,11 @@ int orc_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 			flat[w++] = e->seqcount;
 			flat[w++] = e->len;
 			for (int s = 0; s < e->seqcount; ++s) flat[w++] = e->start[s];
-			mhe_free(e);
+			if (!g_accum) mhe_free(e);
 		}
-		free(t.buckets[b].v);
+		if (!g_accum) free(t.buckets[b].v);
 	}
-	free(t.buckets);
+	if (!g_accum) free(t.buckets);
 	free(occ);
 	for (int g = 0; g < n_seqs; ++g) free(f.keys[g]);
 	free(f.keys);
@@ -657,6 +664,26 @@ int orc_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 		counts_out[3] = max_run;
 	}
 	return 0;
+#undef t
+}
+
+int orc_accumulate_begin(void) {
+	if (g_accum) return 1;
+	g_accum = (table_t*)calloc(1, sizeof(table_t));
+	g_accum->table_size = 40000;
+	g_accum->buckets = (bucket_t*)calloc(g_accum->table_size, sizeof(bucket_t));
+	return 0;
+}
+
+void orc_accumulate_end(void) {
+	if (!g_accum) return;
+	for (uint32_t b = 0; b < g_accum->table_size; ++b) {
+		for (size_t i = 0; i < g_accum->buckets[b].n; ++i) mhe_free(g_accum->buckets[b].v[i]);
+		free(g_accum->buckets[b].v);
+	}
+	free(g_accum->buckets);
+	free(g_accum);
+	g_accum = NULL;
 }
 
 /* ------------------------------------------------------------------ SeedOccurrenceList */

@@ -29,6 +29,7 @@ double now_s() {
 }
 std::string g_err;
 uint64 g_seq_mask = 0;
+MemHash* g_accum_mh = NULL;
 }
 
 extern "C" {
@@ -117,7 +118,8 @@ int ref_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 		}
 		double t1 = now_s();
 		MemHash* mh = NULL;
-		if (mode == 0) mh = new MemHash();
+		if (g_accum_mh) mh = g_accum_mh;
+		else if (mode == 0) mh = new MemHash();
 		else if (mode == 1) mh = new RepeatHash();
 		else if (mode == 2) mh = new PairwiseMatchFinder();
 		else if (mode == 3) {
@@ -126,6 +128,7 @@ int ref_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 			mh = mm;
 		}
 		else { g_err = "bad mode"; return 3; }
+		if (g_accum_mh) mh->ClearSequences();  // keeps the table (MemHash.cpp:72-74)
 		mh->FindMatches(ml);
 		double t2 = now_s();
 		if (times_out) { times_out[0] = t1 - t0; times_out[1] = t2 - t1; }
@@ -141,8 +144,10 @@ int ref_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 		*n_flat_out = flat.size();
 		*flat_out = (int64_t*)malloc(sizeof(int64_t) * (flat.size() ? flat.size() : 1));
 		memcpy(*flat_out, flat.data(), sizeof(int64_t) * flat.size());
-		mh->Clear();
-		delete mh;
+		if (!g_accum_mh) {
+			mh->Clear();
+			delete mh;
+		}
 		ml.Clear();
 		return 0;
 	} catch (gnException& e) {
@@ -151,6 +156,20 @@ int ref_find_matches(int mode, int n_seqs, const char* const* seqs, const uint64
 	} catch (const char* s) {
 		g_err = s;
 		return 2;
+	}
+}
+
+// One MemHash kept across ref_find_matches calls (mode 0), the way ProgressiveAligner.cpp:619-653 accumulates the
+// matches of several seed patterns: Clear() once, then ClearSequences() + FindMatches() per pattern.
+void ref_accumulate_begin() {
+	if (!g_accum_mh) g_accum_mh = new MemHash();
+	g_accum_mh->Clear();
+}
+void ref_accumulate_end() {
+	if (g_accum_mh) {
+		g_accum_mh->Clear();
+		delete g_accum_mh;
+		g_accum_mh = NULL;
 	}
 }
 

@@ -116,6 +116,16 @@ class Oracle(_Checker):
         info = {"mem_count": counts[0], "collisions": counts[1], "hits": counts[2], "max_run": counts[3]}
         return flat_to_matches(out), info
 
+    def find_matches_multi_seed(self, seqs, seeds):
+        """One table across several seed patterns (ClearSequences between FindMatches calls)."""
+        self.lib.orc_accumulate_begin()
+        try:
+            for sd in seeds:
+                out = self.find_matches(0, seqs, sd)
+            return out
+        finally:
+            self.lib.orc_accumulate_end()
+
     def find_matches_masked(self, seqs, seed, seq_mask):
         bufs, arr, lens, flat, nflat, nm = _Checker.find_matches(self, 0, seqs, seed)
         counts = (u64 * 4)()
@@ -182,6 +192,15 @@ class Reference(_Checker):
         self.lib.ref_free(flat)
         info = {"mem_count": counts[0], "collisions": counts[1], "sml_s": times[0], "find_s": times[1]}
         return flat_to_matches(out), info
+
+    def find_matches_multi_seed(self, seqs, seeds):
+        self.lib.ref_accumulate_begin()
+        try:
+            for sd in seeds:
+                out = self.find_matches(0, seqs, sd)
+            return out
+        finally:
+            self.lib.ref_accumulate_end()
 
     def find_matches_masked(self, seqs, seed, seq_mask):
         self.lib.ref_set_seq_mask(u64(seq_mask))

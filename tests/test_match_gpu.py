@@ -203,3 +203,21 @@ def test_seed_weight_sweep(ctx, orc, w):
     got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
     assert got == canonical(want)
     assert info["n_hits"] == winfo["hits"]
+
+
+@pytest.mark.parametrize("it", range(4))
+def test_multi_seed_accumulation(ctx, orc, it):
+    """Three seed ranks accumulated in one table (ClearSequences + FindMatches per pattern, ProgressiveAligner.cpp:619-653)."""
+    gs = synth.genome_family(2 + it % 2, 20000 + 3000 * it, seed=70 + it, snp_rate=0.04, n_indels=5, max_indel=20)
+    w = 11 + 2 * it
+    seeds = [mems.get_seed(w, r) for r in range(3)]
+    want, winfo = orc.find_matches_multi_seed(gs, seeds)
+    table = mems.HashTable()
+    for sd in seeds:
+        smls = ctx.create_smls(gs, sd)
+        flat, info = ctx.find_matches(smls, table=table)
+    assert mems.flat_to_matches(flat) == want
+    assert info["mem_count"] == winfo["mem_count"] and info["collisions"] == winfo["collisions"]
+    table.clear()
+    flat, info = ctx.find_matches(ctx.create_smls(gs, seeds[0]), table=table)
+    assert mems.flat_to_matches(flat) == orc.find_matches(0, gs, seeds[0])[0]

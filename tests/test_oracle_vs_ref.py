@@ -83,3 +83,16 @@ def test_masked_memhash(libs):
         mr, ir = R.find_matches_masked(gs, seed, mask)
         assert mo == mr, mask
         assert io["collisions"] == ir["collisions"]
+
+
+@pytest.mark.parametrize("it", range(4))
+def test_multi_seed_accumulation(libs, it):
+    """Three seed ranks accumulated in one MemHash table (ProgressiveAligner.cpp:619-653)."""
+    O, R = libs
+    gs = synth.genome_family(2 + it % 2, 8000 + 1000 * it, seed=70 + it, snp_rate=0.04, n_indels=5, max_indel=20)
+    w = 11 + 2 * it
+    seeds = [O.get_seed(w, r) for r in range(3)]
+    mo, io = O.find_matches_multi_seed(gs, seeds)
+    mr, ir = R.find_matches_multi_seed(gs, seeds)
+    assert mo == mr
+    assert io["mem_count"] == ir["mem_count"] and io["collisions"] == ir["collisions"]
