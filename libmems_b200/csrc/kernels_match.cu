@@ -29,6 +29,8 @@
 #include <cstring>
 #include <unordered_map>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "mems_b200.h"
 #include "seed_dev.cuh"
@@ -48,6 +50,8 @@ struct MatchArgs {
 	int mode;
 	uint64_t seq_set;  // MaskedMemHash filter: required member set, bit g = sequence g (0 = no filter)
 	int test_hash_bits;  // 0 = use the full diagonal hash; n > 0 keeps only n bits (tests force bucket collisions with it)
+	int warp_budget;     // probes one warp spends on a walk before a CTA takes over (kWarpProbeBudget; tests shrink it)
+	int cta_budget;      // rounds one CTA spends before the whole grid takes over (kCtaRoundBudget; tests shrink it)
 	const uint32_t* packed;
 	const SeqMeta* meta;
 };
@@ -509,7 +513,7 @@ walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView 
 	const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
 	const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
 	bool linked, exhausted;
-	c += w.walk(c, +1, L, has_next ? next_at - c : -1, &linked, kWarpProbeBudget, &exhausted);
+	c += w.walk(c, +1, L, has_next ? next_at - c : -1, &linked, a.warp_budget, &exhausted);
 	if (exhausted) {  // hand the rest of this walk to a whole CTA (long_walk_kernel)
 		if (w.lane == 0) {
 			const uint32_t at = atomicAdd(defer_count, 1u);
@@ -564,7 +568,7 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, lane};
 	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 	bool linked, exhausted;
-	const int32_t c = -w.walk(0, -1, L, -1, &linked, kWarpProbeBudget, &exhausted);
+	const int32_t c = -w.walk(0, -1, L, -1, &linked, a.warp_budget, &exhausted);
 	if (lane == 0) comp_rep[comp] = hi;
 	if (exhausted) {
 		if (lane == 0) {
@@ -584,16 +588,23 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 // would be the critical path of the whole call.  Walks that exhaust their warp budget are finished here by
 // a 32-warp CTA: every round the warps probe 32 x 128 consecutive windows at once, each summarises its 128
 // bits (first match, end of the chain that starts there, last match) and thread 0 stitches the summaries.
-constexpr int kLongWarps = 32;
+constexpr int kLongWarps = 16;   // warps per CTA: two CTAs share an SM, so one's barrier waits overlap the other's probes
 constexpr int kLongSpan = kLongWarps * 128;
+constexpr int kCtaRoundBudget = 192; // rounds one CTA spends on a walk before the whole grid takes it over
 
 template <class KeyT>
 __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_t stop_dist, bool* linked, int4* s_sum,
-                            int32_t* s_result) {
+                            int32_t* s_result, int max_rounds, bool* exhausted) {
 	typedef typename WarpHit<KeyT>::mask_t mask_t;
 	const int warp = threadIdx.x >> 5;
 	int32_t walked = 0;
-	while (true) {
+	*exhausted = false;
+	for (int round = 0;; ++round) {
+		if (round == max_rounds) {  // still going: hand it to the whole grid (giant_walk_kernel)
+			*exhausted = true;
+			*linked = false;
+			return walked;
+		}
 		const mask_t m = w.probe(k0 + dir * (walked + 128 * warp), dir, 128);
 		// summary of this warp's 128 windows (distances 1..128 from its own base): first match, last match of
 		// the chain that starts at the first match, last match overall
@@ -638,15 +649,22 @@ __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_
 }
 
 template <class KeyT>
-__global__ void __launch_bounds__(kLongWarps * 32, 1)
+__global__ void __launch_bounds__(kLongWarps * 32, 2)
 long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ defer,
-                       const uint32_t* __restrict__ defer_count, uint32_t* __restrict__ seg_link,
-                       uint32_t* __restrict__ seg_reach) {
+                       const uint32_t* __restrict__ defer_count, uint32_t* __restrict__ next_item,
+                       uint32_t* __restrict__ seg_link, uint32_t* __restrict__ seg_reach, uint2* __restrict__ giant,
+                       uint32_t* __restrict__ giant_count) {
 	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
 	__shared__ int4 s_sum[kLongWarps];
 	__shared__ int32_t s_result[2];
+	__shared__ uint32_t s_item;
 	const uint32_t n_defer = *defer_count;
-	for (uint32_t i = blockIdx.x; i < n_defer; i += gridDim.x) {
+	while (true) {  // walks differ in length by orders of magnitude: CTAs pull them from a queue
+		if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1u);
+		__syncthreads();
+		const uint32_t i = s_item;
+		__syncthreads();
+		if (i >= n_defer) break;
 		const uint32_t seg = defer[i].x;
 		int32_t c = (int32_t)defer[i].y;
 		const uint32_t hi = v.seg_head[seg];
@@ -657,25 +675,36 @@ long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, Seg
 		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 		const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
 		const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
-		bool linked;
-		c += cta_walk<KeyT>(w, c, +1, L, has_next ? next_at - c : -1, &linked, s_sum, s_result);
+		bool linked, exhausted;
+		c += cta_walk<KeyT>(w, c, +1, L, has_next ? next_at - c : -1, &linked, s_sum, s_result, a.cta_budget, &exhausted);
 		if (threadIdx.x == 0) {
-			seg_link[seg] = linked ? 1u : 0u;
-			seg_reach[seg] = (uint32_t)(x0 + c);
+			if (exhausted) {
+				giant[atomicAdd(giant_count, 1u)] = make_uint2(seg, (uint32_t)c);
+			} else {
+				seg_link[seg] = linked ? 1u : 0u;
+				seg_reach[seg] = (uint32_t)(x0 + c);
+			}
 		}
 	}
 }
 
 template <class KeyT>
-__global__ void __launch_bounds__(kLongWarps * 32, 1)
+__global__ void __launch_bounds__(kLongWarps * 32, 2)
 long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ defer,
-                      const uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ first_excl,
-                      uint32_t* __restrict__ comp_left) {
+                      const uint32_t* __restrict__ defer_count, uint32_t* __restrict__ next_item,
+                      const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_left, uint2* __restrict__ giant,
+                      uint32_t* __restrict__ giant_count) {
 	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
 	__shared__ int4 s_sum[kLongWarps];
 	__shared__ int32_t s_result[2];
+	__shared__ uint32_t s_item;
 	const uint32_t n_defer = *defer_count;
-	for (uint32_t i = blockIdx.x; i < n_defer; i += gridDim.x) {
+	while (true) {
+		if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1u);
+		__syncthreads();
+		const uint32_t i = s_item;
+		__syncthreads();
+		if (i >= n_defer) break;
 		const uint32_t seg = defer[i].x;  // always the first segment of its component
 		int32_t c = (int32_t)defer[i].y;
 		const uint32_t hi = v.seg_head[seg];
@@ -683,9 +712,125 @@ long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegV
 		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
 		WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
 		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
-		bool linked;
-		c -= cta_walk<KeyT>(w, c, -1, L, -1, &linked, s_sum, s_result);
-		if (threadIdx.x == 0) comp_left[first_excl[seg]] = (uint32_t)(x0 + c);
+		bool linked, exhausted;
+		c -= cta_walk<KeyT>(w, c, -1, L, -1, &linked, s_sum, s_result, a.cta_budget, &exhausted);
+		if (threadIdx.x == 0) {
+			if (exhausted) giant[atomicAdd(giant_count, 1u)] = make_uint2(seg, (uint32_t)c);
+			else comp_left[first_excl[seg]] = (uint32_t)(x0 + c);
+		}
+	}
+}
+
+
+// ---- giant walks ------------------------------------------------------------------------------------
+// The few walks that outlast a CTA's budget too (two sequences that agree for Mbp while the others differ) are
+// finished by the WHOLE GRID, one walk at a time: every CTA probes its own span of kLongSpan windows, the
+// per-CTA summaries meet in global memory, CTA 0 stitches them (same rule as inside a CTA) and a grid-wide
+// barrier publishes the result.  One round covers gridDim x 2048 windows (~600 k on a B200), so the longest
+// diagonal of a genome set costs a handful of rounds instead of being the critical path of the whole call.
+struct ChainSummary {
+	int first, chain_end, last;  // 1-based distances inside the summarised span, 0 = no match
+};
+__device__ inline ChainSummary combine_summaries(const int4* child, int n, int unit, int L) {
+	ChainSummary r{0, 0, 0};
+	int cur = 0;
+	bool broken = false;
+	for (int i = 0; i < n; ++i) {
+		const int4 c = child[i];
+		if (!c.x) continue;
+		const int f = unit * i + c.x, ce = unit * i + c.y;
+		if (!r.first) {
+			r.first = f;
+			cur = ce;
+			broken = c.y != c.z;
+		} else if (!broken) {
+			if (f - cur > L) broken = true;
+			else {
+				cur = ce;
+				if (c.y != c.z) broken = true;
+			}
+		}
+		r.last = unit * i + c.z;
+	}
+	r.chain_end = cur;
+	return r;
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(kLongWarps * 32, 2)
+giant_walk_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ giant,
+                  const uint32_t* __restrict__ giant_count, int dir, const uint32_t* __restrict__ first_excl,
+                  uint32_t* __restrict__ seg_link, uint32_t* __restrict__ seg_reach, uint32_t* __restrict__ comp_left,
+                  int4* __restrict__ g_sum, int32_t* __restrict__ g_state) {
+	typedef typename WarpHit<KeyT>::mask_t mask_t;
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
+	__shared__ int4 s_sum[kLongWarps];
+	const int warp = threadIdx.x >> 5;
+	const uint32_t n_items = *giant_count;
+	for (uint32_t it = 0; it < n_items; ++it) {
+		const uint32_t seg = giant[it].x;
+		const int32_t c0 = (int32_t)giant[it].y;
+		const uint32_t hi = v.seg_head[seg];
+		const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
+		const uint32_t h = v.hid[hi];
+		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
+		WarpHit<KeyT> w{a, key_pos, s_mem[warp], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
+		const bool has_next = dir > 0 && seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
+		const int32_t stop_dist = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) - c0 : -1;
+		int32_t walked = 0;
+		int state = 0;
+		while (!state) {
+			const mask_t m = w.probe(c0 + dir * (walked + kLongSpan * (int32_t)blockIdx.x + 128 * warp), dir, 128);
+			const int first = WarpHit<KeyT>::lowest_set(m), last = WarpHit<KeyT>::highest_set(m);
+			int chain_end = 0;
+			if (first) {
+				bool ended;
+				chain_end = WarpHit<KeyT>::follow(m, first, L, 128, &ended);
+				if (!ended) chain_end = last;
+			}
+			if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				const ChainSummary cs = combine_summaries(s_sum, kLongWarps, 128, L);
+				g_sum[blockIdx.x] = make_int4(cs.first, cs.chain_end, cs.last, 0);
+			}
+			grid.sync();
+			if (blockIdx.x == 0 && threadIdx.x == 0) {
+				int32_t cur = 0;  // last confirmed match, as a distance from this round's base
+				int st = 0;       // 0 = ran through the whole span, 1 = chain ended, 2 = linked
+				const int n_cta = (int)gridDim.x;
+				for (int i = 0; i < n_cta && st == 0; ++i) {
+					if (stop_dist >= 0 && stop_dist <= walked + cur + L) st = 2;
+					const int4 sm = g_sum[i];
+					if (st || !sm.x) continue;
+					if (kLongSpan * i + sm.x - cur > L) {
+						st = 1;
+					} else {
+						cur = kLongSpan * i + sm.y;
+						if (stop_dist >= 0 && stop_dist <= walked + cur + L) st = 2;
+						else if (sm.y != sm.z) st = 1;
+					}
+				}
+				if (st == 0 && stop_dist >= 0 && stop_dist <= walked + cur + L) st = 2;
+				if (st == 0 && kLongSpan * n_cta - cur >= L) st = 1;
+				g_state[0] = cur;
+				g_state[1] = st;
+			}
+			grid.sync();
+			walked += g_state[0];
+			state = g_state[1];
+		}
+		if (blockIdx.x == 0 && threadIdx.x == 0) {
+			if (dir > 0) {
+				seg_link[seg] = state == 2 ? 1u : 0u;
+				seg_reach[seg] = (uint32_t)(x0 + c0 + walked);
+			} else {
+				comp_left[first_excl[seg]] = (uint32_t)(x0 + c0 - walked);
+			}
+		}
+		__syncthreads();  // s_mem is rewritten by the next item
 	}
 }
 
@@ -1081,9 +1226,36 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	// ---- 5. extend: right walks link segments into components, left walks finish each component
 	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg, seg_order, suspect.p};
 	DevBuf<uint32_t> seg_link(c, n_seg), seg_reach(c, n_seg), first(c, n_seg), first_excl(c, n_seg);
+	const SegView& v_for_giant = v;
 	DevBuf<uint2> defer(c, n_seg);
 	uint32_t* defer_count = scalars.p + 6;  // [6] right walks, [7] left walks handed to whole CTAs
-	const uint32_t long_grid = (uint32_t)c->sm_count;
+	const uint32_t long_grid = 2u * (uint32_t)c->sm_count;
+	DevBuf<uint32_t> queue_heads(c, 4);  // [0],[1] work-queue heads; [2],[3] giant-walk counts (right, left)
+	MEMS_CUDA(cudaMemsetAsync(queue_heads.p, 0, 4 * sizeof(uint32_t), c->stream));
+	DevBuf<uint2> giant(c, n_seg);
+	int giant_blocks_per_sm = 0;
+	MEMS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&giant_blocks_per_sm, giant_walk_kernel<KeyT>, kLongWarps * 32, 0));
+	const uint32_t giant_grid = (uint32_t)std::max(1, std::min(giant_blocks_per_sm, 2)) * (uint32_t)c->sm_count;
+	DevBuf<int4> g_sum(c, giant_grid);
+	DevBuf<int32_t> g_state(c, 2);
+	auto launch_giant = [&](int dir, uint32_t* count, uint32_t* comp_left_p) {
+		const KeyT* kp_arg = key_pos;
+		int L_arg = L, dir_arg = dir;
+		MatchArgs a_arg = a;
+		SegView v_arg = v_for_giant;
+		const uint2* giant_p = giant.p;
+		const uint32_t* count_p = count;
+		const uint32_t* fe_p = first_excl.p;
+		uint32_t* link_p = seg_link.p;
+		uint32_t* reach_p = seg_reach.p;
+		int4* sum_p = g_sum.p;
+		int32_t* state_p = g_state.p;
+		void* args[] = {&a_arg, &kp_arg, &L_arg, &v_arg, &giant_p, &count_p, &dir_arg, &fe_p, &link_p, &reach_p, &comp_left_p,
+		                &sum_p, &state_p};
+		KernelScope ks(c, dir > 0 ? "giant_walk_right" : "giant_walk_left");
+		MEMS_CUDA(cudaLaunchCooperativeKernel((void*)giant_walk_kernel<KeyT>, dim3(giant_grid), dim3(kLongWarps * 32), args, 0,
+		                                      c->stream));
+	};
 	const uint32_t walk_blocks = (n_seg + kExtendWarps - 1) / kExtendWarps, seg_blocks = (n_seg + 255) / 256;
 	{
 		KernelScope ks(c, "walk_right");
@@ -1094,9 +1266,10 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	{
 		KernelScope ks(c, "long_walk_right");
 		long_walk_right_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, key_pos, L, v, defer.p, defer_count,
-		                                                                           seg_link.p, seg_reach.p);
+		                                                                           queue_heads.p, seg_link.p, seg_reach.p, giant.p, queue_heads.p + 2);
 		MEMS_CUDA(cudaGetLastError());
 	}
+	launch_giant(+1, queue_heads.p + 2, nullptr);
 	{
 		KernelScope ks(c, "chain_first");
 		chain_first_kernel<<<seg_blocks, 256, 0, c->stream>>>(seg_link.p, n_seg, first.p);
@@ -1132,9 +1305,10 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	{
 		KernelScope ks(c, "long_walk_left");
 		long_walk_left_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, key_pos, L, v, defer.p, defer_count + 1,
-		                                                                          first_excl.p, comp_left.p);
+		                                                                          queue_heads.p + 1, first_excl.p, comp_left.p, giant.p, queue_heads.p + 3);
 		MEMS_CUDA(cudaGetLastError());
 	}
+	launch_giant(-1, queue_heads.p + 3, comp_left.p);
 
 	// ---- 6. emit
 	const uint32_t comp_blocks = (n_comp + 255) / 256;
@@ -1337,6 +1511,8 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.mode = mode;
 	// the reference's "match number" puts sequence 0 in the most significant of n_seqs bits; here bit g = sequence g
 	a.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
+	a.warp_budget = getenv("MEMS_TEST_WALK_BUDGET") ? atoi(getenv("MEMS_TEST_WALK_BUDGET")) : kWarpProbeBudget;
+	a.cta_budget = getenv("MEMS_TEST_WALK_BUDGET") ? atoi(getenv("MEMS_TEST_WALK_BUDGET")) : kCtaRoundBudget;
 	a.seq_set = 0;
 	for (int g = 0; g < b.n_seqs; ++g)
 		if ((seq_mask >> (b.n_seqs - 1 - g)) & 1) a.seq_set |= 1ull << g;
@@ -1603,6 +1779,8 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.mode = mode;
 	a1.seq_set = 0;
 	a1.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
+	a1.warp_budget = kWarpProbeBudget;
+	a1.cta_budget = kCtaRoundBudget;
 	a1.packed = nullptr;
 	a1.meta = d_gmeta.p;
 	HitSet hits1;

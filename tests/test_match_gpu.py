@@ -221,3 +221,25 @@ def test_multi_seed_accumulation(ctx, orc, it):
     table.clear()
     flat, info = ctx.find_matches(ctx.create_smls(gs, seeds[0]), table=table)
     assert mems.flat_to_matches(flat) == orc.find_matches(0, gs, seeds[0])[0]
+
+
+def test_grid_wide_walks(orc, monkeypatch):
+    """With the warp and CTA budgets shrunk to 2, the long diagonals of the sparse-hit inputs are finished by the
+    grid-cooperative walker (all CTAs on one walk, grid barrier per round), including the linking case."""
+    monkeypatch.setenv("MEMS_TEST_WALK_BUDGET", "2")
+    c = gpu_context()
+    seed = mems.get_seed(15)
+    rng = np.random.default_rng(98)
+    T = synth.random_genome(40_000, rng)
+    M1, M2 = synth.random_genome(60, rng), synth.random_genome(60, rng)
+    for X in (np.concatenate([T, M1, T]), np.concatenate([T, M1, T, M2, T])):
+        for other in (X, synth.revcomp(X)):
+            want, _ = orc.find_matches(0, [X, other], seed)
+            smls = c.create_smls([X, other], seed)
+            flat, _ = c.find_matches(smls, order=mems.ORDER_REFERENCE)
+            assert mems.flat_to_matches(flat) == want
+    gs = synth.genome_family(4, 150_000, seed=77)
+    want, _ = orc.find_matches(0, gs, seed)
+    flat, _ = c.find_matches(c.create_smls(gs, seed), order=mems.ORDER_CANONICAL)
+    assert mems.flat_to_matches(flat) == canonical(want)
+    c.close()
