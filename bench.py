@@ -283,8 +283,23 @@ def main():
         hbm_kernels = {k: v for k, v in prof.items() if v["bytes"] > 0}
         roof_name, roof = max(hbm_kernels.items(), key=lambda kv: kv[1]["ms"])
         achieved = roof["bytes"] / roof["ms"] / 1e6
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), if it is the
+        # same kernel and workload
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if roof_name == "radix_pass" and name == "c2" and world == 1:
+                traffic = tj["onesweep_kernel<u32>"]["dram_bytes_per_launch"]
+        except (OSError, KeyError):
+            pass
+        # the SML-build stage as a whole (pack + extract + all radix passes), algorithmic bytes per DESIGN.md §4
+        sml = [prof[k] for k in ("pack", "extract", "radix_pass") if k in prof]
+        sml_ms, sml_bytes = sum(v["ms"] for v in sml), sum(v["bytes"] for v in sml)
         roofline = {"bound": "hbm", "kernel": roof_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None,
+                    "frac": achieved / hbm_peak, "traffic": traffic,
+                    "sml_build": {"ms_per_step": sml_ms / args.steps, "achieved": sml_bytes / sml_ms / 1e6 if sml_ms else None,
+                                  "frac": sml_bytes / sml_ms / 1e6 / hbm_peak if sml_ms else None,
+                                  "mbp_per_s": mbp_total / world / (sml_ms / args.steps / 1e3) if sml_ms else None},
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "launches": roof["launches"], "avg_launch_ms": roof["ms"] / max(roof["launches"], 1),
                     "dominant_kernel_by_time": top[0], "kernel_ms_per_step": total_ms / args.steps,
