@@ -24,6 +24,9 @@ struct SeedDesc {
 	uint8_t run_rshift[kMaxSeedRuns];  // window >> rshift brings the run's last base to bits 1..0
 	uint8_t run_bits[kMaxSeedRuns];    // 2 * run length
 	uint8_t run_lshift[kMaxSeedRuns];  // position of the run inside the right-justified w-mer
+	// the same runs as one shift + one mask each: mer |= (window >> run_net[r]) & run_mask[r]
+	uint8_t run_net[kMaxSeedRuns];     // rshift - lshift (always >= 64 - 2L >= 2)
+	uint64_t run_mask[kMaxSeedRuns];   // ((1 << run_bits) - 1) << run_lshift
 };
 
 // One sequence of a batch, as laid out in device memory.

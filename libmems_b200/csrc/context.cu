@@ -130,6 +130,8 @@ SeedDesc make_seed_desc(uint64_t seed) {
 		sd.run_rshift[sd.n_runs] = (uint8_t)(62 - 2 * b);
 		sd.run_bits[sd.n_runs] = (uint8_t)(2 * len);
 		sd.run_lshift[sd.n_runs] = (uint8_t)(2 * (sd.w - ones_before - len));
+		sd.run_net[sd.n_runs] = (uint8_t)(sd.run_rshift[sd.n_runs] - sd.run_lshift[sd.n_runs]);
+		sd.run_mask[sd.n_runs] = ((len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull))) << sd.run_lshift[sd.n_runs];
 		sd.n_runs++;
 		ones_before += len;
 	}

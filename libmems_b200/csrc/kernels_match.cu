@@ -374,23 +374,28 @@ struct WarpHit {
 			for (uint32_t t0 = 0; t0 < cnt; t0 += 4) {
 				KeyT v[4][4];
 				uint32_t rev[4];
+				const uint32_t in_group = cnt - t0 < 4 ? cnt - t0 : 4;  // warp-uniform: the tail group is not padded
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
-					const uint32_t e = s_mem[t0 + u < cnt ? t0 + u : cnt - 1];  // tail: repeat the last member
-					rev[u] = e >> 31;
-					const uint32_t base = e & ~kReverseBit;
+					if ((uint32_t)u < in_group) {
+						const uint32_t e = s_mem[t0 + u];
+						rev[u] = e >> 31;
+						const uint32_t base = e & ~kReverseBit;
 #pragma unroll
-					for (int j = 0; j < 4; ++j)
-						if (32 * j < n_win) v[u][j] = key_pos[base + (uint32_t)(rev[u] ? -kk[j] : kk[j])];  // warp-uniform guard
+						for (int j = 0; j < 4; ++j)
+							if (32 * j < n_win) v[u][j] = key_pos[base + (uint32_t)(rev[u] ? -kk[j] : kk[j])];  // warp-uniform guard
+					}
 				}
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
+					if ((uint32_t)u < in_group) {
 #pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						if (32 * j < n_win) {
-							const KeyT tg = v[u][j] ^ (KeyT)rev[u];  // reverse members flip the strand bit
-							if (first == 0 && t0 == 0 && u == 0) ref[j] = tg;
-							else ok[j] = ok[j] && tg == ref[j];
+						for (int j = 0; j < 4; ++j) {
+							if (32 * j < n_win) {
+								const KeyT tg = v[u][j] ^ (KeyT)rev[u];  // reverse members flip the strand bit
+								if (first == 0 && t0 == 0 && u == 0) ref[j] = tg;
+								else ok[j] = ok[j] && tg == ref[j];
+							}
 						}
 					}
 				}
@@ -422,6 +427,10 @@ struct WarpHit {
 	__device__ static int follow(mask_t m, int from, int L, int n_win, bool* ended) {
 		const mask_t valid = n_win >= 128 ? ~(mask_t)0 : (((mask_t)1 << n_win) - 1);
 		mask_t z = ~m & valid;             // zero bits inside the probed range; beyond it nothing is known
+		if (z == 0) {  // every probed window matches (the common case inside a long match): no gap to look for
+			*ended = false;
+			return n_win > from ? n_win : from;
+		}
 		if (from) z &= ~(((mask_t)1 << from) - 1);  // ignore everything before the starting match
 		// run[i] = z[i] & z[i+1] & ... & z[i+L-1]
 		const mask_t a1 = z, a2 = a1 & (a1 >> 1), a4 = a2 & (a2 >> 2), a8 = a4 & (a4 >> 4), a16 = a8 & (a8 >> 8);

@@ -26,8 +26,7 @@ __device__ __forceinline__ uint64_t extract_fwd(uint64_t win, const SeedDesc& sd
 #pragma unroll
 	for (int r = 0; r < kMaxSeedRuns; ++r) {
 		if (r >= sd.n_runs) break;
-		uint64_t part = (win >> sd.run_rshift[r]) & ((1ull << sd.run_bits[r]) - 1ull);
-		f |= part << sd.run_lshift[r];
+		f |= (win >> sd.run_net[r]) & sd.run_mask[r];  // one shift + one and-or (LOP3) per 32-bit half
 	}
 	return f;
 }
@@ -44,6 +43,13 @@ __device__ __forceinline__ uint64_t revcomp_w(uint64_t fwd, int w) {
 // strictly smaller (SortedMerList::GetDnaSeedMer, :764-769: forward wins ties because rc carries bit 0).
 // Ordering by this key equals ordering by the reference's 64-bit mer.
 __device__ __forceinline__ uint64_t canonical_key(uint64_t fwd, int w) {
+	if (w <= 16) {  // the whole mer fits 32 bits: half the work (warp-uniform branch)
+		const uint32_t f = (uint32_t)fwd;
+		uint32_t x = __brev(~f);
+		x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+		const uint32_t rc = w == 16 ? x : (x >> (32 - 2 * w));
+		return f <= rc ? ((uint64_t)f << 1) : (((uint64_t)rc << 1) | 1ull);
+	}
 	uint64_t rc = revcomp_w(fwd, w);
 	return fwd <= rc ? (fwd << 1) : ((rc << 1) | 1ull);
 }
