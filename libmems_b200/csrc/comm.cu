@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -19,6 +20,7 @@ struct NcclApi {
 	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -51,6 +53,7 @@ NcclApi& nccl() {
 	MEMS_NCCL_SYM(Broadcast)
 	MEMS_NCCL_SYM(GetErrorString)
 #undef MEMS_NCCL_SYM
+	api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(h, "ncclCommSplit"));
 	api.lib = h;
 	return api;
 }
@@ -63,9 +66,18 @@ void check(ncclResult_t r, const char* what) {
 struct Comm {
 	std::shared_ptr<Ctx> ctx;
 	ncclComm_t comm = nullptr;
+	// second communicator + stream: the all-gather of the position-ordered keys runs beside the seed-range
+	// exchange and the local sort instead of in front of them
+	ncclComm_t side_comm = nullptr;
+	cudaStream_t side_stream = nullptr;
+	cudaEvent_t side_ready = nullptr, side_done = nullptr;
 	int rank = 0, world = 1;
 	~Comm() {
+		if (side_comm) nccl().CommDestroy(side_comm);
 		if (comm) nccl().CommDestroy(comm);
+		if (side_stream) cudaStreamDestroy(side_stream);
+		if (side_ready) cudaEventDestroy(side_ready);
+		if (side_done) cudaEventDestroy(side_done);
 	}
 };
 
@@ -90,6 +102,12 @@ Comm* comm_create(std::shared_ptr<Ctx> ctx, const char* id128, int rank, int wor
 	memcpy(&id, id128, 128);
 	try {
 		check(nccl().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
+		if (world > 1 && nccl().CommSplit && !getenv("MEMS_NO_SIDE_COMM")) {
+			check(nccl().CommSplit(c->comm, 0, rank, &c->side_comm, nullptr), "ncclCommSplit");
+			MEMS_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+			MEMS_CUDA(cudaEventCreateWithFlags(&c->side_ready, cudaEventDisableTiming));
+			MEMS_CUDA(cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming));
+		}
 	} catch (...) {
 		delete c;
 		throw;
@@ -135,7 +153,9 @@ void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts,
 	check(nccl().GroupEnd(), "ncclGroupEnd");
 }
 
-// all-gather with per-rank byte counts: rank p's bytes land at d_recv + offsets[p] on every rank
+// all-gather with per-rank byte counts: rank p's bytes land at d_recv + offsets[p] on every rank.
+// With a side communicator the transfer is queued on its own stream (after everything queued on the main stream so
+// far) and the caller continues; comm_all_gather_v_wait() makes the main stream wait for it.
 void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t* byte_counts, const uint64_t* byte_offsets) {
 	char* r = static_cast<char*>(d_recv);
 	if (c->world == 1) {
@@ -143,17 +163,33 @@ void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t
 			MEMS_CUDA(cudaMemcpyAsync(r + byte_offsets[0], d_send, byte_counts[0], cudaMemcpyDeviceToDevice, c->ctx->stream));
 		return;
 	}
+	ncclComm_t comm = c->side_comm ? c->side_comm : c->comm;
+	cudaStream_t stream = c->side_comm ? c->side_stream : c->ctx->stream;
+	if (c->side_comm) {
+		MEMS_CUDA(cudaEventRecord(c->side_ready, c->ctx->stream));
+		MEMS_CUDA(cudaStreamWaitEvent(c->side_stream, c->side_ready, 0));
+	}
 	// every rank sends its slice to every peer and receives theirs: all NVLink ports busy in both directions
 	// (a ring/tree broadcast per rank reached only ~300 GB/s here)
 	check(nccl().GroupStart(), "ncclGroupStart");
 	for (int p = 0; p < c->world; ++p) {
 		if (p == c->rank) continue;
-		if (byte_counts[c->rank]) check(nccl().Send(d_send, byte_counts[c->rank], ncclChar, p, c->comm, c->ctx->stream), "ncclSend");
-		if (byte_counts[p]) check(nccl().Recv(r + byte_offsets[p], byte_counts[p], ncclChar, p, c->comm, c->ctx->stream), "ncclRecv");
+		if (byte_counts[c->rank]) check(nccl().Send(d_send, byte_counts[c->rank], ncclChar, p, comm, stream), "ncclSend");
+		if (byte_counts[p]) check(nccl().Recv(r + byte_offsets[p], byte_counts[p], ncclChar, p, comm, stream), "ncclRecv");
 	}
 	check(nccl().GroupEnd(), "ncclGroupEnd");
 	if (byte_counts[c->rank])
-		MEMS_CUDA(cudaMemcpyAsync(r + byte_offsets[c->rank], d_send, byte_counts[c->rank], cudaMemcpyDeviceToDevice, c->ctx->stream));
+		MEMS_CUDA(cudaMemcpyAsync(r + byte_offsets[c->rank], d_send, byte_counts[c->rank], cudaMemcpyDeviceToDevice, stream));
+	if (c->side_comm) MEMS_CUDA(cudaEventRecord(c->side_done, c->side_stream));
+}
+
+// the main stream continues only after the gathered data has arrived (no-op without a side communicator)
+void comm_all_gather_v_wait(Comm* c) {
+	if (c->world > 1 && c->side_comm) MEMS_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->side_done, 0));
+}
+
+void comm_side_synchronize(Comm* c) {
+	if (c->side_stream) cudaStreamSynchronize(c->side_stream);
 }
 
 }  // namespace mems

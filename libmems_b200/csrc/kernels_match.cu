@@ -1612,7 +1612,8 @@ __global__ void sorted_len_kernel(const uint32_t* __restrict__ hid, const uint16
 	if (i < n_hits) out[i] = hit_len[hid[i]] & ~kFirstStrandBit;
 }
 
-// first index of the sorted hit keys that belongs to rank d (range partition on the top 32 hash bits)
+// first index of the hit keys (grouped by their top 8 hash bits) that belongs to rank d: rank d owns the buckets
+// [ceil(256 d / world), ceil(256 (d+1) / world))
 __global__ void hit_bounds_kernel(const uint64_t* __restrict__ hkey, uint32_t n_hits, int world, uint32_t* __restrict__ bound) {
 	const int d = threadIdx.x;
 	if (d > world) return;
@@ -1620,11 +1621,11 @@ __global__ void hit_bounds_kernel(const uint64_t* __restrict__ hkey, uint32_t n_
 		bound[d] = n_hits;
 		return;
 	}
-	const uint64_t t = ((((uint64_t)d << 32) + (uint64_t)world - 1) / (uint64_t)world) << 32;  // ceil(d * 2^32 / world) << 32
+	const uint64_t t = (uint64_t)((256 * d + world - 1) / world);  // first bucket of rank d
 	uint32_t lo = 0, hi = n_hits;
 	while (lo < hi) {
 		const uint32_t mid = (lo + hi) / 2;
-		if (hkey[mid] < t) lo = mid + 1;
+		if ((hkey[mid] >> 56) < t) lo = mid + 1;
 		else hi = mid;
 	}
 	bound[d] = lo;
@@ -1695,6 +1696,26 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	if (n_loc)
 		launch_extract(c, local->packed.p, local->d_meta.p, local->meta.data(), count, sd, pos_bits, K == 8, keys_loc.p,
 		               vals_loc.p, hist_top.p, 1, top.shift, top.bits);
+	// ---- position-ordered keys of ALL sequences on every rank (window tests read any sequence): started now on the
+	// side communicator, needed only by the extension at the end
+	DevBuf<uint8_t> key_pos_all(c, s_total * K);
+	{
+		std::vector<uint64_t> bytes(W), offs(W);
+		for (int p = 0; p < W; ++p) {
+			int f, n;
+			shard_sequence_range(n_seqs, p, W, &f, &n);
+			uint64_t cnt = 0;
+			for (int g = f; g < f + n; ++g) cnt += gmeta[g].n_seeds;
+			bytes[p] = cnt * K;
+			offs[p] = (n ? gmeta[f].seed_off : 0) * K;
+		}
+		KernelScope ks(c, "nccl_all_gather_keys", (double)s_total * K);
+		comm_all_gather_v(comm, keys_loc.p, key_pos_all.p, bytes.data(), offs.data());
+	}
+	struct SideGuard {  // whatever way this function is left, the side stream must be done with keys_loc / key_pos_all
+		Comm* c;
+		~SideGuard() { comm_side_synchronize(c); }
+	} side_guard{comm};
 	uint32_t h_hist32[256];
 	MEMS_CUDA(cudaMemcpyAsync(h_hist32, hist_top.p, sizeof h_hist32, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
@@ -1745,26 +1766,9 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	vals_part.reset();
 	vals_loc.reset();
 	mark("all-to-all records");
-	// ---- 4. position-ordered keys of ALL sequences on every rank (window tests read any sequence)
-	DevBuf<uint8_t> key_pos_all(c, s_total * K);
-	{
-		std::vector<uint64_t> bytes(W), offs(W);
-		for (int p = 0; p < W; ++p) {
-			int f, n;
-			shard_sequence_range(n_seqs, p, W, &f, &n);
-			uint64_t cnt = 0;
-			for (int g = f; g < f + n; ++g) cnt += gmeta[g].n_seeds;
-			bytes[p] = cnt * K;
-			offs[p] = (n ? gmeta[f].seed_off : 0) * K;
-		}
-		KernelScope ks(c, "nccl_all_gather_keys", (double)s_total * K);
-		comm_all_gather_v(comm, keys_loc.p, key_pos_all.p, bytes.data(), offs.data());
-	}
-	keys_loc.reset();
 	DevBuf<SeqMeta> d_gmeta(c, n_seqs);
 	MEMS_CUDA(cudaMemcpyAsync(d_gmeta.p, gmeta.data(), sizeof(SeqMeta) * n_seqs, cudaMemcpyHostToDevice, c->stream));
 
-	mark("all-gather keys");
 	// ---- 5. sort the received range; hits of this rank's seed range
 	const void* u_keys = rk_a.p;
 	const uint32_t* u_vals = rv_a.p;
@@ -1797,9 +1801,13 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	out.max_run = hits1.max_run;
 
 	mark("sort + run scan");
-	// ---- 6. describe + sort the hits by diagonal hash; ranges of the hash space go to their owner rank
+	// ---- 6. describe the hits and group them by the top 8 bits of their diagonal hash (one counting pass: the owner
+	// re-sorts what it receives anyway); contiguous ranges of those 256 buckets go to their owner rank
 	const uint32_t n1 = hits1.n;
-	SortPlan hplan = make_sort_plan(64);
+	SortPlan hplan;
+	hplan.n_passes = 1;
+	hplan.shift[0] = 56;
+	hplan.bits[0] = 8;
 	DevBuf<uint64_t> hk_a(c, n1), hk_b(c, n1);
 	DevBuf<uint32_t> hid_a(c, n1), hid_b(c, n1), slen(c, n1), moff(c, n1), bound(c, W + 1), scal(c, 2);
 	const uint64_t* hkey = hk_a.p;
@@ -1817,7 +1825,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		}
 		void* kp[2] = {hk_a.p, hk_b.p};
 		uint32_t* vp[2] = {hid_a.p, hid_b.p};
-		const int r = radix_sort_pairs(c, true, kp, vp, n1, hplan, hist.p, "hit_sort_pass");
+		const int r = radix_sort_pairs(c, true, kp, vp, n1, hplan, hist.p, "hit_partition_pass");
 		hkey = r ? hk_b.p : hk_a.p;
 		hid = r ? hid_b.p : hid_a.p;
 		KernelScope ks(c, "shard_hits");
@@ -1868,6 +1876,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers below go out of scope
 	mark("all-to-all hits");
 	// ---- 7. this rank's diagonals: segments, walks, components
+	comm_all_gather_v_wait(comm);  // the gathered keys are needed from here on
 	out.n_hits = n2;
 	if (n2 == 0) return;
 	HitSet hits2;
