@@ -243,3 +243,73 @@ def test_grid_wide_walks(orc, monkeypatch):
     flat, _ = c.find_matches(c.create_smls(gs, seed), order=mems.ORDER_CANONICAL)
     assert mems.flat_to_matches(flat) == canonical(want)
     c.close()
+
+
+def test_many_sequences(ctx, orc):
+    """40 related sequences in one call (BASELINE config 4 has 50): 6 tag bits for the sequence id."""
+    seed = mems.get_seed(13)
+    gs = synth.genome_family(40, 5000, seed=91, n_indels=2, max_indel=15)
+    want, winfo = orc.find_matches(0, gs, seed)
+    got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
+    assert got == canonical(want)
+    assert info["n_hits"] == winfo["hits"]
+    with pytest.raises(mems.MemsError) as e:
+        ctx.find_matches(ctx.create_smls(synth.genome_family(65, 300, seed=92, n_indels=0), seed))
+    assert e.value.code == 4  # more than MEMS_MAX_SEQS
+
+
+def test_repeathash_megabase_vs_oracle(ctx, orc):
+    """RepeatHash on a 2 Mbp sequence with planted repeat families (BASELINE config 3 at a size the oracle
+    finishes in seconds), default seed weight for that length."""
+    g = synth.repeat_genome(2_000_000, seed=93, families=40, copies=20)
+    seed = mems.get_seed(mems.get_default_seed_weight(len(g)))
+    want, winfo = orc.find_matches(1, [g], seed)
+    got, info = gpu_matches(ctx, [g], seed, mems.MODE_REPEAT)
+    assert got == want
+    assert info["collisions"] == winfo["collisions"] and info["max_run"] <= 1000
+
+
+def _window_matches(smls, lens, L, seed_mask, match, k):
+    """The reference's window test (MatchFinder.h:264-308) for window k of `match`, evaluated with the mers the
+    library itself reports at those positions."""
+    _, length, *starts = match
+    ref = None
+    for g, st in enumerate(starts):
+        if st == 0:
+            continue
+        p = st - 1 + k if st > 0 else -st - 1 + (length - L - k)
+        if p < 0 or p > lens[g] - L:
+            return False
+        mer = int(smls[g].seed_mers([p])[1][0])
+        strand = mer & 1
+        tagged = (mer & seed_mask, (strand == 0) if st > 0 else (strand == 1))
+        if ref is None:
+            ref = tagged
+        elif tagged != ref:
+            return False
+    return True
+
+
+def test_full_size_match_properties(ctx):
+    """BASELINE config 2 at full size (8 x 5 Mbp, w15), where the oracle would need minutes: every reported match
+    must start and end on a matching seed window and be maximal (no matching window within L beyond either end),
+    matches must be distinct, and the run must be reproducible."""
+    seed = mems.get_seed(15)
+    gs = synth.genome_family(8, 5_000_000, seed=2)
+    smls = ctx.create_smls(gs, seed)
+    flat, info = ctx.find_matches(smls)
+    matches = mems.flat_to_matches(flat)
+    assert len(matches) == info["n_matches"] == len(set(matches))
+    flat2, _ = ctx.find_matches(smls)
+    assert np.array_equal(flat, flat2)
+    L, mask, lens = smls[0].info["seed_length"], smls[0].info["seed_mask"], [len(g) for g in gs]
+    rng = np.random.default_rng(3)
+    picks = list(rng.choice(len(matches), size=40, replace=False)) + [int(np.argmax([m[1] for m in matches]))]
+    for i in picks:
+        m = matches[i]
+        assert sum(1 for s in m[2:] if s) >= 2 and m[1] >= L
+        assert _window_matches(smls, lens, L, mask, m, 0)
+        assert _window_matches(smls, lens, L, mask, m, m[1] - L)
+        for d in range(1, L + 1):
+            assert not _window_matches(smls, lens, L, mask, m, -d)
+            assert not _window_matches(smls, lens, L, mask, m, m[1] - L + d)
