@@ -1,4 +1,4 @@
-// kernels_match.cu — match finding on the sorted union of a batch (MemHash / RepeatHash).
+// kernels_match.cu — match finding on the sorted union of a batch (MemHash / RepeatHash / PairwiseMatchFinder).
 //
 // Reference flow (CPU, sequential): MatchFinder::SearchRange k-way merges the SMLs and hands every
 // equal-seed run to EnumerateMatches (MatchFinder.cpp:172-340); MemHash keeps runs that hold the seed at
@@ -15,11 +15,17 @@
 //                     offsets) -> sort key (diagonal hash | first-member position)
 //   3. sort         — hits by that key (radix_sort.cu): hits of one diagonal become contiguous, by position
 //   4. segments     — neighbours on the same diagonal <= L apart are connected without looking at sequence
-//   5. extend       — one warp per segment walks RIGHT from its last hit with the window test (lane d tests
-//                     the window d positions away; ballot picks the farthest) until it reaches the next
-//                     segment of its diagonal (link) or fails (component end); chains of linked segments
-//                     are the components, and only each chain's first segment walks LEFT
-//   6. emit         — components -> [SeqCount, Length, starts] records
+//   5. extend       — one warp per segment walks RIGHT from its last hit with the window test: a probe tests
+//                     128 windows at once (4 per lane, one load of the position-ordered key array per member
+//                     and window), the chain of matches <= L apart is followed bit-parallel in the ballot
+//                     mask; the walk ends when it reaches the next segment of its diagonal (link) or a gap
+//                     > L (component end).  Chains of linked segments are the components; only each chain's
+//                     first segment walks LEFT.  Walks that outlast a warp's budget go to 16-warp CTAs (2048
+//                     windows per round), the few that outlast those to the whole grid (cooperative launch)
+//   6. emit         — components -> [SeqCount, Length, starts] records; policies: MemHash (+ MaskedMemHash
+//                     filter), RepeatHash, PairwiseMatchFinder; ORDER_REFERENCE replays the reference's hash
+//                     table on the host (optionally into a persistent table shared by several calls)
+//   sharded         — find_matches_sharded at the bottom: the same stages across ranks with two NCCL exchanges
 // Hash collisions between diagonals only split segments (more window tests), never merge them: every
 // merge decision compares the full member lists.
 #include <algorithm>
@@ -27,7 +33,6 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
-#include <unordered_map>
 
 #include <cooperative_groups.h>
 
@@ -359,14 +364,13 @@ struct WarpHit {
 	// l+1, l+33, l+65, l+97.  Members are taken four at a time and all 16 loads of a group are issued before
 	// any is compared, so a group costs one memory round trip.  Returns the match bits, identical in every lane.
 	__device__ mask_t probe(int32_t k0, int dir, int n_win) {
-		int32_t kk[4];
 		bool ok[4];
 		KeyT ref[4];
+		const int32_t k_first = k0 + dir * (lane + 1);  // this lane's nearest window; the others are 32, 64, 96 further
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
-			kk[j] = k0 + dir * (lane + 32 * j + 1);
-			ok[j] = lane + 32 * j < n_win && kk[j] >= kmin && kk[j] <= kmax;
-			if (!ok[j]) kk[j] = 0;  // window 0 is the hit itself, always valid: keeps the loads in range
+			const int32_t k = k_first + dir * 32 * j;
+			ok[j] = lane + 32 * j < n_win && k >= kmin && k <= kmax;  // invalid windows are never loaded
 		}
 		for (uint32_t first = 0; first < len; first += kMemberTile) {
 			if (first) load_tile(first);
@@ -380,10 +384,14 @@ struct WarpHit {
 					if ((uint32_t)u < in_group) {
 						const uint32_t e = s_mem[t0 + u];
 						rev[u] = e >> 31;
-						const uint32_t base = e & ~kReverseBit;
+						// reverse members run backwards: index = base -/+ k, one multiply-add per member and an
+						// immediate stride per further window (IMAD runs beside the ALU pipe the compares use)
+						const int32_t sign = 1 - 2 * (int32_t)rev[u];
+						const uint32_t p0 = (e & ~kReverseBit) + (uint32_t)(sign * k_first);
+						const int32_t stride = sign * dir * 32;
 #pragma unroll
 						for (int j = 0; j < 4; ++j)
-							if (32 * j < n_win) v[u][j] = key_pos[base + (uint32_t)(rev[u] ? -kk[j] : kk[j])];  // warp-uniform guard
+							if (32 * j < n_win && ok[j]) v[u][j] = key_pos[p0 + (uint32_t)(stride * j)];
 					}
 				}
 #pragma unroll
