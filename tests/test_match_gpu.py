@@ -313,3 +313,32 @@ def test_full_size_match_properties(ctx):
         for d in range(1, L + 1):
             assert not _window_matches(smls, lens, L, mask, m, -d)
             assert not _window_matches(smls, lens, L, mask, m, m[1] - L + d)
+
+
+def test_contexts_are_independent_across_threads(orc):
+    """One context per host thread, used concurrently (the reference keeps one MemHash per OpenMP thread,
+    Aligner.h:198 / ProgressiveAligner.cpp:695): results must equal the oracle's for every thread."""
+    import threading
+    seed = mems.get_seed(13)
+    jobs = [synth.genome_family(3, 20000 + 3000 * t, seed=200 + t, n_indels=4, max_indel=20) for t in range(4)]
+    want = [canonical(orc.find_matches(0, gs, seed)[0]) for gs in jobs]
+    got, errors = [None] * len(jobs), []
+
+    def work(t):
+        try:
+            c = gpu_context()
+            for _ in range(5):
+                flat, _ = c.find_matches(c.create_smls(jobs[t], seed), order=mems.ORDER_CANONICAL)
+                got[t] = mems.flat_to_matches(flat)
+                assert got[t] == want[t]
+            c.close()
+        except Exception as e:  # surfaced below: a failing assert in a thread would otherwise be lost
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert got == want
