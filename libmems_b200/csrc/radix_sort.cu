@@ -24,6 +24,7 @@ namespace mems {
 
 constexpr int kRadix = 256;
 constexpr int kTile = 4096;  // pairs per CTA
+constexpr int kMinB32 = 5, kMinB64 = 4;  // resident CTAs per SM the kernels are compiled for
 
 constexpr uint32_t kFlagPartial = 0x40000000u;
 constexpr uint32_t kFlagInclusive = 0x80000000u;
@@ -55,108 +56,133 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 	asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// THREADS x ITEMS = kTile.  The kernel is bound by the latency of its shared-memory ranking chain, not by
-// HBM (ncu, profiles/r01_*): what buys throughput is resident warps, so the register footprint is kept
-// small — ranks are 16-bit, values are not loaded until the reorder step — and MINB CTAs share an SM.
-// lanes of the warp holding the same 8-bit digit.  MATCH.ANY is a single instruction but occupies its pipe for
-// tens of cycles; eight VOTEs plus a little logic (the digit is <= 8 bits) issue at full rate.
-template <bool BALLOT>
+// Lanes of the warp that hold the same digit as this lane, from NBITS ballots (MATCH.ANY is one instruction but
+// occupies its pipe for tens of cycles; a ballot costs test + VOTE + select + AND at full issue rate).
+// written in PTX: the C++ form makes the compiler derive the vote predicate and the select mask separately
+// (7 instructions per bit instead of 4)
+template <int B>
+__device__ __forceinline__ void peers_bit(uint32_t& peers, uint32_t d) {
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred p;\n\t"
+	    ".reg .b32 t, m;\n\t"
+	    "and.b32 t, %1, %2;\n\t"
+	    "setp.ne.u32 p, t, 0;\n\t"
+	    "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+	    "@!p not.b32 m, m;\n\t"
+	    "and.b32 %0, %0, m;\n\t"
+	    "}"
+	    : "+r"(peers)
+	    : "r"(d), "n"(1 << B));
+}
+template <int NBITS>
 __device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
-	if (!BALLOT) return __match_any_sync(0xffffffffu, d);
 	uint32_t peers = 0xffffffffu;
-#pragma unroll
-	for (int b = 0; b < 8; ++b) {
-		const bool bit = (d >> b) & 1u;
-		const uint32_t m = __ballot_sync(0xffffffffu, bit);
-		peers &= bit ? m : ~m;
-	}
+	peers_bit<0>(peers, d);
+	peers_bit<1>(peers, d);
+	peers_bit<2>(peers, d);
+	peers_bit<3>(peers, d);
+	peers_bit<4>(peers, d);
+	peers_bit<5>(peers, d);
+	peers_bit<6>(peers, d);
+	if (NBITS > 7) peers_bit<7>(peers, d);
 	return peers;
 }
 
-template <class KeyT, int THREADS, int MINB, bool BALLOT = false>
-__global__ void __launch_bounds__(THREADS, MINB)
-onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t digit_mask,
-                const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+__device__ __forceinline__ void cp_async_u32(void* smem_dst, const uint32_t* gmem_src) {
+	const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One tile of one pass.  THREADS x ITEMS = kTile, THREADS == kRadix (thread d also owns digit d).  The pass is
+// bound by instruction issue, not by HBM (ncu, profiles/r01_*), so the body is written for instruction count:
+// FULL tiles carry no bounds predicates; every lane reads its digit's running counter itself (one LDS) instead
+// of a leader read + shuffle; the scan over digits folds the tile-local digit offset into the per-warp counters
+// so the reorder step is one LDS + add per item; values never pass through registers (cp.async straight into
+// their reordered shared-memory slot); the tile's partial counts are published before the reorder and the
+// look-back runs after it, so predecessors have usually finished by the time they are polled.
+template <class KeyT, int THREADS, bool FULL, int NBITS>
+__device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                              KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_valid,
+                                              uint32_t tile, int shift, uint32_t digit_mask,
+                                              const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, KeyT* s_keys,
+                                              uint32_t* s_vals, uint16_t (*s_warp_cnt)[kRadix], uint32_t* s_global_base,
+                                              uint32_t* s_warp_tot) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int ITEMS = kTile / THREADS;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
-	uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * kTile);
-	__shared__ uint16_t s_warp_cnt[WARPS][kRadix];  // per-warp digit counts (<= 32*ITEMS), then exclusive over warps
-	__shared__ uint32_t s_digit_excl[kRadix];
-	__shared__ uint32_t s_global_base[kRadix];
-	__shared__ uint32_t s_warp_tot[8];
-	__shared__ uint32_t s_tile;
-
+	static_assert(THREADS == kRadix, "thread d owns digit d");
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-	for (int i = lane; i < kRadix; i += 32) s_warp_cnt[warp][i] = 0;
-	__syncthreads();
-	const uint32_t tile = s_tile;
 	const uint32_t tile_base = tile * (uint32_t)kTile;
-	const uint32_t n_valid = n - tile_base < (uint32_t)kTile ? n - tile_base : (uint32_t)kTile;
+	const uint32_t warp_base = warp * (32 * ITEMS);
+	const KeyT* kin = keys_in + tile_base + warp_base + lane;
+	const uint32_t* vin = vals_in + tile_base + warp_base + lane;
 
 	KeyT key[ITEMS];
 	uint16_t rank[ITEMS];
-	const uint32_t warp_base = warp * (32 * ITEMS);
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
-		const uint32_t local = warp_base + i * 32 + lane;
-		key[i] = local < n_valid ? keys_in[tile_base + local] : ~(KeyT)0;
+		if (FULL) key[i] = kin[i * 32];
+		else key[i] = warp_base + i * 32 + lane < n_valid ? kin[i * 32] : ~(KeyT)0;
 	}
 	// ---- rank inside the warp, in memory order
 	const uint32_t lanemask_lt = (1u << lane) - 1u;
+	uint16_t* my_cnt = s_warp_cnt[warp];
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
-		const uint32_t local = warp_base + i * 32 + lane;
-		const uint32_t d = local < n_valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
-		const uint32_t peers = digit_peers<BALLOT>(d);
-		const int leader = __ffs(peers) - 1;
-		uint32_t base = 0;
-		if (lane == leader) {
-			base = s_warp_cnt[warp][d];
-			s_warp_cnt[warp][d] = (uint16_t)(base + __popc(peers));
-		}
-		base = __shfl_sync(0xffffffffu, base, leader);
-		rank[i] = (uint16_t)(base + __popc(peers & lanemask_lt));
+		uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
+		if (!FULL && !(warp_base + i * 32 + lane < n_valid)) d = kRadix - 1;  // padding ranks after every real item
+		const uint32_t peers = digit_peers<FULL ? NBITS : 8>(d);
+		const uint32_t base = my_cnt[d];
+		__syncwarp();
+		const uint32_t below = peers & lanemask_lt;
+		if (below == 0u) my_cnt[d] = (uint16_t)(base + __popc(peers));
+		rank[i] = (uint16_t)(base + __popc(below));
 		__syncwarp();
 	}
 	__syncthreads();
-	// ---- thread d owns digit d: exclusive scan over warps, tile count, look-back
+	// ---- thread d owns digit d: counts per warp -> exclusive over warps; tile count; scan over digits
 	uint32_t count = 0;
-	if (tid < kRadix) {
-		uint32_t sum = 0;
+#pragma unroll
+	for (int w = 0; w < WARPS; ++w) count += s_warp_cnt[w][tid];
+	if (!FULL && tid == kRadix - 1) count -= (uint32_t)kTile - n_valid;
+	uint32_t* my_status = status + (size_t)tile * kRadix + tid;
+	st_volatile_u32(my_status, count | (tile == 0 ? kFlagInclusive : kFlagPartial));
+	uint32_t incl = count;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) s_warp_tot[warp] = incl;
+	__syncthreads();
+	uint32_t digit_excl = incl - count;  // first tile-local sorted index of digit tid
+#pragma unroll
+	for (int w = 0; w < WARPS; ++w)
+		if (w < warp) digit_excl += s_warp_tot[w];
+	{
+		uint32_t run = digit_excl;
 #pragma unroll
 		for (int w = 0; w < WARPS; ++w) {
 			const uint32_t c = s_warp_cnt[w][tid];
-			s_warp_cnt[w][tid] = (uint16_t)sum;
-			sum += c;
+			s_warp_cnt[w][tid] = (uint16_t)run;  // tile-local sorted index of warp w's first item with digit tid
+			run += c;
 		}
-		// padding items of the last tile were ranked as digit 255, after every real item
-		count = sum - (tid == kRadix - 1 ? (uint32_t)kTile - n_valid : 0u);
-		uint32_t incl = count;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += t;
-		}
-		if (lane == 31) s_warp_tot[warp] = incl;
-		s_digit_excl[tid] = incl - count;  // exclusive inside this warp's 32 digits; warp offsets added below
 	}
 	__syncthreads();
-	if (tid < kRadix) {
-		uint32_t woff = 0;
+	// ---- reorder through shared memory; values go straight from global to their slot
 #pragma unroll
-		for (int w = 0; w < kRadix / 32; ++w)
-			if (w < warp) woff += s_warp_tot[w];
-		const uint32_t digit_excl = s_digit_excl[tid] + woff;
+	for (int i = 0; i < ITEMS; ++i) {
+		const bool valid = FULL || warp_base + i * 32 + lane < n_valid;
+		const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
+		const uint32_t pos = (uint32_t)my_cnt[d] + rank[i];
+		s_keys[pos] = key[i];
+		if (valid) cp_async_u32(s_vals + pos, vin + i * 32);
+	}
+	// ---- decoupled look-back for digit tid
+	{
 		uint32_t excl = 0;
-		uint32_t* my_status = status + (size_t)tile * kRadix + tid;
-		if (tile == 0) {
-			st_volatile_u32(my_status, count | kFlagInclusive);
-		} else {
-			st_volatile_u32(my_status, count | kFlagPartial);
+		if (tile != 0) {
 			const uint32_t* look = my_status - kRadix;
 			while (true) {
 				uint32_t s;
@@ -169,25 +195,14 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 			}
 			st_volatile_u32(my_status, (excl + count) | kFlagInclusive);
 		}
-		s_digit_excl[tid] = digit_excl;
 		s_global_base[tid] = bin_base[tid] + excl - digit_excl;  // + tile-local sorted index = global index
 	}
-	__syncthreads();
-	// ---- reorder through shared memory (values are loaded only now: one register live per value)
-#pragma unroll
-	for (int i = 0; i < ITEMS; ++i) {
-		const uint32_t local = warp_base + i * 32 + lane;
-		const bool valid = local < n_valid;
-		const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : (uint32_t)(kRadix - 1);
-		const uint32_t pos = s_digit_excl[d] + s_warp_cnt[warp][d] + rank[i];
-		s_keys[pos] = key[i];
-		s_vals[pos] = valid ? vals_in[tile_base + local] : 0u;
-	}
+	cp_async_wait_all();
 	__syncthreads();
 #pragma unroll
 	for (int k = 0; k < ITEMS; ++k) {
 		const uint32_t idx = k * THREADS + tid;
-		if (idx < n_valid) {
+		if (FULL || idx < n_valid) {
 			const KeyT kk = s_keys[idx];
 			const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
 			const uint32_t g = s_global_base[d] + idx;
@@ -195,6 +210,38 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 			vals_out[g] = s_vals[idx];
 		}
 	}
+}
+
+template <class KeyT, int THREADS, int MINB, int NBITS>
+__global__ void __launch_bounds__(THREADS, MINB)
+onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t digit_mask,
+                const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+	constexpr int WARPS = THREADS / 32;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
+	uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * kTile);
+	__shared__ uint16_t s_warp_cnt[WARPS][kRadix];  // per-warp digit counts, then tile-local offsets
+	__shared__ uint32_t s_global_base[kRadix];
+	__shared__ uint32_t s_warp_tot[WARPS];
+	__shared__ uint32_t s_tile;
+
+	const int tid = threadIdx.x;
+	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+	{
+		uint32_t* z = reinterpret_cast<uint32_t*>(&s_warp_cnt[0][0]);
+		for (int i = tid; i < WARPS * kRadix / 2; i += THREADS) z[i] = 0;
+	}
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t tile_base = tile * (uint32_t)kTile;
+	const uint32_t n_valid = n - tile_base < (uint32_t)kTile ? n - tile_base : (uint32_t)kTile;
+	if (n_valid == (uint32_t)kTile)
+		onesweep_tile<KeyT, THREADS, true, NBITS>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask, bin_base,
+		                                          status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot);
+	else
+		onesweep_tile<KeyT, THREADS, false, NBITS>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask,
+		                                           bin_base, status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot);
 }
 
 // exclusive scan of each pass's 256 digit counts -> first output index of each digit
@@ -239,12 +286,7 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 	const size_t key_bytes = key64 ? 8 : 4;
 	const size_t smem = (key_bytes + 4) * kTile;
 	// launch configuration (measured on B200, tools/sort_bench.py): 256 threads x 16 pairs, 5 CTAs per SM for
-	// 32-bit keys and 4 for 64-bit keys; MEMS_SORT_VARIANT selects the alternatives for experiments
-	static int variant = -1;
-	if (variant < 0) {
-		const char* e = getenv("MEMS_SORT_VARIANT");
-		variant = e ? atoi(e) : 0;
-	}
+	// 32-bit keys and 4 for 64-bit keys
 	auto launch = [&](auto kern, int threads, int q, int cur) {
 		MEMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		uint32_t* st = status.p + status_words * q;
@@ -259,14 +301,13 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 	int cur = 0;
 	for (int q = 0; q < P; ++q) {
 		KernelScope ks(c, prof_name, 2.0 * (double)n * (double)(key_bytes + 4));
+		const bool eight = plan.bits[q] > 7;
 		if (key64) {
-			if (variant == 1) launch(onesweep_kernel<uint64_t, 512, 3, true>, 512, q, cur);
-			else if (variant == 2) launch(onesweep_kernel<uint64_t, 256, 3, true>, 256, q, cur);
-			else launch(onesweep_kernel<uint64_t, 256, 4, true>, 256, q, cur);
+			if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8>, 256, q, cur);
+			else launch(onesweep_kernel<uint64_t, 256, kMinB64, 7>, 256, q, cur);
 		} else {
-			if (variant == 1) launch(onesweep_kernel<uint32_t, 512, 3, true>, 512, q, cur);
-			else if (variant == 2) launch(onesweep_kernel<uint32_t, 256, 4, true>, 256, q, cur);
-			else launch(onesweep_kernel<uint32_t, 256, 5, true>, 256, q, cur);
+			if (eight) launch(onesweep_kernel<uint32_t, 256, kMinB32, 8>, 256, q, cur);
+			else launch(onesweep_kernel<uint32_t, 256, kMinB32, 7>, 256, q, cur);
 		}
 		cur ^= 1;
 	}
