@@ -70,15 +70,18 @@ void launch_pack(Ctx* c, const uint8_t* d_ascii, uint32_t* d_packed, const SeqMe
 }
 
 // ------------------------------------------------------------------------------------------------
-// extract: one CTA per tile of kExtractTile consecutive seed positions of one sequence.
-// The tile's packed words are staged in shared memory with coalesced loads; every thread then builds
-// its windows from shared memory, so global traffic is 0.25 B/base read + one key/value write per seed.
-// The digit histograms of ALL radix passes are accumulated here (shared-memory atomics, one flush per
-// CTA), which removes the separate 8 B/seed histogram pre-pass of a classic onesweep sort.
+// extract: one thread per 8 consecutive seed positions of one sequence, chosen so that the thread's 8 slots of
+// the union arrays start on a 16-byte boundary: keys and values leave as 128-bit stores.  The thread reads the
+// four packed words under its positions once (coalesced, L1 serves the overlap between neighbours), shifts them
+// into place once, and derives each window with two funnel shifts by a constant.  Loops run over the pattern's
+// runs / the radix passes on the outside and over the 8 items on the inside, so each run descriptor is fetched
+// once per thread.  For weights <= 16 the mer fits 32 bits and every step works on single registers.
+// The digit histograms of ALL radix passes are accumulated here (shared-memory atomics, one flush per CTA),
+// which removes the separate histogram pre-pass of a classic onesweep sort.
+// Global traffic: 0.25 B/base read + one key and one value written per seed.
 constexpr int kExtractThreads = 256;
 constexpr int kExtractItems = 8;
 constexpr int kExtractTile = kExtractThreads * kExtractItems;
-constexpr int kExtractWords = kExtractTile / 16 + 4;  // tile + up to 31 bases of overhang + funnel word
 constexpr int kMaxPasses = 8;
 
 struct PassDesc {
@@ -88,45 +91,123 @@ struct PassDesc {
 };
 
 template <class KeyT>
+__device__ __forceinline__ void store8(KeyT* dst, const KeyT (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<uint32_t>(uint32_t* dst, const uint32_t (&v)[8]) {
+	reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+	reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<uint64_t>(uint64_t* dst, const uint64_t (&v)[8]) {
+#pragma unroll
+	for (int j = 0; j < 4; ++j) reinterpret_cast<ulonglong2*>(dst)[j] = make_ulonglong2(v[2 * j], v[2 * j + 1]);
+}
+
+template <class KeyT, bool W32>
 __global__ void __launch_bounds__(kExtractThreads)
 extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ meta, SeedDesc sd, int pos_bits,
-               KeyT* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist, PassDesc pd) {
-	__shared__ uint32_t s_words[kExtractWords];
+               KeyT* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist, PassDesc pd,
+               uint32_t tiles_per_cta) {
 	__shared__ uint32_t s_hist[kMaxPasses * 256];
 	const SeqMeta m = meta[blockIdx.y];
-	const uint32_t tile0 = blockIdx.x * (uint32_t)kExtractTile;
-	if (tile0 >= m.n_seeds) return;
+	const uint32_t lead = (uint32_t)(m.seed_off & 3u);  // slots before the sequence's first seed in its 4-slot group
+	const uint64_t span = (uint64_t)m.n_seeds + lead;
+	if ((uint64_t)blockIdx.x * tiles_per_cta * kExtractTile >= span) return;
 	for (int i = threadIdx.x; i < pd.n_passes * 256; i += kExtractThreads) s_hist[i] = 0;
-	// words [tile0/16, ...): the sequence buffer carries two zero pad words, and reads are clamped to it
-	const uint64_t n_words = ((uint64_t)m.n_bases + 15) / 16 + 2;
-	const uint32_t w0 = tile0 >> 4;
-	const uint32_t* src = packed + m.word_off;
-	for (int i = threadIdx.x; i < kExtractWords; i += kExtractThreads) {
-		uint64_t wi = (uint64_t)w0 + i;
-		s_words[i] = wi < n_words ? src[wi] : 0u;
-	}
 	__syncthreads();
 	const uint32_t seq_tag = m.tag << pos_bits;
+	const uint32_t* src = packed + m.word_off;
+	// a CTA walks tiles_per_cta consecutive tiles and flushes its histograms once: one flush per tile would be
+	// ~1000 same-address global atomics per 2048 seeds, which bounds the kernel at the L2 atomic units
+	for (uint32_t t = 0; t < tiles_per_cta; ++t) {
+	const uint64_t tile0 = ((uint64_t)blockIdx.x * tiles_per_cta + t) * kExtractTile;
+	if (tile0 >= span) break;
+	// first position of this thread; negative (as int64) only for the first thread of a sequence with lead > 0
+	const int64_t p0 = (int64_t)tile0 + (int64_t)threadIdx.x * kExtractItems - (int64_t)lead;
+	KeyT key[kExtractItems];
+	bool all = p0 >= 0 && p0 + kExtractItems <= (int64_t)m.n_seeds;
+	if (all) {
+		// words wi .. wi+3 hold bits [0, 128) of the thread's span; the last valid window ends before bit
+		// 2*15 + 2*7 + 62.  The buffer carries two zero pad words; reads past it are clamped.
+		const uint64_t n_words = ((uint64_t)m.n_bases + 15) / 16 + 2;
+		const uint32_t wi = (uint32_t)p0 >> 4, sh = ((uint32_t)p0 & 15u) * 2u;
+		const uint32_t w0 = src[wi], w1 = src[wi + 1], w2 = src[wi + 2];
+		const uint32_t w3 = (uint64_t)wi + 3 < n_words ? src[wi + 3] : 0u;
+		const uint32_t v0 = __funnelshift_l(w1, w0, sh), v1 = __funnelshift_l(w2, w1, sh), v2 = __funnelshift_l(w3, w2, sh);
+		uint32_t hi[kExtractItems], lo[kExtractItems];
 #pragma unroll
-	for (int k = 0; k < kExtractItems; ++k) {
-		uint32_t local = k * kExtractThreads + threadIdx.x;  // striped: a warp writes 32 consecutive keys
-		uint32_t p = tile0 + local;
-		if (p < m.n_seeds) {
-			uint64_t win = window64(s_words, local);  // tile0 is a multiple of 16, so local indexes s_words directly
-			uint64_t ck = canonical_key(extract_fwd(win, sd), sd.w);
+		for (int k = 0; k < kExtractItems; ++k) {
+			hi[k] = __funnelshift_l(v1, v0, 2 * k);
+			lo[k] = __funnelshift_l(v2, v1, 2 * k);
+		}
+		if (W32) {
+			uint32_t f[kExtractItems];
+#pragma unroll
+			for (int k = 0; k < kExtractItems; ++k) f[k] = 0;
+			// fully unrolled with a uniform early exit: run descriptors are then read from the kernel-parameter
+			// constant bank at fixed offsets (a runtime-indexed parameter array would be copied to local memory)
+#pragma unroll
+			for (int r = 0; r < kMaxSeedRuns; ++r) {
+				if (r >= sd.n_runs) break;
+				const uint32_t net = sd.run_net[r], mask = (uint32_t)sd.run_mask[r];
+				if (net >= 32u) {
+#pragma unroll
+					for (int k = 0; k < kExtractItems; ++k) f[k] |= (hi[k] >> (net - 32u)) & mask;
+				} else {
+#pragma unroll
+					for (int k = 0; k < kExtractItems; ++k) f[k] |= __funnelshift_r(lo[k], hi[k], net) & mask;
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < kExtractItems; ++k) key[k] = (KeyT)canonical_key((uint64_t)f[k], sd.w);
+		} else {
+			uint64_t f[kExtractItems];
+#pragma unroll
+			for (int k = 0; k < kExtractItems; ++k) f[k] = 0;
+#pragma unroll
+			for (int r = 0; r < kMaxSeedRuns; ++r) {
+				if (r >= sd.n_runs) break;
+				const uint32_t net = sd.run_net[r];
+				const uint64_t mask = sd.run_mask[r];
+#pragma unroll
+				for (int k = 0; k < kExtractItems; ++k) f[k] |= ((((uint64_t)hi[k] << 32) | lo[k]) >> net) & mask;
+			}
+#pragma unroll
+			for (int k = 0; k < kExtractItems; ++k) key[k] = (KeyT)canonical_key(f[k], sd.w);
+		}
+		const uint64_t slot = m.seed_off + (uint64_t)p0;  // a multiple of 4
+		store8<KeyT>(keys + slot, key);
+		uint32_t val[kExtractItems];
+#pragma unroll
+		for (int k = 0; k < kExtractItems; ++k) val[k] = seq_tag | ((uint32_t)p0 + k);
+		store8<uint32_t>(vals + slot, val);
+#pragma unroll
+		for (int q = 0; q < kMaxPasses; ++q) {
+			if (q >= pd.n_passes) break;
+			const int shift = pd.shift[q];
+			const uint32_t mask = (1u << pd.bits[q]) - 1u;
+#pragma unroll
+			for (int k = 0; k < kExtractItems; ++k) atomicAdd(&s_hist[q * 256 + ((uint32_t)(key[k] >> shift) & mask)], 1u);
+		}
+	} else {
+		// the (at most two) threads per sequence whose span crosses the sequence's first or last seed
+		for (int k = 0; k < kExtractItems; ++k) {
+			const int64_t p = p0 + k;
+			if (p < 0 || p >= (int64_t)m.n_seeds) continue;
+			const uint64_t ck = canonical_key(extract_fwd(window64(src, (uint32_t)p), sd), sd.w);
 			keys[m.seed_off + p] = (KeyT)ck;
-			vals[m.seed_off + p] = seq_tag | p;
+			vals[m.seed_off + p] = seq_tag | (uint32_t)p;
 #pragma unroll
 			for (int q = 0; q < kMaxPasses; ++q) {
 				if (q >= pd.n_passes) break;
-				uint32_t d = (uint32_t)(ck >> pd.shift[q]) & ((1u << pd.bits[q]) - 1u);
-				atomicAdd(&s_hist[q * 256 + d], 1u);
+				atomicAdd(&s_hist[q * 256 + ((uint32_t)(ck >> pd.shift[q]) & ((1u << pd.bits[q]) - 1u))], 1u);
 			}
 		}
 	}
+	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < pd.n_passes * 256; i += kExtractThreads) {
-		uint32_t v = s_hist[i];
+		const uint32_t v = s_hist[i];
 		if (v) atomicAdd(&hist[i], v);
 	}
 }
@@ -148,15 +229,23 @@ void launch_extract(Ctx* c, const uint32_t* d_packed, const SeqMeta* d_meta, con
 		pd.shift[q] = pass_shift[q];
 		pd.bits[q] = pass_bits[q];
 	}
-	dim3 grid((max_seeds + kExtractTile - 1) / kExtractTile, (unsigned)n_seqs);
+	const uint64_t tiles_max = ((uint64_t)max_seeds + 3 + kExtractTile - 1) / kExtractTile;
+	const uint64_t tiles_all = (total + 3 * (uint64_t)n_seqs + kExtractTile - 1) / kExtractTile;
+	uint64_t tpc = (tiles_all + (uint64_t)c->sm_count * 8 - 1) / ((uint64_t)c->sm_count * 8);  // ~8 CTAs per SM in total
+	if (tpc < 1) tpc = 1;
+	dim3 grid((unsigned)((tiles_max + tpc - 1) / tpc), (unsigned)n_seqs);
 	double bytes = (double)total * (0.25 + (key64 ? 8.0 : 4.0) + 4.0);
 	KernelScope ks(c, "extract", bytes);
-	if (key64)
-		extract_kernel<uint64_t><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
-		                                                                   (uint64_t*)d_keys, d_vals, d_hist, pd);
+	const bool w32 = sd.w <= 16;
+	if (!key64)
+		extract_kernel<uint32_t, true><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
+		                                                                         (uint32_t*)d_keys, d_vals, d_hist, pd, (uint32_t)tpc);
+	else if (w32)
+		extract_kernel<uint64_t, true><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
+		                                                                         (uint64_t*)d_keys, d_vals, d_hist, pd, (uint32_t)tpc);
 	else
-		extract_kernel<uint32_t><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
-		                                                                   (uint32_t*)d_keys, d_vals, d_hist, pd);
+		extract_kernel<uint64_t, false><<<grid, kExtractThreads, 0, c->stream>>>(d_packed, d_meta, sd, pos_bits,
+		                                                                          (uint64_t*)d_keys, d_vals, d_hist, pd, (uint32_t)tpc);
 	MEMS_CUDA(cudaGetLastError());
 }
 

@@ -47,13 +47,14 @@ SortPlan make_sort_plan(int key_bits, int begin_bit) {
 	return p;
 }
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+// tile status words carry flag and value together, so relaxed device-scope accesses are enough
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
 	uint32_t v;
-	asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-	asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Lanes of the warp that hold the same digit as this lane, from NBITS ballots (MATCH.ANY is one instruction but
@@ -102,7 +103,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // so the reorder step is one LDS + add per item; values never pass through registers (cp.async straight into
 // their reordered shared-memory slot); the tile's partial counts are published before the reorder and the
 // look-back runs after it, so predecessors have usually finished by the time they are polled.
-template <class KeyT, int THREADS, bool FULL, int NBITS>
+template <class KeyT, int THREADS, bool FULL, int NBITS, int kLookBack>
 __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_valid,
                                               uint32_t tile, int shift, uint32_t digit_mask,
@@ -111,7 +112,8 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
                                               uint32_t* s_warp_tot) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int ITEMS = kTile / THREADS;
-	static_assert(THREADS == kRadix, "thread d owns digit d");
+	static_assert(THREADS >= kRadix, "thread d < 256 owns digit d");
+	const bool owner = THREADS == kRadix || threadIdx.x < kRadix;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t tile_base = tile * (uint32_t)kTile;
 	const uint32_t warp_base = warp * (32 * ITEMS);
@@ -142,25 +144,27 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
 	}
 	__syncthreads();
 	// ---- thread d owns digit d: counts per warp -> exclusive over warps; tile count; scan over digits
-	uint32_t count = 0;
-#pragma unroll
-	for (int w = 0; w < WARPS; ++w) count += s_warp_cnt[w][tid];
-	if (!FULL && tid == kRadix - 1) count -= (uint32_t)kTile - n_valid;
+	uint32_t count = 0, incl = 0;
 	uint32_t* my_status = status + (size_t)tile * kRadix + tid;
-	st_volatile_u32(my_status, count | (tile == 0 ? kFlagInclusive : kFlagPartial));
-	uint32_t incl = count;
+	if (owner) {
 #pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl += t;
+		for (int w = 0; w < WARPS; ++w) count += s_warp_cnt[w][tid];
+		if (!FULL && tid == kRadix - 1) count -= (uint32_t)kTile - n_valid;
+		st_status(my_status, count | (tile == 0 ? kFlagInclusive : kFlagPartial));
+		incl = count;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) s_warp_tot[warp] = incl;
 	}
-	if (lane == 31) s_warp_tot[warp] = incl;
 	__syncthreads();
 	uint32_t digit_excl = incl - count;  // first tile-local sorted index of digit tid
+	if (owner) {
 #pragma unroll
-	for (int w = 0; w < WARPS; ++w)
-		if (w < warp) digit_excl += s_warp_tot[w];
-	{
+		for (int w = 0; w < kRadix / 32; ++w)
+			if (w < warp) digit_excl += s_warp_tot[w];
 		uint32_t run = digit_excl;
 #pragma unroll
 		for (int w = 0; w < WARPS; ++w) {
@@ -180,20 +184,32 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
 		if (valid) cp_async_u32(s_vals + pos, vin + i * 32);
 	}
 	// ---- decoupled look-back for digit tid
-	{
+	if (owner) {
 		uint32_t excl = 0;
 		if (tile != 0) {
+			// predecessors are polled kLookBack at a time (independent loads in flight): a serial walk costs one
+			// L2 round trip per predecessor and was a third of all stall samples (profiles/r01_ncu_onesweep_*)
 			const uint32_t* look = my_status - kRadix;
-			while (true) {
-				uint32_t s;
-				do {
-					s = ld_volatile_u32(look);
-				} while ((s & kFlagMask) == 0u);
-				excl += s & kValueMask;
-				if (s & kFlagInclusive) break;
-				look -= kRadix;
+			uint32_t left = tile;  // predecessors not yet consumed
+			bool done = false;
+			while (!done) {
+				uint32_t s[kLookBack];
+#pragma unroll
+				for (int j = 0; j < kLookBack; ++j)
+					s[j] = (uint32_t)j < left ? ld_status(look - j * kRadix) : kFlagInclusive;
+				int used = 0;
+#pragma unroll
+				for (int j = 0; j < kLookBack; ++j) {
+					if (!done && used == j && (s[j] & kFlagMask) != 0u) {
+						excl += s[j] & kValueMask;
+						used = j + 1;
+						if (s[j] & kFlagInclusive) done = true;
+					}
+				}
+				look -= used * kRadix;
+				left -= used;
 			}
-			st_volatile_u32(my_status, (excl + count) | kFlagInclusive);
+			st_status(my_status, (excl + count) | kFlagInclusive);
 		}
 		s_global_base[tid] = bin_base[tid] + excl - digit_excl;  // + tile-local sorted index = global index
 	}
@@ -212,7 +228,7 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
 	}
 }
 
-template <class KeyT, int THREADS, int MINB, int NBITS>
+template <class KeyT, int THREADS, int MINB, int NBITS, int LB = 8>
 __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t digit_mask,
@@ -223,7 +239,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 	uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * kTile);
 	__shared__ uint16_t s_warp_cnt[WARPS][kRadix];  // per-warp digit counts, then tile-local offsets
 	__shared__ uint32_t s_global_base[kRadix];
-	__shared__ uint32_t s_warp_tot[WARPS];
+	__shared__ uint32_t s_warp_tot[kRadix / 32];
 	__shared__ uint32_t s_tile;
 
 	const int tid = threadIdx.x;
@@ -237,10 +253,10 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 	const uint32_t tile_base = tile * (uint32_t)kTile;
 	const uint32_t n_valid = n - tile_base < (uint32_t)kTile ? n - tile_base : (uint32_t)kTile;
 	if (n_valid == (uint32_t)kTile)
-		onesweep_tile<KeyT, THREADS, true, NBITS>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask, bin_base,
+		onesweep_tile<KeyT, THREADS, true, NBITS, LB>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask, bin_base,
 		                                          status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot);
 	else
-		onesweep_tile<KeyT, THREADS, false, NBITS>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask,
+		onesweep_tile<KeyT, THREADS, false, NBITS, LB>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask,
 		                                           bin_base, status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot);
 }
 
@@ -302,7 +318,18 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 	for (int q = 0; q < P; ++q) {
 		KernelScope ks(c, prof_name, 2.0 * (double)n * (double)(key_bytes + 4));
 		const bool eight = plan.bits[q] > 7;
-		if (key64) {
+		static int variant = -1;
+		if (variant < 0) {
+			const char* e = getenv("MEMS_SORT_VARIANT");
+			variant = e ? atoi(e) : 0;
+		}
+		if (variant == 1 && !key64) launch(onesweep_kernel<uint32_t, 512, 4, 8, 8>, 512, q, cur);
+		else if (variant == 2 && !key64) launch(onesweep_kernel<uint32_t, 512, 3, 8, 8>, 512, q, cur);
+		else if (variant == 3 && !key64) launch(onesweep_kernel<uint32_t, 256, 5, 8, 16>, 256, q, cur);
+		else if (variant == 4 && !key64) launch(onesweep_kernel<uint32_t, 256, 5, 8, 32>, 256, q, cur);
+		else if (variant == 5 && !key64) launch(onesweep_kernel<uint32_t, 256, 4, 8, 8>, 256, q, cur);
+		else if (variant == 6 && !key64) launch(onesweep_kernel<uint32_t, 512, 4, 8, 32>, 512, q, cur);
+		else if (key64) {
 			if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8>, 256, q, cur);
 			else launch(onesweep_kernel<uint64_t, 256, kMinB64, 7>, 256, q, cur);
 		} else {
