@@ -196,8 +196,9 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 	__shared__ uint32_t s_hist[kMaxHitPasses * 256];
 	for (int i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) s_hist[i] = 0;
 	__syncthreads();
-	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-	if (h < n_hits) {
+	// grid-stride: a CTA describes many hits and flushes its histograms once (one flush per 256 hits would be
+	// 8 same-address global atomics per hit)
+	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += gridDim.x * blockDim.x) {
 		const uint32_t s = hit_start[h];
 		const uint32_t len = hit_len[h];
 		MemberIter<KeyT> it(a, s, len);
@@ -327,7 +328,10 @@ struct WarpHit {
 	uint32_t n_probes = 0;
 #endif
 	static constexpr int kProbe = 128;
-	typedef unsigned __int128 mask_t;  // bit i = the window at distance i+1 matches
+	// match bits of one probe, identical in every lane: bit i of word j = the window at distance 32*j + i + 1 matches
+	struct mask_t {
+		uint32_t w[4];
+	};
 
 	__device__ uint32_t member_entry(uint32_t j, int32_t& lo, int32_t& hi) const {
 		const uint32_t val = a.vals[j];
@@ -350,112 +354,136 @@ struct WarpHit {
 		len = hit_len;
 		sf = first_strand;
 		int32_t lo = INT32_MIN, hi = INT32_MAX;
-		for (uint32_t t = lane; t < len; t += 32) {
+		for (uint32_t t = lane; t < len; t += 32) {  // one pass: valid range and the first member tile together
 			int32_t l2, h2;
-			member_entry(s + t, l2, h2);
+			const uint32_t e = member_entry(s + t, l2, h2);
+			if (t < kMemberTile) s_mem[t] = e;
 			lo = max(lo, l2);
 			hi = min(hi, h2);
 		}
 		kmin = __reduce_max_sync(0xffffffffu, lo);
 		kmax = __reduce_min_sync(0xffffffffu, hi);
-		load_tile(0);
+		__syncwarp();
+	}
+	// The four keys one member contributes to this lane's windows.  e = the member's s_mem entry, k_first = the
+	// lane's nearest window.  Reverse members run backwards; the walk direction flips that again: the product is
+	// warp-uniform, so each case is straight-line code with immediate load offsets (no address arithmetic per window).
+	__device__ __forceinline__ void member_keys(uint32_t e, int32_t k_first, int dir, const bool (&ok)[4], KeyT (&v)[4]) const {
+		const bool rev = (e & kReverseBit) != 0u;
+		const int32_t base = (int32_t)(e & ~kReverseBit);
+		const KeyT* ptr = key_pos + (ptrdiff_t)(rev ? base - k_first : base + k_first);
+		if ((dir > 0) != rev) {
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				if (ok[j]) v[j] = ptr[32 * j];
+		} else {
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				if (ok[j]) v[j] = ptr[-32 * j];
+		}
 	}
 	// Probe the windows at distances 1..n_win (<= 128) from k0 in direction dir (+1/-1): lane l tests distances
 	// l+1, l+33, l+65, l+97.  Members are taken four at a time and all 16 loads of a group are issued before
-	// any is compared, so a group costs one memory round trip.  Returns the match bits, identical in every lane.
+	// any is compared, so a group costs one memory round trip; a compare is one LOP3 (difference OR-ed into the
+	// window's accumulator; reverse members compare against the reference with its strand bit flipped).
 	__device__ mask_t probe(int32_t k0, int dir, int n_win) {
 		bool ok[4];
-		KeyT ref[4];
+		KeyT ref[4], refx[4], diff[4];
 		const int32_t k_first = k0 + dir * (lane + 1);  // this lane's nearest window; the others are 32, 64, 96 further
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			const int32_t k = k_first + dir * 32 * j;
 			ok[j] = lane + 32 * j < n_win && k >= kmin && k <= kmax;  // invalid windows are never loaded
+			ref[j] = 0;
+			diff[j] = 0;
+		}
+		{
+			const uint32_t e0 = s_mem[0];
+			member_keys(e0, k_first, dir, ok, ref);
+			const KeyT r0 = (KeyT)(e0 >> 31);
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				ref[j] ^= r0;
+				refx[j] = ref[j] ^ (KeyT)1;
+			}
 		}
 		for (uint32_t first = 0; first < len; first += kMemberTile) {
 			if (first) load_tile(first);
 			const uint32_t cnt = len - first < kMemberTile ? len - first : kMemberTile;
-			for (uint32_t t0 = 0; t0 < cnt; t0 += 4) {
+			for (uint32_t t0 = first ? 0u : 1u; t0 < cnt; t0 += 4) {
 				KeyT v[4][4];
-				uint32_t rev[4];
 				const uint32_t in_group = cnt - t0 < 4 ? cnt - t0 : 4;  // warp-uniform: the tail group is not padded
 #pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					if ((uint32_t)u < in_group) {
-						const uint32_t e = s_mem[t0 + u];
-						rev[u] = e >> 31;
-						// reverse members run backwards: index = base -/+ k, one multiply-add per member and an
-						// immediate stride per further window (IMAD runs beside the ALU pipe the compares use)
-						const int32_t sign = 1 - 2 * (int32_t)rev[u];
-						const uint32_t p0 = (e & ~kReverseBit) + (uint32_t)(sign * k_first);
-						const int32_t stride = sign * dir * 32;
-#pragma unroll
-						for (int j = 0; j < 4; ++j)
-							if (32 * j < n_win && ok[j]) v[u][j] = key_pos[p0 + (uint32_t)(stride * j)];
-					}
-				}
+				for (int u = 0; u < 4; ++u)
+					if ((uint32_t)u < in_group) member_keys(s_mem[t0 + u], k_first, dir, ok, v[u]);
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
 					if ((uint32_t)u < in_group) {
+						if (s_mem[t0 + u] & kReverseBit) {
 #pragma unroll
-						for (int j = 0; j < 4; ++j) {
-							if (32 * j < n_win) {
-								const KeyT tg = v[u][j] ^ (KeyT)rev[u];  // reverse members flip the strand bit
-								if (first == 0 && t0 == 0 && u == 0) ref[j] = tg;
-								else ok[j] = ok[j] && tg == ref[j];
-							}
+							for (int j = 0; j < 4; ++j) diff[j] |= v[u][j] ^ refx[j];
+						} else {
+#pragma unroll
+							for (int j = 0; j < 4; ++j) diff[j] |= v[u][j] ^ ref[j];
 						}
 					}
 				}
-				if (cnt > 4 && !__any_sync(0xffffffffu, ok[0] | ok[1] | ok[2] | ok[3])) {  // nothing left to decide
-					t0 = cnt;
-					first = len;
+				if (t0 + 4 < cnt || first + kMemberTile < len) {  // more members to come: stop if nothing is left to decide
+					const bool alive = (ok[0] && diff[0] == 0) || (ok[1] && diff[1] == 0) || (ok[2] && diff[2] == 0) ||
+					                   (ok[3] && diff[3] == 0);
+					if (!__any_sync(0xffffffffu, alive)) {
+						t0 = cnt;
+						first = len;
+					}
 				}
 			}
 			if (len > kMemberTile) __syncwarp();
 		}
 		if (len > kMemberTile) load_tile(0);
-		const uint32_t b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
-		const uint32_t b2 = __ballot_sync(0xffffffffu, ok[2]), b3 = __ballot_sync(0xffffffffu, ok[3]);
-		return ((mask_t)(((uint64_t)b3 << 32) | b2) << 64) | (mask_t)(((uint64_t)b1 << 32) | b0);
+		mask_t m;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) m.w[j] = __ballot_sync(0xffffffffu, ok[j] && diff[j] == 0);
+		return m;
 	}
-	__device__ static int highest_set(mask_t m) {  // 1-based distance of the highest set bit, 0 if none
-		const uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
-		return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
+	__device__ static int highest_set(const mask_t& m) {  // 1-based distance of the highest set bit, 0 if none
+		if (m.w[3]) return 128 - __clz((int)m.w[3]);
+		if (m.w[2]) return 96 - __clz((int)m.w[2]);
+		if (m.w[1]) return 64 - __clz((int)m.w[1]);
+		return 32 - __clz((int)m.w[0]);
 	}
-	__device__ static int lowest_set(mask_t m) {  // 1-based distance of the lowest set bit, 0 if none
-		const uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
-		return lo ? __ffsll((long long)lo) : (hi ? 64 + __ffsll((long long)hi) : 0);
+	__device__ static int lowest_set(const mask_t& m) {  // 1-based distance of the lowest set bit, 0 if none
+		if (m.w[0]) return __ffs((int)m.w[0]);
+		if (m.w[1]) return 32 + __ffs((int)m.w[1]);
+		if (m.w[2]) return 64 + __ffs((int)m.w[2]);
+		return m.w[3] ? 96 + __ffs((int)m.w[3]) : 0;
 	}
 	// Follow the chain of matches inside one probe, starting from a match at distance `from` (0 = the window
-	// the walk stands on): consecutive matches may be at most L apart.  Bit-parallel: the chain ends right
-	// before the first run of L zero bits, found by AND-ing shifted copies of the zero mask (log steps).
-	// Returns the chain's last match; *ended tells whether that L-gap lies completely inside the n_win
-	// probed windows (the chain is over) or the probe simply ran out (continue from the returned distance).
-	__device__ static int follow(mask_t m, int from, int L, int n_win, bool* ended) {
-		const mask_t valid = n_win >= 128 ? ~(mask_t)0 : (((mask_t)1 << n_win) - 1);
-		mask_t z = ~m & valid;             // zero bits inside the probed range; beyond it nothing is known
-		if (z == 0) {  // every probed window matches (the common case inside a long match): no gap to look for
-			*ended = false;
-			return n_win > from ? n_win : from;
-		}
-		if (from) z &= ~(((mask_t)1 << from) - 1);  // ignore everything before the starting match
-		// run[i] = z[i] & z[i+1] & ... & z[i+L-1]
-		const mask_t a1 = z, a2 = a1 & (a1 >> 1), a4 = a2 & (a2 >> 2), a8 = a4 & (a4 >> 4), a16 = a8 & (a8 >> 8);
-		mask_t run = ~(mask_t)0;
-		int off = 0;
-		if (L & 16) { run &= a16 >> off; off += 16; }
-		if (L & 8) { run &= a8 >> off; off += 8; }
-		if (L & 4) { run &= a4 >> off; off += 4; }
-		if (L & 2) { run &= a2 >> off; off += 2; }
-		if (L & 1) { run &= a1 >> off; }
-		const int gap_at = lowest_set(run);  // distance of the first window of the first L-gap
-		if (gap_at) {
+	// the walk stands on): consecutive matches may be at most L apart.  The chain's last match is the first
+	// window x >= from (x = from, or a match) whose next L windows x+1..x+L all mismatch; every lane tests that
+	// for its own four windows (one funnel shift + mask each) and four ballots find the first.  Only gaps that
+	// lie completely inside the n_win probed windows count: *ended tells whether one was found (the chain is
+	// over) or the probe simply ran out (continue from the returned distance, the last match seen).
+	__device__ int follow(const mask_t& m, int from, int L, int n_win, bool* ended) const {
+		const uint32_t l_mask = (1u << L) - 1u;  // L <= 31
+		if (from == 0 && L <= n_win && (m.w[0] & l_mask) == 0u) {
 			*ended = true;
-			return gap_at - 1 > from ? gap_at - 1 : from;  // the window right before the gap is the chain's last match
+			return 0;
+		}
+		mask_t brk;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int x = lane + 1 + 32 * j;
+			const uint32_t next = __funnelshift_rc(m.w[j], j < 3 ? m.w[j + 1] : 0u, lane + 1) & l_mask;
+			const bool here = ((m.w[j] >> lane) & 1u) ? x >= from : x == from;
+			brk.w[j] = __ballot_sync(0xffffffffu, here && next == 0u && x + L <= n_win);
+		}
+		const int gap_after = lowest_set(brk);
+		if (gap_after) {
+			*ended = true;
+			return gap_after;
 		}
 		*ended = false;
-		const int last = highest_set(m & valid);
+		const int last = highest_set(m);
 		return last > from ? last : from;
 	}
 	// Walk from window k0 in direction dir over matching windows that start <= L apart, as far as they go
@@ -629,7 +657,7 @@ __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_
 		int chain_end = 0;
 		if (first) {
 			bool ended;
-			chain_end = WarpHit<KeyT>::follow(m, first, L, 128, &ended);
+			chain_end = w.follow(m, first, L, 128, &ended);
 			if (!ended) chain_end = last;
 		}
 		if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
@@ -804,7 +832,7 @@ giant_walk_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView 
 			int chain_end = 0;
 			if (first) {
 				bool ended;
-				chain_end = WarpHit<KeyT>::follow(m, first, L, 128, &ended);
+				chain_end = w.follow(m, first, L, 128, &ended);
 				if (!ended) chain_end = last;
 			}
 			if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
@@ -1197,8 +1225,9 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	const uint32_t hit_blocks = (n_hits + 255) / 256;
 	{
 		KernelScope ks(c, "hit_describe");
-		hit_describe_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, hit_start.p, hit_len.p, n_hits, hk_a.p, hid_a.p,
-		                                                             hist.p, plan);
+		const uint32_t describe_blocks = std::min(hit_blocks, (uint32_t)c->sm_count * 8u);
+		hit_describe_kernel<KeyT><<<describe_blocks, 256, 0, c->stream>>>(a, hit_start.p, hit_len.p, n_hits, hk_a.p, hid_a.p,
+		                                                                  hist.p, plan);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	void* kp[2] = {hk_a.p, hk_b.p};
@@ -1825,10 +1854,10 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	if (n1) {
 		DevBuf<uint32_t> hist(c, (size_t)hplan.n_passes * 256);
 		MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)hplan.n_passes * 256 * sizeof(uint32_t), c->stream));
-		const uint32_t hb = (n1 + 255) / 256;
+		const uint32_t hb = (n1 + 255) / 256, describe_blocks = std::min(hb, (uint32_t)c->sm_count * 8u);
 		{
 			KernelScope ks(c, "hit_describe");
-			hit_describe_kernel<KeyT><<<hb, 256, 0, c->stream>>>(a1, hits1.start.p, hits1.len.p, n1, hk_a.p, hid_a.p, hist.p, hplan);
+			hit_describe_kernel<KeyT><<<describe_blocks, 256, 0, c->stream>>>(a1, hits1.start.p, hits1.len.p, n1, hk_a.p, hid_a.p, hist.p, hplan);
 			MEMS_CUDA(cudaGetLastError());
 		}
 		void* kp[2] = {hk_a.p, hk_b.p};
