@@ -74,53 +74,124 @@ __device__ __forceinline__ uint32_t strand_of(const void* keys, uint32_t i) {
 constexpr int kScanBlock = 256;
 
 // run_info[i] = number of union entries in the hit that starts at i (0 = no hit starts here)
+//
+// Warp-cooperative: a warp looks at 32 consecutive union entries and decides the runs that START in its first
+// `own` lanes (the next warp starts `own` entries further, so the windows overlap by 32 - own entries and
+// runs of up to that length close inside the window).  Heads and run ends are two ballots; a sequence that
+// occurs twice in a run is found with one MATCH.ANY on (run start, sequence); every decision is then bit
+// arithmetic on warp-uniform masks — no per-thread loop over the run, no divergent loads.  Runs that do not
+// close inside the window (longer than the overlap: repeats, or more sequences than the overlap) are walked
+// serially by their head lane as before.
+struct ScanShape {
+	uint32_t own;             // run heads a warp decides: entries [warp * own, warp * own + own)
+	uint32_t chunks_per_cta;  // a CTA takes this many consecutive chunks of kScanBlock / 32 warps
+};
+__host__ __device__ inline uint32_t scan_chunk_entries(const ScanShape& sh) { return sh.own * (kScanBlock / 32); }
+
+template <class KeyT>
+__device__ __forceinline__ uint16_t serial_run(const MatchArgs& a, uint32_t i, uint64_t mk, uint32_t* my_run) {
+	uint32_t len = 1;
+	bool ok = true;
+	if (a.mode == MEMS_MODE_MEMHASH) {
+		// at most one occurrence per sequence (repeat_tolerance 0), >= 2 sequences
+		uint64_t seen = 1ull << (a.vals[i] >> a.pos_bits);
+		uint32_t j = i + 1;
+		while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
+			if (ok) {
+				uint64_t bit = 1ull << (a.vals[j] >> a.pos_bits);
+				if (seen & bit) ok = false;
+				seen |= bit;
+			}
+			++len;
+			++j;
+		}
+		if (a.seq_set && seen != a.seq_set) ok = false;  // MaskedMemHash::HashMatch, MaskedMemHash.cpp:50-60
+	} else {
+		uint32_t j = i + 1;
+		while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
+			++len;
+			++j;
+		}
+	}
+	*my_run = len;
+	if (len > kRunCap) ok = false;
+	return ok ? (uint16_t)len : (uint16_t)0;
+}
+
 template <class KeyT>
 __global__ void __launch_bounds__(kScanBlock)
-run_scan_kernel(MatchArgs a, uint16_t* __restrict__ run_info, uint32_t* __restrict__ block_hits,
+run_scan_kernel(MatchArgs a, ScanShape sh, uint16_t* __restrict__ run_info, uint32_t* __restrict__ block_hits,
                 uint32_t* __restrict__ max_run) {
 	__shared__ uint32_t s_cnt[kScanBlock / 32];
 	__shared__ uint32_t s_max[kScanBlock / 32];
-	const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-	uint16_t info = 0;
-	uint32_t my_run = 0;
-	if (i < a.n) {
-		const uint64_t mk = masked_of<KeyT>(a.keys, i);
-		const bool head = i == 0 || masked_of<KeyT>(a.keys, i - 1) != mk;
-		if (head && i + 1 < a.n && masked_of<KeyT>(a.keys, i + 1) == mk) {
-			uint32_t len = 1;
-			bool ok = true;
-			if (a.mode == MEMS_MODE_MEMHASH) {
-				// at most one occurrence per sequence (repeat_tolerance 0), >= 2 sequences
-				uint64_t seen = 1ull << (a.vals[i] >> a.pos_bits);
-				uint32_t j = i + 1;
-				while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
-					if (ok) {
-						uint64_t bit = 1ull << (a.vals[j] >> a.pos_bits);
-						if (seen & bit) ok = false;
-						seen |= bit;
-					}
-					++len;
-					++j;
-				}
-				if (a.seq_set && seen != a.seq_set) ok = false;  // MaskedMemHash::HashMatch, MaskedMemHash.cpp:50-60
-			} else {
-				uint32_t j = i + 1;
-				while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
-					++len;
-					++j;
-				}
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const KeyT* keys = reinterpret_cast<const KeyT*>(a.keys);
+	const uint32_t lanemask_lt = (1u << lane) - 1u;
+	const int n_set = __popcll(a.seq_set);
+	const int seq_bits = 32 - __clz(max(a.n_seqs - 1, 1));
+	uint32_t hits = 0, longest = 0;  // per warp (kept in lane 0) / per lane
+	for (uint32_t c = 0; c < sh.chunks_per_cta; ++c) {
+		const uint64_t g0 = ((uint64_t)(blockIdx.x * sh.chunks_per_cta + c) * (kScanBlock / 32) + warp) * sh.own;
+		if (g0 >= a.n) break;  // warp-uniform
+		const uint32_t i = (uint32_t)g0 + lane;
+		const bool in = i < a.n;
+		const KeyT mk = in ? (KeyT)(keys[i] >> 1) : (KeyT)0;
+		const uint32_t seq = in ? a.vals[i] >> a.pos_bits : 0u;
+		// neighbours' keys straight from memory (L1 hits): shuffles, like MATCH, queue in the MIO pipe, which bounds
+		// this kernel (ncu: mio_throttle is the top stall with MATCH.ANY + 64-bit shuffles)
+		const bool has_prev = i > 0, has_next = i + 1 < a.n;
+		const KeyT prev_mk = in && has_prev ? (KeyT)(keys[i - 1] >> 1) : (KeyT)0;
+		const KeyT next_mk = in && has_next ? (KeyT)(keys[i + 1] >> 1) : (KeyT)0;
+		const bool head = in && (!has_prev || prev_mk != mk);
+		const bool end = in && (!has_next || next_mk != mk);
+		const uint32_t heads = __ballot_sync(0xffffffffu, head), ends = __ballot_sync(0xffffffffu, end);
+		// the run this lane belongs to: from the nearest head at or below it to the nearest end at or above it
+		const uint32_t at_or_below = heads & (lanemask_lt | (1u << lane));
+		const uint32_t at_or_above = ends & ~lanemask_lt;
+		uint32_t dups = 0, foreign = 0;
+		if (a.mode == MEMS_MODE_MEMHASH) {
+			// lanes holding the same sequence: one ballot per bit of the sequence id
+			uint32_t same_seq = 0xffffffffu;
+			for (int b = 0; b < seq_bits; ++b) {
+				const bool bit = (seq >> b) & 1u;
+				const uint32_t m = __ballot_sync(0xffffffffu, bit);
+				same_seq &= bit ? m : ~m;
 			}
-			my_run = len;
-			if (len > kRunCap) ok = false;
-			if (ok) info = (uint16_t)len;
+			// earlier lanes of my run (runs that began before the window are decided by the previous warp)
+			const uint32_t run_from = at_or_below ? 31u - (uint32_t)__clz((int)at_or_below) : 32u;
+			const uint32_t earlier = run_from < 32u ? lanemask_lt & ~((1u << run_from) - 1u) : 0u;
+			dups = __ballot_sync(0xffffffffu, in && (same_seq & earlier) != 0u);
+			if (a.seq_set) foreign = __ballot_sync(0xffffffffu, in && !((a.seq_set >> seq) & 1ull));
 		}
-		run_info[i] = info;
+		uint16_t info = 0;
+		uint32_t my_run = 0;
+		if (head && lane < sh.own) {
+			if (at_or_above) {
+				const uint32_t e = (uint32_t)__ffs((int)at_or_above) - 1u;
+				const uint32_t len = e - lane + 1u;
+				const uint32_t members = (2u << e) - (1u << lane);  // lanes lane..e (e = 31 wraps to the right mask)
+				if (len >= 2u) {
+					my_run = len;
+					bool ok = true;  // len <= 32 < kRunCap
+					if (a.mode == MEMS_MODE_MEMHASH) {
+						ok = (dups & members) == 0u;
+						if (a.seq_set) ok = ok && (foreign & members) == 0u && (int)len == n_set;  // MaskedMemHash.cpp:50-60
+					}
+					if (ok) info = (uint16_t)len;
+				}
+			} else {  // the run goes on past the window
+				info = serial_run<KeyT>(a, i, (uint64_t)mk, &my_run);
+			}
+		}
+		if (in && lane < sh.own) run_info[i] = info;
+		const uint32_t b = __ballot_sync(0xffffffffu, info != 0);
+		hits += __popc(b);
+		longest = max(longest, my_run);
 	}
-	uint32_t b = __ballot_sync(0xffffffffu, info != 0);
-	my_run = __reduce_max_sync(0xffffffffu, my_run);
-	if ((threadIdx.x & 31) == 0) {
-		s_cnt[threadIdx.x >> 5] = __popc(b);
-		s_max[threadIdx.x >> 5] = my_run;
+	longest = __reduce_max_sync(0xffffffffu, longest);
+	if (lane == 0) {
+		s_cnt[warp] = hits;
+		s_max[warp] = longest;
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -134,22 +205,57 @@ run_scan_kernel(MatchArgs a, uint16_t* __restrict__ run_info, uint32_t* __restri
 	}
 }
 
+// hits in key order: every CTA compacts the entries run_scan_kernel's CTA of the same index decided;
+// a thread takes 8 consecutive entries (one 128-bit load), a CTA 2048 per round
 __global__ void __launch_bounds__(kScanBlock)
-hit_compact_kernel(const uint16_t* __restrict__ run_info, uint32_t n, const uint32_t* __restrict__ block_off,
+hit_compact_kernel(const uint16_t* __restrict__ run_info, uint32_t n, ScanShape sh, const uint32_t* __restrict__ block_off,
                    uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len) {
 	__shared__ uint32_t s_cnt[kScanBlock / 32];
-	const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-	const uint16_t info = i < n ? run_info[i] : (uint16_t)0;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t b = __ballot_sync(0xffffffffu, info != 0);
-	if (lane == 0) s_cnt[warp] = __popc(b);
-	__syncthreads();
+	const uint64_t per_cta = (uint64_t)scan_chunk_entries(sh) * sh.chunks_per_cta;  // a multiple of 8
+	const uint64_t first = (uint64_t)blockIdx.x * per_cta;
+	const uint64_t last = first + per_cta < n ? first + per_cta : n;
 	uint32_t off = block_off[blockIdx.x];
-	for (uint32_t w = 0; w < warp; ++w) off += s_cnt[w];
-	if (info) {
-		uint32_t at = off + __popc(b & ((1u << lane) - 1u));
-		hit_start[at] = i;
-		hit_len[at] = info;
+	for (uint64_t base = first; base < last; base += kScanBlock * 8) {
+		const uint64_t i0 = base + (uint64_t)threadIdx.x * 8;
+		uint16_t info[8];
+		if (i0 + 8 <= last) {
+			const uint4 raw = *reinterpret_cast<const uint4*>(run_info + i0);
+			const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+			for (int k = 0; k < 8; ++k) info[k] = (uint16_t)(r[k >> 1] >> ((k & 1) * 16));
+		} else {
+#pragma unroll
+			for (int k = 0; k < 8; ++k) info[k] = i0 + k < last ? run_info[i0 + k] : (uint16_t)0;
+		}
+		uint32_t mine = 0;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) mine += info[k] != 0;
+		uint32_t incl = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) s_cnt[warp] = incl;
+		__syncthreads();
+		uint32_t at = off + incl - mine, total = 0;
+#pragma unroll
+		for (uint32_t w = 0; w < kScanBlock / 32; ++w) {
+			const uint32_t cnt = s_cnt[w];
+			if (w < warp) at += cnt;
+			total += cnt;
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			if (info[k]) {
+				hit_start[at] = (uint32_t)(i0 + k);
+				hit_len[at] = info[k];
+				++at;
+			}
+		}
+		off += total;
+		__syncthreads();
 	}
 }
 
@@ -634,8 +740,61 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 // a 32-warp CTA: every round the warps probe 32 x 128 consecutive windows at once, each summarises its 128
 // bits (first match, end of the chain that starts there, last match) and thread 0 stitches the summaries.
 constexpr int kLongWarps = 16;   // warps per CTA: two CTAs share an SM, so one's barrier waits overlap the other's probes
-constexpr int kLongSpan = kLongWarps * 128;
-constexpr int kCtaRoundBudget = 192; // rounds one CTA spends on a walk before the whole grid takes it over
+constexpr int kLongProbes = 4;   // consecutive probes a warp makes per round: the barriers and the stitch are paid once per
+                                 // 8192 windows, and the warps' probe latencies overlap freely in between
+constexpr int kWarpSpan = 128 * kLongProbes;
+constexpr int kLongSpan = kLongWarps * kWarpSpan;
+constexpr int kCtaRoundBudget = 48; // rounds one CTA spends on a walk before the whole grid takes it over
+
+struct ChainSummary {
+	int first, chain_end, last;  // 1-based distances inside the summarised span, 0 = no match
+};
+__device__ inline ChainSummary combine_summaries(const int4* child, int n, int unit, int L) {
+	ChainSummary r{0, 0, 0};
+	int cur = 0;
+	bool broken = false;
+	for (int i = 0; i < n; ++i) {
+		const int4 c = child[i];
+		if (!c.x) continue;
+		const int f = unit * i + c.x, ce = unit * i + c.y;
+		if (!r.first) {
+			r.first = f;
+			cur = ce;
+			broken = c.y != c.z;
+		} else if (!broken) {
+			if (f - cur > L) broken = true;
+			else {
+				cur = ce;
+				if (c.y != c.z) broken = true;
+			}
+		}
+		r.last = unit * i + c.z;
+	}
+	r.chain_end = cur;
+	return r;
+}
+
+// Summary of the kWarpSpan windows after k_base (distances 1..kWarpSpan), probe by probe: first match, last match
+// of the chain that starts at the first match, last match overall.
+template <class KeyT>
+__device__ __forceinline__ int4 warp_span_summary(WarpHit<KeyT>& w, int32_t k_base, int dir, int L) {
+	typedef typename WarpHit<KeyT>::mask_t mask_t;
+	int4 child[kLongProbes];
+#pragma unroll
+	for (int p = 0; p < kLongProbes; ++p) {
+		const mask_t m = w.probe(k_base + dir * 128 * p, dir, 128);
+		const int f = WarpHit<KeyT>::lowest_set(m), l = WarpHit<KeyT>::highest_set(m);
+		int ce = 0;
+		if (f) {
+			bool ended;
+			ce = w.follow(m, f, L, 128, &ended);
+			if (!ended) ce = l;
+		}
+		child[p] = make_int4(f, ce, l, 0);
+	}
+	const ChainSummary cs = combine_summaries(child, kLongProbes, 128, L);
+	return make_int4(cs.first, cs.chain_end, cs.last, 0);
+}
 
 template <class KeyT>
 __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_t stop_dist, bool* linked, int4* s_sum,
@@ -650,17 +809,8 @@ __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_
 			*linked = false;
 			return walked;
 		}
-		const mask_t m = w.probe(k0 + dir * (walked + 128 * warp), dir, 128);
-		// summary of this warp's 128 windows (distances 1..128 from its own base): first match, last match of
-		// the chain that starts at the first match, last match overall
-		const int first = WarpHit<KeyT>::lowest_set(m), last = WarpHit<KeyT>::highest_set(m);
-		int chain_end = 0;
-		if (first) {
-			bool ended;
-			chain_end = w.follow(m, first, L, 128, &ended);
-			if (!ended) chain_end = last;
-		}
-		if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
+		const int4 mine = warp_span_summary<KeyT>(w, k0 + dir * (walked + kWarpSpan * warp), dir, L);
+		if (w.lane == 0) s_sum[warp] = mine;
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			int32_t cur = 0;  // last confirmed match, as a distance from this round's base
@@ -669,10 +819,10 @@ __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_
 				if (stop_dist >= 0 && stop_dist <= walked + cur + L) state = 2;
 				const int4 sm = s_sum[i];
 				if (state || !sm.x) continue;
-				if (128 * i + sm.x - cur > L) {
+				if (kWarpSpan * i + sm.x - cur > L) {
 					state = 1;
 				} else {
-					cur = 128 * i + sm.y;
+					cur = kWarpSpan * i + sm.y;
 					if (stop_dist >= 0 && stop_dist <= walked + cur + L) state = 2;
 					else if (sm.y != sm.z) state = 1;  // a gap > L inside this warp's windows
 				}
@@ -773,34 +923,6 @@ long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegV
 // per-CTA summaries meet in global memory, CTA 0 stitches them (same rule as inside a CTA) and a grid-wide
 // barrier publishes the result.  One round covers gridDim x 2048 windows (~600 k on a B200), so the longest
 // diagonal of a genome set costs a handful of rounds instead of being the critical path of the whole call.
-struct ChainSummary {
-	int first, chain_end, last;  // 1-based distances inside the summarised span, 0 = no match
-};
-__device__ inline ChainSummary combine_summaries(const int4* child, int n, int unit, int L) {
-	ChainSummary r{0, 0, 0};
-	int cur = 0;
-	bool broken = false;
-	for (int i = 0; i < n; ++i) {
-		const int4 c = child[i];
-		if (!c.x) continue;
-		const int f = unit * i + c.x, ce = unit * i + c.y;
-		if (!r.first) {
-			r.first = f;
-			cur = ce;
-			broken = c.y != c.z;
-		} else if (!broken) {
-			if (f - cur > L) broken = true;
-			else {
-				cur = ce;
-				if (c.y != c.z) broken = true;
-			}
-		}
-		r.last = unit * i + c.z;
-	}
-	r.chain_end = cur;
-	return r;
-}
-
 template <class KeyT>
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
 giant_walk_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ giant,
@@ -827,18 +949,11 @@ giant_walk_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView 
 		int32_t walked = 0;
 		int state = 0;
 		while (!state) {
-			const mask_t m = w.probe(c0 + dir * (walked + kLongSpan * (int32_t)blockIdx.x + 128 * warp), dir, 128);
-			const int first = WarpHit<KeyT>::lowest_set(m), last = WarpHit<KeyT>::highest_set(m);
-			int chain_end = 0;
-			if (first) {
-				bool ended;
-				chain_end = w.follow(m, first, L, 128, &ended);
-				if (!ended) chain_end = last;
-			}
-			if (w.lane == 0) s_sum[warp] = make_int4(first, chain_end, last, 0);
+			const int4 mine = warp_span_summary<KeyT>(w, c0 + dir * (walked + kLongSpan * (int32_t)blockIdx.x + kWarpSpan * warp), dir, L);
+			if (w.lane == 0) s_sum[warp] = mine;
 			__syncthreads();
 			if (threadIdx.x == 0) {
-				const ChainSummary cs = combine_summaries(s_sum, kLongWarps, 128, L);
+				const ChainSummary cs = combine_summaries(s_sum, kLongWarps, kWarpSpan, L);
 				g_sum[blockIdx.x] = make_int4(cs.first, cs.chain_end, cs.last, 0);
 			}
 			grid.sync();
@@ -1073,13 +1188,19 @@ struct HitSet {
 template <class KeyT>
 static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	const uint32_t n = a.n;
-	const uint32_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
+	// overlap of the warps' windows = the longest run that must close inside one (up to 16 sequences' worth)
+	ScanShape sh;
+	sh.own = 32u - (uint32_t)std::min(std::max(a.n_seqs, 2), 16);
+	if (a.mode != MEMS_MODE_MEMHASH) sh.own = 24;  // repeat policy: copies per family, not sequences, set the run length
+	const uint64_t n_chunks = ((uint64_t)n + scan_chunk_entries(sh) - 1) / scan_chunk_entries(sh);
+	sh.chunks_per_cta = (uint32_t)std::max<uint64_t>(1, n_chunks / ((uint64_t)c->sm_count * 16));
+	const uint32_t n_blocks = (uint32_t)((n_chunks + sh.chunks_per_cta - 1) / sh.chunks_per_cta);
 	DevBuf<uint16_t> run_info(c, n);
 	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 2);
 	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(uint32_t), c->stream));
 	{
 		KernelScope ks(c, "run_scan", (double)n * (sizeof(KeyT) + 2.0));
-		run_scan_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, run_info.p, block_hits.p, scalars.p + 0);
+		run_scan_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, sh, run_info.p, block_hits.p, scalars.p + 0);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, block_hits.p, block_hits.p, n_blocks, scalars.p + 1);
@@ -1093,7 +1214,7 @@ static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	hits.len = DevBuf<uint16_t>(c, hits.n);
 	{
 		KernelScope ks(c, "hit_compact", (double)n * 2.0);
-		hit_compact_kernel<<<n_blocks, kScanBlock, 0, c->stream>>>(run_info.p, n, block_hits.p, hits.start.p, hits.len.p);
+		hit_compact_kernel<<<n_blocks, kScanBlock, 0, c->stream>>>(run_info.p, n, sh, block_hits.p, hits.start.p, hits.len.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 }
