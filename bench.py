@@ -53,47 +53,62 @@ def make_genomes(name, n_genomes, length, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons while the timed regions run (B200_PROFILING.md's clocks line), sampled
+    in-process through NVML every 20 ms: an `nvidia-smi -lms` child takes the driver lock while it starts up and
+    stalled the first timed region by milliseconds."""
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.stop_flag, self.t, self.nvml = device, [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()  # first query outside the timed region
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001 - NVML missing or refused: report it instead of failing the bench
+            self.nvml, self.err = None, str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if self.device < len(ids) and ids[self.device].strip().isdigit():
+                return int(ids[self.device])
+        return self.device
+
+    def _sample(self):
+        n = self.nvml
+        self.rows.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)),
+                          int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+
+    def _loop(self):
+        while not self.stop_flag.wait(0.02):
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                return
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if not self.nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag.set()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for k, nm in enumerate(names):
-                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        n = self.nvml
+        names = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
+        try:
+            n.nvmlShutdown()
+        except Exception:  # noqa: BLE001
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(sm), "source": "NVML, 20 ms period, all three timed regions"}
 
 
 def run_reference(args, name):
@@ -164,6 +179,12 @@ def main():
     name = args.workload
     if args.impl == "reference":
         return run_reference(args, name)
+
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) are sent to stderr, the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import libmems_b200 as mems
@@ -328,7 +349,8 @@ def main():
             line["kernel_ms_total_per_rank"] = [sum(d.values()) for d in rank_kernel_ms]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(name)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         comm.close()
     ctx.close()

@@ -132,25 +132,36 @@ void comm_all_gather_u64(Comm* c, const uint64_t* d_send, uint64_t* d_recv, size
 	check(nccl().AllGather(d_send, d_recv, n, ncclUint64, c->comm, c->ctx->stream), "ncclAllGather");
 }
 
-// all-to-all with per-peer element counts; buffers are laid out peer-major (offsets = prefix sums of the counts)
+// all-to-all with per-peer element counts; buffers are laid out peer-major (offsets = prefix sums of the counts).
+// Several arrays that share the counts (keys and values of the same records) go out in ONE NCCL group, i.e. one
+// fused send/recv kernel instead of one per array, and the rank's own slice is a plain device copy instead of
+// an NCCL send to itself.
+void comm_all_to_all_v_multi(Comm* c, int n_arrays, const void* const* d_send, void* const* d_recv, const size_t* elem_bytes,
+                             const uint64_t* send_counts, const uint64_t* recv_counts) {
+	if (c->world > 1) check(nccl().GroupStart(), "ncclGroupStart");
+	for (int a = 0; a < n_arrays; ++a) {
+		const char* s = static_cast<const char*>(d_send[a]);
+		char* r = static_cast<char*>(d_recv[a]);
+		const size_t eb = elem_bytes[a];
+		size_t so = 0, ro = 0;
+		for (int p = 0; p < c->world; ++p) {
+			if (p == c->rank) {
+				if (send_counts[p])
+					MEMS_CUDA(cudaMemcpyAsync(r + ro, s + so, send_counts[p] * eb, cudaMemcpyDeviceToDevice, c->ctx->stream));
+			} else {
+				if (send_counts[p]) check(nccl().Send(s + so, send_counts[p] * eb, ncclChar, p, c->comm, c->ctx->stream), "ncclSend");
+				if (recv_counts[p]) check(nccl().Recv(r + ro, recv_counts[p] * eb, ncclChar, p, c->comm, c->ctx->stream), "ncclRecv");
+			}
+			so += send_counts[p] * eb;
+			ro += recv_counts[p] * eb;
+		}
+	}
+	if (c->world > 1) check(nccl().GroupEnd(), "ncclGroupEnd");
+}
+
 void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts, void* d_recv, const uint64_t* recv_counts,
                        size_t elem_bytes) {
-	const char* s = static_cast<const char*>(d_send);
-	char* r = static_cast<char*>(d_recv);
-	if (c->world == 1) {
-		if (send_counts[0])
-			MEMS_CUDA(cudaMemcpyAsync(r, s, send_counts[0] * elem_bytes, cudaMemcpyDeviceToDevice, c->ctx->stream));
-		return;
-	}
-	check(nccl().GroupStart(), "ncclGroupStart");
-	size_t so = 0, ro = 0;
-	for (int p = 0; p < c->world; ++p) {
-		if (send_counts[p]) check(nccl().Send(s + so, send_counts[p] * elem_bytes, ncclChar, p, c->comm, c->ctx->stream), "ncclSend");
-		if (recv_counts[p]) check(nccl().Recv(r + ro, recv_counts[p] * elem_bytes, ncclChar, p, c->comm, c->ctx->stream), "ncclRecv");
-		so += send_counts[p] * elem_bytes;
-		ro += recv_counts[p] * elem_bytes;
-	}
-	check(nccl().GroupEnd(), "ncclGroupEnd");
+	comm_all_to_all_v_multi(c, 1, &d_send, &d_recv, &elem_bytes, send_counts, recv_counts);
 }
 
 // all-gather with per-rank byte counts: rank p's bytes land at d_recv + offsets[p] on every rank.

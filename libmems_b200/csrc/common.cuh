@@ -218,6 +218,8 @@ void comm_all_reduce_u64(Comm* c, uint64_t* d_buf, size_t n);
 void comm_all_gather_u64(Comm* c, const uint64_t* d_send, uint64_t* d_recv, size_t n);
 void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts, void* d_recv, const uint64_t* recv_counts,
                        size_t elem_bytes);
+void comm_all_to_all_v_multi(Comm* c, int n_arrays, const void* const* d_send, void* const* d_recv, const size_t* elem_bytes,
+                             const uint64_t* send_counts, const uint64_t* recv_counts);  // arrays sharing the counts, one group
 void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t* byte_counts, const uint64_t* byte_offsets);
 void comm_all_gather_v_wait(Comm* c);
 void comm_side_synchronize(Comm* c);

@@ -1917,8 +1917,10 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	DevBuf<uint32_t> rv_a(c, n_recv), rv_b(c, n_recv);
 	{
 		KernelScope ks(c, "nccl_all_to_all_records", (double)n_loc * (K + 4));
-		comm_all_to_all_v(comm, keys_part.p, send_counts.data(), rk_a.p, recv_counts.data(), K);
-		comm_all_to_all_v(comm, vals_part.p, send_counts.data(), rv_a.p, recv_counts.data(), 4);
+		const void* snd[2] = {keys_part.p, vals_part.p};
+		void* rcv[2] = {rk_a.p, rv_a.p};
+		const size_t eb[2] = {K, 4};
+		comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, send_counts.data(), recv_counts.data());
 	}
 	keys_part.reset();
 	vals_part.reset();
@@ -2028,8 +2030,10 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	{
 		KernelScope ks(c, "nccl_all_to_all_hits", (double)n1 * 4 + (double)n_mem1 * 5);
 		comm_all_to_all_v(comm, slen.p, hs.data(), r_len.p, hr.data(), 4);
-		comm_all_to_all_v(comm, s_mval.p, ms.data(), r_mval.p, mr.data(), 4);
-		comm_all_to_all_v(comm, s_mstr.p, ms.data(), r_mstr.p, mr.data(), 1);
+		const void* snd[2] = {s_mval.p, s_mstr.p};
+		void* rcv[2] = {r_mval.p, r_mstr.p};
+		const size_t eb[2] = {4, 1};
+		comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, ms.data(), mr.data());
 	}
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers below go out of scope
 	mark("all-to-all hits");
