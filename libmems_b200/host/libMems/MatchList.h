@@ -50,6 +50,39 @@ public:
 			sml_table.push_back(sml);
 		}
 	}
+	// LoadSMLs (MatchList.h:262-349): one .sml file per sequence (sml_filename); a file that loads and carries the
+	// wanted seed is used, any other is (re)created with DNAFileSML::Create.  `solid` has no effect, as in the
+	// reference: it assigns getSolidSeed() to a shadowing local that dies at once (MatchList.h:275-276).
+	void LoadSMLs(unsigned mer_size, std::ostream* log_stream, int seed_rank = 0, bool solid = false, bool force_create = false) {
+		if (mer_size == 0) {
+			mer_size = GetDefaultMerSize(seq_table);
+			if (log_stream) (*log_stream) << "Using weight " << mer_size << " mers for initial seeds\n";
+		}
+		(void)solid;
+		const uint64_t default_seed = (uint64_t)getSeed((int)mer_size, seed_rank);
+		for (size_t i = 0; i < seq_table.size(); ++i) {
+			DNAFileSML* file_sml = new DNAFileSML(sml_filename[i]);
+			sml_table.push_back(file_sml);
+			bool usable = !force_create;
+			if (usable) {
+				try {
+					file_sml->LoadFile(sml_filename[i]);
+				} catch (const MemsException&) {
+					usable = false;
+				}
+			}
+			if (usable && file_sml->Seed() != default_seed) {
+				if (log_stream) (*log_stream) << "Default seed mismatch.  A new sorted mer list will be created.\n";
+				usable = false;
+			}
+			if (usable) {
+				if (log_stream) (*log_stream) << "Sorted mer list loaded successfully\n";
+				continue;
+			}
+			if (log_stream) (*log_stream) << "Creating sorted mer list\n";
+			file_sml->Create(*seq_table[i], default_seed);
+		}
+	}
 	void Clear() {  // MatchList.h:438-457
 		for (auto* s : seq_table) delete s;
 		for (auto* s : sml_table) delete s;

@@ -15,6 +15,7 @@
 #include "libMems/SeedOccurrenceList.h"
 
 #include <chrono>
+#include <cstddef>
 #include <vector>
 #include <string>
 #include <cstring>
@@ -72,6 +73,72 @@ int ref_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* position
 	} catch (const char* s) {
 		g_err = s;
 		return 2;
+	}
+}
+
+// The bytes FileSML::Create would write for this sequence (FileSML.cpp:344-366: header struct, SetSequence's
+// words, sorted positions), assembled from the reference's own in-memory DNAMemorySML — FileSML.cpp itself
+// needs the whole aligner to compile.  header.version is set like DNAFileSML's constructors do
+// (DNAFileSML.cpp:22-31).  layout_out (optional, 16 entries) receives sizeof(SMLHeader) and the offset of
+// every field, so the façade's copy of the struct can be pinned to the reference's header.
+namespace {
+struct ExposedSML : public DNAMemorySML {
+	const uint32* words() const { return sequence; }
+	uint64 n_words() const { return binary_seq_len; }
+	SMLHeader& hdr() { return header; }
+};
+}
+int64_t ref_sml_file_image(const char* seq, uint64_t n, uint64_t seed, uint8_t* out, uint64_t cap, uint32_t* layout_out) {
+	try {
+		if (layout_out) {
+			uint32_t* l = layout_out;
+			*l++ = (uint32_t)sizeof(SMLHeader);
+			*l++ = (uint32_t)offsetof(SMLHeader, version);
+			*l++ = (uint32_t)offsetof(SMLHeader, alphabet_bits);
+			*l++ = (uint32_t)offsetof(SMLHeader, seed);
+			*l++ = (uint32_t)offsetof(SMLHeader, seed_length);
+			*l++ = (uint32_t)offsetof(SMLHeader, seed_weight);
+			*l++ = (uint32_t)offsetof(SMLHeader, length);
+			*l++ = (uint32_t)offsetof(SMLHeader, unique_mers);
+			*l++ = (uint32_t)offsetof(SMLHeader, word_size);
+			*l++ = (uint32_t)offsetof(SMLHeader, little_endian);
+			*l++ = (uint32_t)offsetof(SMLHeader, id);
+			*l++ = (uint32_t)offsetof(SMLHeader, circular);
+			*l++ = (uint32_t)offsetof(SMLHeader, translation_table);
+			*l++ = (uint32_t)offsetof(SMLHeader, description);
+			*l++ = (uint32_t)sizeof(smlSeqI_t);
+			*l++ = 0;
+		}
+		gnSequence gs(seq, n);
+		ExposedSML sml;
+		sml.Create(gs, seed);
+		sml.hdr().version = 5;  // DNAFileSML::FormatVersion()
+		const uint64_t len = sml.SMLLength();
+		const uint64_t total = sizeof(SMLHeader) + sml.n_words() * sizeof(uint32) + len * sizeof(smlSeqI_t);
+		if (!out) return (int64_t)total;
+		if (cap < total) {
+			g_err = "buffer too small";
+			return -1;
+		}
+		uint8_t* w = out;
+		SMLHeader h = sml.GetHeader();
+		memcpy(w, &h, sizeof h);
+		w += sizeof h;
+		memcpy(w, sml.words(), sml.n_words() * sizeof(uint32));
+		w += sml.n_words() * sizeof(uint32);
+		std::vector<bmer> all;
+		sml.Read(all, len, 0);
+		for (uint64_t i = 0; i < len; ++i) {
+			memcpy(w, &all[i].position, sizeof(smlSeqI_t));
+			w += sizeof(smlSeqI_t);
+		}
+		return (int64_t)total;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return -1;
+	} catch (const char* m) {
+		g_err = m;
+		return -1;
 	}
 }
 

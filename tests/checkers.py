@@ -170,6 +170,20 @@ class Reference(_Checker):
         self.last = {"seed_mask": sm.value, "mer_mask": mm.value, "secs": secs.value}
         return pos[:n.value].copy(), mers[:n.value].copy()
 
+    def sml_file_image(self, seq, seed):
+        """Bytes of the .sml file FileSML::Create would write (header, packed words, positions) + header layout."""
+        s = _as_bytes(seq)
+        layout = np.zeros(16, np.uint32)
+        self.lib.ref_sml_file_image.restype = ctypes.c_int64
+        total = self.lib.ref_sml_file_image(s, u64(len(s)), u64(seed), None, u64(0), _ptr(layout))
+        if total < 0:
+            raise RuntimeError(self.err())
+        buf = np.zeros(total, np.uint8)
+        got = self.lib.ref_sml_file_image(s, u64(len(s)), u64(seed), _ptr(buf), u64(total), None)
+        if got != total:
+            raise RuntimeError(self.err())
+        return buf.tobytes(), [int(x) for x in layout]
+
     def sml_time(self, seq, seed):
         s = _as_bytes(seq)
         n = u64()

@@ -1,8 +1,12 @@
 // facade_demo.cpp — the anchoring call sequence of the reference's callers (MatchList::CreateMemorySMLs +
 // MemHash::FindMatches, e.g. ProgressiveAligner.cpp:636-653) written against the façade headers.
-// Usage: facade_demo <memhash|repeat|pairwise|mums> <seed_weight> <raw-sequence-file>...
+// Usage: facade_demo <memhash|repeat|pairwise|mums|smlmemhash> <seed_weight> <raw-sequence-file>...
 //   prints "len\tstart0\tstart1..." lines ("mums": MemHash, then the .mums file WriteList produces, re-read with ReadList)
 //        facade_demo readmums <file.mums>     parses a .mums file and prints its matches
+//        facade_demo writesml <seed_weight> <raw-sequence-file> <out.sml>   DNAFileSML::Create
+//        facade_demo loadsml <file.sml>       DNAFileSML::LoadFile, prints seed, lengths and the first entries
+//        facade_demo smllayout                sizeof / offsets of the façade's SMLHeader
+#include <cstddef>
 #include <fstream>
 #include <iostream>
 #include <iterator>
@@ -14,8 +18,39 @@
 using namespace mems;
 
 int main(int argc, char** argv) {
+	if (argc >= 2 && std::string(argv[1]) == "smllayout") {
+		std::cout << sizeof(SMLHeader) << " " << offsetof(SMLHeader, version) << " " << offsetof(SMLHeader, alphabet_bits) << " "
+		          << offsetof(SMLHeader, seed) << " " << offsetof(SMLHeader, seed_length) << " " << offsetof(SMLHeader, seed_weight)
+		          << " " << offsetof(SMLHeader, length) << " " << offsetof(SMLHeader, unique_mers) << " "
+		          << offsetof(SMLHeader, word_size) << " " << offsetof(SMLHeader, little_endian) << " " << offsetof(SMLHeader, id)
+		          << " " << offsetof(SMLHeader, circular) << " " << offsetof(SMLHeader, translation_table) << " "
+		          << offsetof(SMLHeader, description) << " " << sizeof(smlSeqI_t) << "\n";
+		return 0;
+	}
 	if (argc < 3) return 2;
 	const std::string mode = argv[1];
+	try {
+		if (mode == "writesml") {
+			if (argc < 5) return 2;
+			std::ifstream f(argv[3], std::ios::binary);
+			std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+			genome::gnSequence seq(s);
+			DNAFileSML sml(argv[4]);
+			sml.Create(seq, getSeed((unsigned)atoi(argv[2])));
+			return 0;
+		}
+		if (mode == "loadsml") {
+			DNAFileSML sml;
+			sml.LoadFile(argv[2]);
+			std::cout << std::hex << sml.Seed() << std::dec << " " << sml.Length() << " " << sml.SMLLength();
+			for (uint64_t i = 0; i < 4 && i < sml.SMLLength(); ++i) std::cout << " " << sml[i].position << ":" << sml[i].mer;
+			std::cout << "\n";
+			return 0;
+		}
+	} catch (const MemsException& e) {
+		std::cerr << "error " << e.code << ": " << e.what() << "\n";
+		return 1;
+	}
 	if (mode == "readmums") {
 		std::ifstream f(argv[2]);
 		MatchList ml;
@@ -33,7 +68,12 @@ int main(int argc, char** argv) {
 			ml.seq_table.push_back(new genome::gnSequence(s));
 			ml.seq_filename.push_back(argv[i]);
 		}
-		ml.CreateMemorySMLs(weight, &std::cerr);
+		if (mode == "smlmemhash") {  // on-disk lists next to the sequences (MatchList::LoadSMLs)
+			for (int i = 3; i < argc; ++i) ml.sml_filename.push_back(std::string(argv[i]) + ".sml");
+			ml.LoadSMLs(weight, &std::cerr);
+		} else {
+			ml.CreateMemorySMLs(weight, &std::cerr);
+		}
 		std::cerr << "seed " << std::hex << ml.sml_table[0]->Seed() << std::dec << " length " << ml.sml_table[0]->SeedLength()
 		          << " sml[0] = {" << (*ml.sml_table[0])[0].position << ", " << (*ml.sml_table[0])[0].mer << "}\n";
 		MemHash* mh = mode == "repeat" ? new RepeatHash() : (mode == "pairwise" ? new PairwiseMatchFinder() : new MemHash());

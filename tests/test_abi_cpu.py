@@ -47,3 +47,25 @@ def test_no_cpu_fallback():
     with pytest.raises(mems.MemsError) as e:
         mems.Context(0)
     assert e.value.code == 3  # MEMS_ERR_CUDA
+
+
+def test_sml_header_layout_is_the_reference_s():
+    """The façade's copy of SMLHeader (.sml files, SortedMerList.h:48-63) has the size and field offsets of the
+    reference's struct as compiled against the shim (oracle/_ref), and the image the reference would write for
+    a small sequence has the expected three parts."""
+    import subprocess
+    from checkers import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref not built")
+    demo = os.path.join(ROOT, "build", "facade_demo")
+    if not os.path.exists(demo):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([demo, "smllayout"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    seq = b"ACGTTGCAAGGCTTAACCGGTTAGCATCGATCGGATCCGATTACAGGCAT" * 3
+    image, layout = Reference().sml_file_image(seq, mems.get_seed(11))
+    assert [int(x) for x in r.stdout.split()] == layout[:15]
+    n_words = (len(seq) * 2 + 31) // 32 + 2
+    n_pos = len(seq) - mems.get_seed_length(mems.get_seed(11)) + 1
+    assert len(image) == layout[0] + 4 * n_words + 4 * n_pos

@@ -87,3 +87,78 @@ def test_mums_files_round_trip_through_the_reference(tmp_path):
         v = [int(x) for x in line.split("\t")]
         got.append((len(v) - 1, v[0]) + tuple(v[1:]))
     assert got == want  # their file, our reader
+
+
+def test_sml_file_matches_the_reference_image(tmp_path):
+    """DNAFileSML::Create writes the file FileSML::Create would (FileSML.cpp:344-366): same header fields at the
+    same offsets, same packed words, same positions; only the bytes the reference leaves uninitialised
+    (word_size, little_endian, struct padding) are excluded.  LoadFile reads the reference's image back."""
+    from checkers import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref not built")
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(DEMO):
+        import __graft_entry__
+        __graft_entry__.build()
+    R = Reference()
+    g = synth.genome_family(1, 40_001, seed=35)[0]
+    seed = mems.get_seed(15)
+    want, layout = R.sml_file_image(g, seed)
+    r = subprocess.run([DEMO, "smllayout"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert [int(x) for x in r.stdout.split()] == layout[:15]
+    raw = tmp_path / "g.raw"
+    raw.write_bytes(g.tobytes())
+    out = tmp_path / "g.sml"
+    r = subprocess.run([DEMO, "writesml", "15", str(raw), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = out.read_bytes()
+    assert len(got) == len(want)
+    size, off = layout[0], dict(zip(["version", "alphabet_bits", "seed", "seed_length", "seed_weight", "length", "unique_mers",
+                                     "word_size", "little_endian", "id", "circular", "translation_table", "description"],
+                                    layout[1:14]))
+    defined = [("version", 4), ("alphabet_bits", 4), ("seed", 8), ("seed_length", 4), ("seed_weight", 4), ("length", 8),
+               ("unique_mers", 4), ("id", 2), ("circular", 1), ("translation_table", 255), ("description", 1)]
+    for name, n in defined:
+        assert got[off[name]:off[name] + n] == want[off[name]:off[name] + n], name
+    # packed words are identical; positions list the same mers in the same order (std::sort leaves ties unspecified)
+    n_words = (len(g) * 2 + 31) // 32 + 2
+    assert got[size:size + 4 * n_words] == want[size:size + 4 * n_words]
+    import numpy as np
+    mine = np.frombuffer(got[size + 4 * n_words:], np.uint32)
+    theirs = np.frombuffer(want[size + 4 * n_words:], np.uint32)
+    assert sorted(mine.tolist()) == sorted(theirs.tolist())
+    pos, mers = R.sml_build(g, seed)
+    mer_at = dict(zip(pos.tolist(), mers.tolist()))
+    assert [mer_at[p] for p in mine.tolist()] == [mer_at[p] for p in theirs.tolist()]
+    # the reference's image through our reader
+    ref_file = tmp_path / "ref.sml"
+    ref_file.write_bytes(want)
+    r = subprocess.run([DEMO, "loadsml", str(ref_file)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    f = r.stdout.split()
+    assert int(f[0], 16) == seed and int(f[1]) == len(g) and int(f[2]) == len(pos)
+    assert f[3] == "%d:%d" % (pos[0], mers[0]) or int(f[3].split(":")[1]) == int(mers[0])
+    # a truncated file is rejected like FileSML::LoadFile does
+    bad = tmp_path / "bad.sml"
+    bad.write_bytes(want[:size + 100])
+    r = subprocess.run([DEMO, "loadsml", str(bad)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "sequence data" in r.stderr
+
+
+def test_load_smls_creates_then_reuses_the_files(tmp_path):
+    """MatchList::LoadSMLs (MatchList.h:262-349): the first run creates <seq>.sml, the second loads them."""
+    gs = synth.genome_family(3, 25000, seed=36)
+    want, _ = Oracle().find_matches(0, gs, mems.get_seed(15))
+    got, log = run_demo(tmp_path, "smlmemhash", 15, gs)
+    assert got == want
+    assert log.count("Creating sorted mer list") == 3
+    assert all(os.path.exists(str(tmp_path / ("seq%d.raw.sml" % i))) for i in range(3))
+    got, log = run_demo(tmp_path, "smlmemhash", 15, gs)
+    assert got == want
+    assert log.count("Sorted mer list loaded successfully") == 3 and "Creating" not in log
+    got, log = run_demo(tmp_path, "smlmemhash", 13, gs)  # other weight: seed mismatch, lists are recreated
+    assert got == Oracle().find_matches(0, gs, mems.get_seed(13))[0]
+    assert log.count("Default seed mismatch") == 3
