@@ -72,7 +72,31 @@ struct Comm {
 	cudaStream_t side_stream = nullptr;
 	cudaEvent_t side_ready = nullptr, side_done = nullptr;
 	int rank = 0, world = 1;
+	// exchange windows: device buffers every peer can write straight into over NVLink (CUDA IPC mappings);
+	// the all-to-all steps are plain peer-to-peer copies into them plus one barrier.  Two windows, because a peer
+	// may already be sending hits (window 1) while this rank still reads the seed records it received (window 0).
+	struct Window {
+		void* local = nullptr;
+		size_t bytes = 0;
+		std::vector<void*> peer;  // peer[p] = rank p's window mapped here (peer[rank] = local)
+	};
+	Window win[3];  // 0: seed records, 1: hits, 2: position-ordered keys of all sequences
+	bool windows_ok = true;     // false once IPC mapping failed on any rank: the NCCL send/recv path is used
+	uint32_t* d_barrier = nullptr;
+	void free_window(int w) {
+		Window& x = win[w];
+		for (int p = 0; p < (int)x.peer.size(); ++p)
+			if (p != rank && x.peer[p]) cudaIpcCloseMemHandle(x.peer[p]);
+		x.peer.clear();
+		if (x.local) cudaFree(x.local);
+		x.local = nullptr;
+		x.bytes = 0;
+	}
 	~Comm() {
+		free_window(0);
+		free_window(1);
+		free_window(2);
+		if (d_barrier) cudaFree(d_barrier);
 		if (side_comm) nccl().CommDestroy(side_comm);
 		if (comm) nccl().CommDestroy(comm);
 		if (side_stream) cudaStreamDestroy(side_stream);
@@ -164,6 +188,119 @@ void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts,
 	comm_all_to_all_v_multi(c, 1, &d_send, &d_recv, &elem_bytes, send_counts, recv_counts);
 }
 
+// ---- exchange windows ------------------------------------------------------------------------------
+// Make window w hold at least `bytes` on EVERY rank (all ranks call this with the same value: it is computed
+// from counts every rank already has, so growing needs no negotiation).  Growing is collective: allocate,
+// all-gather the IPC handles through NCCL, map the peers' buffers.  Returns false if the windows cannot be used
+// (IPC refused on some rank); the caller then falls back to NCCL send/recv.
+bool comm_window_reserve(Comm* c, int w, size_t bytes) {
+	if (!c->windows_ok) return false;
+	Comm::Window& x = c->win[w];
+	if (x.local && x.bytes >= bytes) return true;
+	MEMS_CUDA(cudaStreamSynchronize(c->ctx->stream));
+	c->free_window(w);
+	const size_t want = (bytes + bytes / 4 + (1u << 20)) & ~(size_t)0xfffff;  // head room, 1 MiB granules
+	MEMS_CUDA(cudaMalloc(&x.local, want));
+	x.bytes = want;
+	x.peer.assign(c->world, nullptr);
+	x.peer[c->rank] = x.local;
+	if (c->world == 1) return true;
+	if (!c->d_barrier) {
+		MEMS_CUDA(cudaMalloc(&c->d_barrier, 256));
+		MEMS_CUDA(cudaMemset(c->d_barrier, 0, 256));
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+	struct Slot {
+		cudaIpcMemHandle_t h;
+		uint64_t ok;
+	};
+	Slot mine;
+	memset(&mine, 0, sizeof mine);
+	mine.ok = cudaIpcGetMemHandle(&mine.h, x.local) == cudaSuccess ? 1 : 0;
+	if (!mine.ok) cudaGetLastError();
+	DevBuf<uint64_t> d_slots(c->ctx.get(), sizeof(Slot) / 8 * (size_t)(c->world + 1));
+	MEMS_CUDA(cudaMemcpyAsync(d_slots.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->ctx->stream));
+	check(nccl().AllGather(d_slots.p, d_slots.p + sizeof(Slot) / 8, sizeof(Slot) / 8, ncclUint64, c->comm, c->ctx->stream),
+	      "ncclAllGather");
+	std::vector<Slot> all(c->world);
+	MEMS_CUDA(cudaMemcpyAsync(all.data(), d_slots.p + sizeof(Slot) / 8, sizeof(Slot) * c->world, cudaMemcpyDeviceToHost,
+	                          c->ctx->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->ctx->stream));
+	uint64_t ok = 1;
+	for (int p = 0; p < c->world; ++p) ok &= all[p].ok;
+	for (int p = 0; p < c->world && ok; ++p) {
+		if (p == c->rank) continue;
+		if (cudaIpcOpenMemHandle(&x.peer[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			cudaGetLastError();
+			x.peer[p] = nullptr;
+			ok = 0;
+		}
+	}
+	// every rank must take the same path: agree on the outcome
+	DevBuf<uint64_t> d_ok(c->ctx.get(), 1);
+	MEMS_CUDA(cudaMemcpyAsync(d_ok.p, &ok, 8, cudaMemcpyHostToDevice, c->ctx->stream));
+	check(nccl().AllReduce(d_ok.p, d_ok.p, 1, ncclUint64, ncclMin, c->comm, c->ctx->stream), "ncclAllReduce");
+	MEMS_CUDA(cudaMemcpyAsync(&ok, d_ok.p, 8, cudaMemcpyDeviceToHost, c->ctx->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->ctx->stream));
+	if (!ok) {
+		c->free_window(w);
+		c->windows_ok = false;
+		return false;
+	}
+	return true;
+}
+
+void* comm_window_local(Comm* c, int w) { return c->win[w].local; }
+void* comm_window_peer(Comm* c, int w, int p) { return c->win[w].peer[p]; }
+
+// All ranks' writes into the windows that were queued before this call are complete on every rank once the
+// calling stream passes it (a one-word all-reduce: it cannot finish before every rank's stream has reached it).
+void comm_window_barrier(Comm* c) {
+	if (c->world == 1) return;
+	check(nccl().AllReduce(c->d_barrier, c->d_barrier + 8, 1, ncclUint32, ncclSum, c->comm, c->ctx->stream), "ncclAllReduce");
+}
+
+// all-to-all-v into window w: array a of every rank lands in the window region that starts at region_off[a]
+// (the same layout on every rank: regions are sized for the largest receiver), source q's slice at element
+// offset sum_{q' < q} counts[q' * world + p] inside the region of destination p.  counts is the full
+// world x world matrix (row = sender), identical on every rank.  Copies are peer-to-peer DMA over NVLink.
+void comm_window_all_to_all(Comm* c, int w, int n_arrays, const void* const* d_send, const size_t* elem_bytes,
+                            const size_t* region_off, const uint64_t* counts, bool barrier) {
+	const int W = c->world, R = c->rank;
+	for (int a = 0; a < n_arrays; ++a) {
+		const char* s = static_cast<const char*>(d_send[a]);
+		size_t so = 0;
+		for (int p = 0; p < W; ++p) {
+			const uint64_t n = counts[(size_t)R * W + p];
+			uint64_t before = 0;
+			for (int q = 0; q < R; ++q) before += counts[(size_t)q * W + p];
+			if (n) {
+				char* dst = static_cast<char*>(c->win[w].peer[p]) + region_off[a] + before * elem_bytes[a];
+				MEMS_CUDA(cudaMemcpyAsync(dst, s + so, n * elem_bytes[a], cudaMemcpyDefault, c->ctx->stream));
+			}
+			so += n * elem_bytes[a];
+		}
+	}
+	if (barrier) comm_window_barrier(c);
+}
+
+// all-gather into window w: this rank's bytes go to byte offset `offset` of EVERY rank's window (its own included),
+// queued on the side stream behind whatever the main stream holds so far, so the caller carries on at once.
+// comm_all_gather_v_wait() + comm_window_barrier() on the main stream make the gathered data readable.
+void comm_window_all_gather(Comm* c, int w, const void* d_send, size_t bytes, size_t offset) {
+	cudaStream_t stream = c->side_stream ? c->side_stream : c->ctx->stream;
+	if (c->side_stream) {
+		MEMS_CUDA(cudaEventRecord(c->side_ready, c->ctx->stream));
+		MEMS_CUDA(cudaStreamWaitEvent(c->side_stream, c->side_ready, 0));
+	}
+	if (bytes)
+		for (int i = 0; i < c->world; ++i) {
+			const int p = (c->rank + 1 + i) % c->world;  // start with the next rank: the ranks do not all hit rank 0 first
+			MEMS_CUDA(cudaMemcpyAsync(static_cast<char*>(c->win[w].peer[p]) + offset, d_send, bytes, cudaMemcpyDefault, stream));
+		}
+	if (c->side_stream) MEMS_CUDA(cudaEventRecord(c->side_done, c->side_stream));
+}
+
 // all-gather with per-rank byte counts: rank p's bytes land at d_recv + offsets[p] on every rank.
 // With a side communicator the transfer is queued on its own stream (after everything queued on the main stream so
 // far) and the caller continues; comm_all_gather_v_wait() makes the main stream wait for it.
@@ -196,7 +333,7 @@ void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t
 
 // the main stream continues only after the gathered data has arrived (no-op without a side communicator)
 void comm_all_gather_v_wait(Comm* c) {
-	if (c->world > 1 && c->side_comm) MEMS_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->side_done, 0));
+	if (c->world > 1 && c->side_stream) MEMS_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->side_done, 0));
 }
 
 void comm_side_synchronize(Comm* c) {

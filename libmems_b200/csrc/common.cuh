@@ -220,6 +220,14 @@ void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts,
                        size_t elem_bytes);
 void comm_all_to_all_v_multi(Comm* c, int n_arrays, const void* const* d_send, void* const* d_recv, const size_t* elem_bytes,
                              const uint64_t* send_counts, const uint64_t* recv_counts);  // arrays sharing the counts, one group
+// exchange windows (peer-mapped device buffers): reserve is collective and returns false when IPC is unavailable
+bool comm_window_reserve(Comm* c, int w, size_t bytes);
+void* comm_window_local(Comm* c, int w);
+void* comm_window_peer(Comm* c, int w, int p);
+void comm_window_barrier(Comm* c);
+void comm_window_all_gather(Comm* c, int w, const void* d_send, size_t bytes, size_t offset);
+void comm_window_all_to_all(Comm* c, int w, int n_arrays, const void* const* d_send, const size_t* elem_bytes,
+                            const size_t* region_off, const uint64_t* counts, bool barrier);
 void comm_all_gather_v(Comm* c, const void* d_send, void* d_recv, const uint64_t* byte_counts, const uint64_t* byte_offsets);
 void comm_all_gather_v_wait(Comm* c);
 void comm_side_synchronize(Comm* c);

@@ -1854,9 +1854,32 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	if (n_loc)
 		launch_extract(c, local->packed.p, local->d_meta.p, local->meta.data(), count, sd, pos_bits, K == 8, keys_loc.p,
 		               vals_loc.p, hist_top.p, 1, top.shift, top.bits);
-	// ---- position-ordered keys of ALL sequences on every rank (window tests read any sequence): started now on the
+	DevBuf<uint8_t> key_pos_own;  // (declared before the guard: released only after the side stream is done with it)
+	uint8_t* key_pos_all_p = nullptr;
+	struct SideGuard {  // whatever way this function is left, the side stream must be done with keys_loc / key_pos_all
+		Comm* c;
+		~SideGuard() { comm_side_synchronize(c); }
+	} side_guard{comm};
+	// every rank's top-digit histogram to every rank in one all-gather: the sum gives the owners of the key ranges,
+	// row p gives what rank p will send here — no separate all-reduce and no count exchange, one host sync
+	DevBuf<uint32_t> hist_all(c, (size_t)256 * W);
+	comm_all_gather_u64(comm, reinterpret_cast<const uint64_t*>(hist_top.p), reinterpret_cast<uint64_t*>(hist_all.p), 128);
+	std::vector<uint32_t> h_all((size_t)256 * W);
+	MEMS_CUDA(cudaMemcpyAsync(h_all.data(), hist_all.p, h_all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	const uint32_t* h_hist32 = h_all.data() + (size_t)256 * R;
+	uint64_t g_hist[256];
+	for (int b = 0; b < 256; ++b) {
+		g_hist[b] = 0;
+		for (int p = 0; p < W; ++p) g_hist[b] += h_all[(size_t)256 * p + b];
+	}
+	DevBuf<uint64_t> d_u64(c, 256 + (size_t)4 * W * W + 4 * W);
+	// ---- position-ordered keys of ALL sequences on every rank (window tests read any sequence): started on the
 	// side communicator, needed only by the extension at the end
-	DevBuf<uint8_t> key_pos_all(c, s_total * K);
+	// (written straight into every peer's window over NVLink; NCCL all-gather where CUDA IPC is not available).
+	// Only now: a peer may write this rank's window once this rank has left the previous call, and the histogram
+	// all-gather above is the first point that proves it.
+	const bool direct_keys = !getenv("MEMS_NO_PEER_WINDOWS") && comm_window_reserve(comm, 2, s_total * K);
 	{
 		std::vector<uint64_t> bytes(W), offs(W);
 		for (int p = 0; p < W; ++p) {
@@ -1867,24 +1890,16 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 			bytes[p] = cnt * K;
 			offs[p] = (n ? gmeta[f].seed_off : 0) * K;
 		}
-		KernelScope ks(c, "nccl_all_gather_keys", (double)s_total * K);
-		comm_all_gather_v(comm, keys_loc.p, key_pos_all.p, bytes.data(), offs.data());
+		KernelScope ks(c, direct_keys ? "peer_all_gather_keys" : "nccl_all_gather_keys", (double)s_total * K);
+		if (direct_keys) {
+			key_pos_all_p = static_cast<uint8_t*>(comm_window_local(comm, 2));
+			comm_window_all_gather(comm, 2, keys_loc.p, bytes[R], offs[R]);
+		} else {
+			key_pos_own = DevBuf<uint8_t>(c, s_total * K);
+			key_pos_all_p = key_pos_own.p;
+			comm_all_gather_v(comm, keys_loc.p, key_pos_all_p, bytes.data(), offs.data());
+		}
 	}
-	struct SideGuard {  // whatever way this function is left, the side stream must be done with keys_loc / key_pos_all
-		Comm* c;
-		~SideGuard() { comm_side_synchronize(c); }
-	} side_guard{comm};
-	uint32_t h_hist32[256];
-	MEMS_CUDA(cudaMemcpyAsync(h_hist32, hist_top.p, sizeof h_hist32, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
-	uint64_t h_hist[256];
-	for (int b = 0; b < 256; ++b) h_hist[b] = h_hist32[b];
-	DevBuf<uint64_t> d_u64(c, 256 + (size_t)4 * W * W + 4 * W);
-	MEMS_CUDA(cudaMemcpyAsync(d_u64.p, h_hist, sizeof h_hist, cudaMemcpyHostToDevice, c->stream));
-	comm_all_reduce_u64(comm, d_u64.p, 256);
-	uint64_t g_hist[256];
-	MEMS_CUDA(cudaMemcpyAsync(g_hist, d_u64.p, sizeof g_hist, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 
 	mark("pack+extract+histogram");
 	// ---- 2. owners of the key ranges; partition the local records by top digit (stable counting pass)
@@ -1898,30 +1913,61 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		radix_sort_pairs(c, K == 8, kp, vp, n_loc, top, hist_top.p, "shard_partition_pass");
 	}
 	mark("partition pass");
-	// ---- 3. exchange: counts, then the records of every key range to its owner
-	auto exchange_counts = [&](const std::vector<uint64_t>& mine, std::vector<uint64_t>& theirs) {
+	// ---- 3. exchange the records of every key range to its owner (the counts follow from the gathered histograms)
+	std::vector<uint64_t> rec_counts((size_t)W * W, 0);  // [sender][receiver], identical on every rank
+	for (int q = 0; q < W; ++q)
+		for (int b = 0; b < 256; ++b) rec_counts[(size_t)q * W + owner[b]] += h_all[(size_t)256 * q + b];
+	uint64_t max_recv = 0;
+	for (int p = 0; p < W; ++p) {
+		uint64_t n = 0;
+		for (int q = 0; q < W; ++q) n += rec_counts[(size_t)q * W + p];
+		max_recv = std::max(max_recv, n);
+		recv_counts[p] = rec_counts[(size_t)p * W + R];
+	}
+	// k values per rank to every rank; all[(p * k + j) * W + d] = value j of what rank p holds for rank d
+	auto exchange_counts = [&](int k, const std::vector<uint64_t>* mine) {
 		uint64_t* d_send = d_u64.p + 256;
-		uint64_t* d_all = d_send + W;
-		MEMS_CUDA(cudaMemcpyAsync(d_send, mine.data(), W * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-		comm_all_gather_u64(comm, d_send, d_all, W);
-		std::vector<uint64_t> all((size_t)W * W);
+		uint64_t* d_all = d_send + (size_t)k * W;
+		std::vector<uint64_t> flat((size_t)k * W);
+		for (int j = 0; j < k; ++j)
+			for (int p = 0; p < W; ++p) flat[(size_t)j * W + p] = mine[j][p];
+		MEMS_CUDA(cudaMemcpyAsync(d_send, flat.data(), flat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+		comm_all_gather_u64(comm, d_send, d_all, (size_t)k * W);
+		std::vector<uint64_t> all((size_t)k * W * W);
 		MEMS_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
-		for (int p = 0; p < W; ++p) theirs[p] = all[(size_t)p * W + R];  // what rank p sends to me
+		return all;
 	};
-	exchange_counts(send_counts, recv_counts);
+	auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
 	uint64_t n_recv = 0;
 	for (int p = 0; p < W; ++p) n_recv += recv_counts[p];
 	if (n_recv > radix_max_items()) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30-1 seed records on one rank");
-	DevBuf<uint8_t> rk_a(c, n_recv * K), rk_b(c, n_recv * K);
-	DevBuf<uint32_t> rv_a(c, n_recv), rv_b(c, n_recv);
+	// received records: straight into this rank's exchange window (peers write it over NVLink), or — where CUDA IPC
+	// is not available — through NCCL send/recv into ordinary buffers
+	const size_t rec_region[2] = {0, align256(max_recv * K)};
+	const bool direct = !getenv("MEMS_NO_PEER_WINDOWS") && comm_window_reserve(comm, 0, rec_region[1] + align256(max_recv * 4));
+	DevBuf<uint8_t> rk_own, rk_b(c, n_recv * K);
+	DevBuf<uint32_t> rv_own, rv_b(c, n_recv);
+	uint8_t* rk_a_p;
+	uint32_t* rv_a_p;
 	{
-		KernelScope ks(c, "nccl_all_to_all_records", (double)n_loc * (K + 4));
+		KernelScope ks(c, direct ? "peer_all_to_all_records" : "nccl_all_to_all_records", (double)n_loc * (K + 4));
 		const void* snd[2] = {keys_part.p, vals_part.p};
-		void* rcv[2] = {rk_a.p, rv_a.p};
 		const size_t eb[2] = {K, 4};
-		comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, send_counts.data(), recv_counts.data());
+		if (direct) {
+			comm_window_all_to_all(comm, 0, 2, snd, eb, rec_region, rec_counts.data(), true);
+			rk_a_p = static_cast<uint8_t*>(comm_window_local(comm, 0)) + rec_region[0];
+			rv_a_p = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(comm_window_local(comm, 0)) + rec_region[1]);
+		} else {
+			rk_own = DevBuf<uint8_t>(c, n_recv * K);
+			rv_own = DevBuf<uint32_t>(c, n_recv);
+			rk_a_p = rk_own.p;
+			rv_a_p = rv_own.p;
+			void* rcv[2] = {rk_a_p, rv_a_p};
+			comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, send_counts.data(), recv_counts.data());
+		}
 	}
+	if (direct) MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers are released below; the copies read them
 	keys_part.reset();
 	vals_part.reset();
 	vals_loc.reset();
@@ -1930,14 +1976,14 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	MEMS_CUDA(cudaMemcpyAsync(d_gmeta.p, gmeta.data(), sizeof(SeqMeta) * n_seqs, cudaMemcpyHostToDevice, c->stream));
 
 	// ---- 5. sort the received range; hits of this rank's seed range
-	const void* u_keys = rk_a.p;
-	const uint32_t* u_vals = rv_a.p;
+	const void* u_keys = rk_a_p;
+	const uint32_t* u_vals = rv_a_p;
 	if (n_recv) {
 		SortPlan plan = make_sort_plan(sd.key_bits);
 		DevBuf<uint32_t> hist(c, (size_t)plan.n_passes * 256);
-		launch_histogram(c, K == 8, rk_a.p, n_recv, plan, hist.p);
-		void* kp[2] = {rk_a.p, rk_b.p};
-		uint32_t* vp[2] = {rv_a.p, rv_b.p};
+		launch_histogram(c, K == 8, rk_a_p, n_recv, plan, hist.p);
+		void* kp[2] = {rk_a_p, rk_b.p};
+		uint32_t* vp[2] = {rv_a_p, rv_b.p};
 		const int r = radix_sort_pairs(c, K == 8, kp, vp, n_recv, plan, hist.p, "radix_pass");
 		u_keys = kp[r];
 		u_vals = vp[r];
@@ -2017,28 +2063,71 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		hs[d] = h_bound[d + 1] - h_bound[d];
 		ms[d] = h_mbound[d + 1] - h_mbound[d];
 	}
-	exchange_counts(hs, hr);
-	exchange_counts(ms, mr);
-	uint64_t n2 = 0, n_mem2 = 0;
+	std::vector<uint64_t> hit_counts((size_t)W * W), mem_counts((size_t)W * W);
+	{
+		const std::vector<uint64_t> mine[2] = {hs, ms};
+		const std::vector<uint64_t> all = exchange_counts(2, mine);  // hit and member counts in one round
+		for (int p = 0; p < W; ++p)
+			for (int d = 0; d < W; ++d) {
+				hit_counts[(size_t)p * W + d] = all[((size_t)p * 2 + 0) * W + d];
+				mem_counts[(size_t)p * W + d] = all[((size_t)p * 2 + 1) * W + d];
+			}
+	}
+	uint64_t n2 = 0, n_mem2 = 0, max_n2 = 0, max_mem2 = 0;
+	for (int d = 0; d < W; ++d) {
+		uint64_t a = 0, b = 0;
+		for (int p = 0; p < W; ++p) {
+			a += hit_counts[(size_t)p * W + d];
+			b += mem_counts[(size_t)p * W + d];
+		}
+		max_n2 = std::max(max_n2, a);
+		max_mem2 = std::max(max_mem2, b);
+	}
 	for (int p = 0; p < W; ++p) {
+		hr[p] = hit_counts[(size_t)p * W + R];
+		mr[p] = mem_counts[(size_t)p * W + R];
 		n2 += hr[p];
 		n_mem2 += mr[p];
 	}
 	if (n_mem2 >= (1ull << 31)) throw Error(MEMS_ERR_UNSUPPORTED, "too many hit members on one rank");
-	DevBuf<uint32_t> r_len(c, n2), r_mval(c, n_mem2);
-	DevBuf<uint8_t> r_mstr(c, n_mem2);
+	const size_t hit_region[3] = {0, align256(max_n2 * 4), align256(max_n2 * 4) + align256(max_mem2 * 4)};
+	const bool direct_hits = direct && comm_window_reserve(comm, 1, hit_region[2] + align256(max_mem2));
+	DevBuf<uint32_t> r_len_own, r_mval_own;
+	DevBuf<uint8_t> r_mstr_own;
+	uint32_t *r_len_p, *r_mval_p;
+	uint8_t* r_mstr_p;
 	{
-		KernelScope ks(c, "nccl_all_to_all_hits", (double)n1 * 4 + (double)n_mem1 * 5);
-		comm_all_to_all_v(comm, slen.p, hs.data(), r_len.p, hr.data(), 4);
-		const void* snd[2] = {s_mval.p, s_mstr.p};
-		void* rcv[2] = {r_mval.p, r_mstr.p};
-		const size_t eb[2] = {4, 1};
-		comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, ms.data(), mr.data());
+		KernelScope ks(c, direct_hits ? "peer_all_to_all_hits" : "nccl_all_to_all_hits", (double)n1 * 4 + (double)n_mem1 * 5);
+		if (direct_hits) {
+			uint8_t* base = static_cast<uint8_t*>(comm_window_local(comm, 1));
+			r_len_p = reinterpret_cast<uint32_t*>(base + hit_region[0]);
+			r_mval_p = reinterpret_cast<uint32_t*>(base + hit_region[1]);
+			r_mstr_p = base + hit_region[2];
+			const void* s1[1] = {slen.p};
+			const size_t e1[1] = {4};
+			comm_window_all_to_all(comm, 1, 1, s1, e1, hit_region, hit_counts.data(), false);
+			const void* s2[2] = {s_mval.p, s_mstr.p};
+			const size_t e2[2] = {4, 1};
+			comm_window_all_to_all(comm, 1, 2, s2, e2, hit_region + 1, mem_counts.data(), true);
+		} else {
+			r_len_own = DevBuf<uint32_t>(c, n2);
+			r_mval_own = DevBuf<uint32_t>(c, n_mem2);
+			r_mstr_own = DevBuf<uint8_t>(c, n_mem2);
+			r_len_p = r_len_own.p;
+			r_mval_p = r_mval_own.p;
+			r_mstr_p = r_mstr_own.p;
+			comm_all_to_all_v(comm, slen.p, hs.data(), r_len_p, hr.data(), 4);
+			const void* snd[2] = {s_mval.p, s_mstr.p};
+			void* rcv[2] = {r_mval_p, r_mstr_p};
+			const size_t eb[2] = {4, 1};
+			comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, ms.data(), mr.data());
+		}
 	}
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers below go out of scope
 	mark("all-to-all hits");
 	// ---- 7. this rank's diagonals: segments, walks, components
 	comm_all_gather_v_wait(comm);  // the gathered keys are needed from here on
+	if (direct_keys) comm_window_barrier(comm);  // ... on every rank: the peers' copies into this rank's window are done
 	out.n_hits = n2;
 	if (n2 == 0) return;
 	HitSet hits2;
@@ -2046,19 +2135,19 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	hits2.start = DevBuf<uint32_t>(c, n2);
 	hits2.len = DevBuf<uint16_t>(c, n2);
 	DevBuf<KeyT> keys2(c, n_mem2);
-	exclusive_scan_u32(c, r_len.p, hits2.start.p, n2, nullptr);
+	exclusive_scan_u32(c, r_len_p, hits2.start.p, n2, nullptr);
 	{
 		KernelScope ks(c, "shard_hits");
 		const uint32_t nmax = (uint32_t)std::max<uint64_t>(n2, n_mem2);
-		received_hits_kernel<KeyT><<<(nmax + 255) / 256, 256, 0, c->stream>>>(r_len.p, r_mstr.p, (uint32_t)n2, (uint32_t)n_mem2,
+		received_hits_kernel<KeyT><<<(nmax + 255) / 256, 256, 0, c->stream>>>(r_len_p, r_mstr_p, (uint32_t)n2, (uint32_t)n_mem2,
 		                                                                        hits2.len.p, keys2.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	MatchArgs a2 = a1;
 	a2.keys = keys2.p;
-	a2.vals = r_mval.p;
+	a2.vals = r_mval_p;
 	a2.n = (uint32_t)n_mem2;
-	extend_hits<KeyT>(ctx, a2, reinterpret_cast<const KeyT*>(key_pos_all.p), sd.L, hits2, order, 40000u, out);
+	extend_hits<KeyT>(ctx, a2, reinterpret_cast<const KeyT*>(key_pos_all_p), sd.L, hits2, order, 40000u, out);
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 	mark("extend + emit + D2H");
 }
