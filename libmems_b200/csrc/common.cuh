@@ -164,7 +164,11 @@ size_t radix_max_items();  // largest n one sort call accepts
 // Returns 0 or 1: the index of the buffer pair that holds the sorted result.  If first_keys_in is given, the
 // first pass reads its keys from there (and leaves that array untouched) instead of d_keys[0].
 int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], uint64_t n, const SortPlan& plan,
-                     uint32_t* d_hist, const char* prof_name, const void* first_keys_in = nullptr);
+                     uint32_t* d_hist, const char* prof_name, const void* first_keys_in = nullptr,
+                     const uint64_t* d_key_dst = nullptr, const uint64_t* d_val_dst = nullptr);
+// d_key_dst / d_val_dst (optional, single-pass plans only): 256 byte addresses, one per digit; digit d's run is
+// written to address[d] + g * element size (g = index in the partitioned order) instead of the second buffers —
+// the addresses may lie in other GPUs' memory (exchange windows), which makes the pass the send side of an all-to-all
 // standalone digit histograms of a key array (for inputs not produced by launch_extract)
 void launch_histogram(Ctx* c, bool key64, const void* d_keys, uint64_t n, const SortPlan& plan, uint32_t* d_hist);
 // exclusive prefix sum of n u32 values (in -> out, may alias); *d_total (optional, device) gets the sum

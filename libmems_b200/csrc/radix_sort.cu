@@ -103,13 +103,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // so the reorder step is one LDS + add per item; values never pass through registers (cp.async straight into
 // their reordered shared-memory slot); the tile's partial counts are published before the reorder and the
 // look-back runs after it, so predecessors have usually finished by the time they are polled.
-template <class KeyT, int THREADS, bool FULL, int NBITS, int kLookBack>
+template <class KeyT, int THREADS, bool FULL, int NBITS, int kLookBack, bool PEER>
 __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_valid,
                                               uint32_t tile, int shift, uint32_t digit_mask,
                                               const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, KeyT* s_keys,
                                               uint32_t* s_vals, uint16_t (*s_warp_cnt)[kRadix], uint32_t* s_global_base,
-                                              uint32_t* s_warp_tot) {
+                                              uint32_t* s_warp_tot, const uint64_t* __restrict__ key_dst,
+                                              const uint64_t* __restrict__ val_dst, uint64_t* s_kaddr, uint64_t* s_vaddr) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int ITEMS = kTile / THREADS;
 	static_assert(THREADS >= kRadix, "thread d < 256 owns digit d");
@@ -211,7 +212,12 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
 			}
 			st_status(my_status, (excl + count) | kFlagInclusive);
 		}
-		s_global_base[tid] = bin_base[tid] + excl - digit_excl;  // + tile-local sorted index = global index
+		const uint32_t gbase = bin_base[tid] + excl - digit_excl;  // + tile-local sorted index = global index
+		s_global_base[tid] = gbase;
+		if (PEER) {  // every digit has its own destination array (a peer's exchange window): byte address of index gbase
+			s_kaddr[tid] = key_dst[tid] + (uint64_t)gbase * sizeof(KeyT);
+			s_vaddr[tid] = val_dst[tid] + (uint64_t)gbase * sizeof(uint32_t);
+		}
 	}
 	cp_async_wait_all();
 	__syncthreads();
@@ -221,18 +227,27 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
 		if (FULL || idx < n_valid) {
 			const KeyT kk = s_keys[idx];
 			const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
-			const uint32_t g = s_global_base[d] + idx;
-			keys_out[g] = kk;
-			vals_out[g] = s_vals[idx];
+			if (PEER) {
+				*reinterpret_cast<KeyT*>(s_kaddr[d] + (uint64_t)idx * sizeof(KeyT)) = kk;
+				*reinterpret_cast<uint32_t*>(s_vaddr[d] + (uint64_t)idx * sizeof(uint32_t)) = s_vals[idx];
+			} else {
+				const uint32_t g = s_global_base[d] + idx;
+				keys_out[g] = kk;
+				vals_out[g] = s_vals[idx];
+			}
 		}
 	}
 }
 
-template <class KeyT, int THREADS, int MINB, int NBITS, int LB = 8>
+// PEER: the pass is also the send side of an all-to-all — digit d's run is written to key_dst[d] / val_dst[d]
+// (byte addresses such that index g of this rank's partitioned order lands at address + g * element size), which
+// point into the exchange windows of the ranks that own the digits: the scatter goes straight over NVLink.
+template <class KeyT, int THREADS, int MINB, int NBITS, int LB = 8, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t digit_mask,
-                const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+                const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                const uint64_t* __restrict__ key_dst, const uint64_t* __restrict__ val_dst) {
 	constexpr int WARPS = THREADS / 32;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
@@ -241,6 +256,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 	__shared__ uint32_t s_global_base[kRadix];
 	__shared__ uint32_t s_warp_tot[kRadix / 32];
 	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_kaddr[PEER ? kRadix : 1], s_vaddr[PEER ? kRadix : 1];
 
 	const int tid = threadIdx.x;
 	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -253,11 +269,13 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 	const uint32_t tile_base = tile * (uint32_t)kTile;
 	const uint32_t n_valid = n - tile_base < (uint32_t)kTile ? n - tile_base : (uint32_t)kTile;
 	if (n_valid == (uint32_t)kTile)
-		onesweep_tile<KeyT, THREADS, true, NBITS, LB>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask, bin_base,
-		                                          status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot);
+		onesweep_tile<KeyT, THREADS, true, NBITS, LB, PEER>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask,
+		                                                bin_base, status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot,
+		                                                key_dst, val_dst, s_kaddr, s_vaddr);
 	else
-		onesweep_tile<KeyT, THREADS, false, NBITS, LB>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask,
-		                                           bin_base, status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot);
+		onesweep_tile<KeyT, THREADS, false, NBITS, LB, PEER>(keys_in, vals_in, keys_out, vals_out, n_valid, tile, shift, digit_mask,
+		                                                 bin_base, status, s_keys, s_vals, s_warp_cnt, s_global_base, s_warp_tot,
+		                                                 key_dst, val_dst, s_kaddr, s_vaddr);
 }
 
 // exclusive scan of each pass's 256 digit counts -> first output index of each digit
@@ -280,12 +298,13 @@ __global__ void scan_bins_kernel(const uint32_t* __restrict__ hist, uint32_t* __
 
 template <class K>
 static const K* first_arg_of(void (*)(const K*, const uint32_t*, K*, uint32_t*, uint32_t, int, uint32_t, const uint32_t*, uint32_t*,
-                                      uint32_t*)) {
+                                      uint32_t*, const uint64_t*, const uint64_t*)) {
 	return nullptr;
 }
 
 int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], uint64_t n, const SortPlan& plan,
-                     uint32_t* d_hist, const char* prof_name, const void* first_keys_in) {
+                     uint32_t* d_hist, const char* prof_name, const void* first_keys_in, const uint64_t* d_key_dst,
+                     const uint64_t* d_val_dst) {
 	if (n == 0) return 0;
 	if (n > radix_max_items()) throw Error(4, "radix sort: more than 2^30-1 items in one device sort");
 	const uint32_t n_tiles = (uint32_t)((n + kTile - 1) / kTile);
@@ -311,25 +330,22 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 		using K = std::remove_const_t<std::remove_pointer_t<decltype(first_arg_of(kern))>>;
 		kern<<<n_tiles, threads, smem, c->stream>>>((const K*)(q == 0 && first_keys_in ? first_keys_in : d_keys[cur]), d_vals[cur],
 		                                            (K*)d_keys[cur ^ 1], d_vals[cur ^ 1], (uint32_t)n, plan.shift[q], mask,
-		                                            bin_base.p + q * kRadix, st, ticket);
+		                                            bin_base.p + q * kRadix, st, ticket, d_key_dst, d_val_dst);
 		MEMS_CUDA(cudaGetLastError());
 	};
 	int cur = 0;
 	for (int q = 0; q < P; ++q) {
 		KernelScope ks(c, prof_name, 2.0 * (double)n * (double)(key_bytes + 4));
 		const bool eight = plan.bits[q] > 7;
-		static int variant = -1;
-		if (variant < 0) {
-			const char* e = getenv("MEMS_SORT_VARIANT");
-			variant = e ? atoi(e) : 0;
-		}
-		if (variant == 1 && !key64) launch(onesweep_kernel<uint32_t, 512, 4, 8, 8>, 512, q, cur);
-		else if (variant == 2 && !key64) launch(onesweep_kernel<uint32_t, 512, 3, 8, 8>, 512, q, cur);
-		else if (variant == 3 && !key64) launch(onesweep_kernel<uint32_t, 256, 5, 8, 16>, 256, q, cur);
-		else if (variant == 4 && !key64) launch(onesweep_kernel<uint32_t, 256, 5, 8, 32>, 256, q, cur);
-		else if (variant == 5 && !key64) launch(onesweep_kernel<uint32_t, 256, 4, 8, 8>, 256, q, cur);
-		else if (variant == 6 && !key64) launch(onesweep_kernel<uint32_t, 512, 4, 8, 32>, 512, q, cur);
-		else if (key64) {
+		if (d_key_dst) {  // single-pass partition whose output goes to the peers' exchange windows
+			if (key64) {
+				if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8, 8, true>, 256, q, cur);
+				else launch(onesweep_kernel<uint64_t, 256, kMinB64, 7, 8, true>, 256, q, cur);
+			} else {
+				if (eight) launch(onesweep_kernel<uint32_t, 256, kMinB32, 8, 8, true>, 256, q, cur);
+				else launch(onesweep_kernel<uint32_t, 256, kMinB32, 7, 8, true>, 256, q, cur);
+			}
+		} else if (key64) {
 			if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8>, 256, q, cur);
 			else launch(onesweep_kernel<uint64_t, 256, kMinB64, 7>, 256, q, cur);
 		} else {

@@ -26,32 +26,36 @@ def main():
     length = int(sys.argv[2]) if len(sys.argv) > 2 else 60_000
     weight = int(sys.argv[3]) if len(sys.argv) > 3 else 15
     seed = mems.get_seed(weight)
-    gs = synth.genome_family(n_genomes, length, seed=11)
     ctx = mems.Context(local)
     uid = [mems.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     comm = ctx.create_comm(uid[0], rank, world)
-    first, count = mems.shard_sequence_range(n_genomes, rank, world)
-    seqs = [g if first <= i < first + count else None for i, g in enumerate(gs)]
-    flat, info = ctx.find_matches_sharded(comm, seqs, [len(g) for g in gs], seed, order=mems.ORDER_CANONICAL)
-    mine = mems.flat_to_matches(flat)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (mine, info["n_hits"]))
-    if rank == 0:
-        union = [m for part, _ in gathered for m in part]
-        assert len(union) == len(set(union)), "ranks returned overlapping matches"
-        hits = sum(h for _, h in gathered)
-        if length <= 400_000:
-            from checkers import Oracle
-            want, winfo = Oracle().find_matches(0, gs, seed)
-            assert sorted(union) == sorted(set(want)), "sharded MatchList differs from the oracle"
-            assert hits == winfo["hits"]
-        smls = ctx.create_smls(gs, seed)
-        single, sinfo = ctx.find_matches(smls, order=mems.ORDER_CANONICAL)
-        assert sorted(union) == mems.flat_to_matches(single), "sharded MatchList differs from the single-GPU one"
-        assert hits == sinfo["n_hits"]
-        print("sharded ok: world=%d genomes=%d x %d matches=%d hits=%d per-rank matches=%s" %
-              (world, n_genomes, length, len(union), hits, [len(p) for p, _ in gathered]))
+    # several calls on one communicator: the exchange windows are reused, grown (second call is larger) and reused again
+    for call, (n_len, g_seed) in enumerate([(length, 11), (length * 2, 12), (length, 13)]):
+        gs = synth.genome_family(n_genomes, n_len, seed=g_seed)
+        first, count = mems.shard_sequence_range(n_genomes, rank, world)
+        seqs = [g if first <= i < first + count else None for i, g in enumerate(gs)]
+        flat, info = ctx.find_matches_sharded(comm, seqs, [len(g) for g in gs], seed, order=mems.ORDER_CANONICAL)
+        mine = mems.flat_to_matches(flat)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, info["n_hits"]))
+        if rank == 0:
+            union = [m for part, _ in gathered for m in part]
+            assert len(union) == len(set(union)), "ranks returned overlapping matches"
+            hits = sum(h for _, h in gathered)
+            if n_len <= 400_000:
+                from checkers import Oracle
+                want, winfo = Oracle().find_matches(0, gs, seed)
+                assert sorted(union) == sorted(set(want)), "sharded MatchList differs from the oracle"
+                assert hits == winfo["hits"]
+            smls = ctx.create_smls(gs, seed)
+            single, sinfo = ctx.find_matches(smls, order=mems.ORDER_CANONICAL)
+            for sml in smls:
+                sml.close()
+            assert sorted(union) == mems.flat_to_matches(single), "sharded MatchList differs from the single-GPU one"
+            assert hits == sinfo["n_hits"]
+            print("sharded ok: call=%d world=%d genomes=%d x %d matches=%d hits=%d per-rank matches=%s" %
+                  (call, world, n_genomes, n_len, len(union), hits, [len(p) for p, _ in gathered]))
     dist.barrier()
     comm.close()
     ctx.close()

@@ -30,13 +30,23 @@ def test_world_of_one_equals_oracle():
     ctx.close()
 
 
-def test_two_ranks_under_torchrun():
+@pytest.mark.parametrize("transport", ["peer_copy", "peer_scatter", "nccl"])
+def test_two_ranks_under_torchrun(transport):
+    """Two ranks, every way the exchanges can travel: DMA copies into the peers' exchange windows (default), the
+    partition kernel scattering straight into them (MEMS_PEER_SCATTER), NCCL send/recv (MEMS_NO_PEER_WINDOWS)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ)
+    env.pop("MEMS_PEER_SCATTER", None)
+    env.pop("MEMS_NO_PEER_WINDOWS", None)
+    if transport == "peer_scatter":
+        env["MEMS_PEER_SCATTER"] = "1"
+    elif transport == "nccl":
+        env["MEMS_NO_PEER_WINDOWS"] = "1"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(ROOT, "tests", "sharded_worker.py"), "5", "60000", "15"],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "sharded ok" in r.stdout
