@@ -242,7 +242,7 @@ __device__ __forceinline__ void onesweep_tile(const KeyT* __restrict__ keys_in, 
 // PEER: the pass is also the send side of an all-to-all — digit d's run is written to key_dst[d] / val_dst[d]
 // (byte addresses such that index g of this rank's partitioned order lands at address + g * element size), which
 // point into the exchange windows of the ranks that own the digits: the scatter goes straight over NVLink.
-template <class KeyT, int THREADS, int MINB, int NBITS, int LB = 8, bool PEER = false>
+template <class KeyT, int THREADS, int MINB, int NBITS, int LB = 4, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t digit_mask,
@@ -339,11 +339,11 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 		const bool eight = plan.bits[q] > 7;
 		if (d_key_dst) {  // single-pass partition whose output goes to the peers' exchange windows
 			if (key64) {
-				if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8, 8, true>, 256, q, cur);
-				else launch(onesweep_kernel<uint64_t, 256, kMinB64, 7, 8, true>, 256, q, cur);
+				if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8, 4, true>, 256, q, cur);
+				else launch(onesweep_kernel<uint64_t, 256, kMinB64, 7, 4, true>, 256, q, cur);
 			} else {
-				if (eight) launch(onesweep_kernel<uint32_t, 256, kMinB32, 8, 8, true>, 256, q, cur);
-				else launch(onesweep_kernel<uint32_t, 256, kMinB32, 7, 8, true>, 256, q, cur);
+				if (eight) launch(onesweep_kernel<uint32_t, 256, kMinB32, 8, 4, true>, 256, q, cur);
+				else launch(onesweep_kernel<uint32_t, 256, kMinB32, 7, 4, true>, 256, q, cur);
 			}
 		} else if (key64) {
 			if (eight) launch(onesweep_kernel<uint64_t, 256, kMinB64, 8>, 256, q, cur);
