@@ -266,20 +266,32 @@ template <class KeyT>
 struct MemberIter {
 	const MatchArgs& a;
 	uint32_t i0, m, i1, e;
+	uint32_t v0, v1;  // heads of the two sublists (valid while i0 < m / i1 < e)
 	__device__ MemberIter(const MatchArgs& args, uint32_t s, uint32_t len) : a(args), i0(s), e(s + len) {
-		m = s;
-		while (m < e && strand_of<KeyT>(a.keys, m) == 0) ++m;
+		// first strand-1 entry: eight independent loads at a time instead of a chain of dependent ones
+		m = e;
+		for (uint32_t base = s; base < e && m == e; base += 8) {
+			uint32_t mask = 0;
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+				if (base + j < e) mask |= strand_of<KeyT>(a.keys, base + j) << j;
+			if (mask) m = base + (uint32_t)__ffs((int)mask) - 1u;
+		}
 		i1 = m;
+		v0 = i0 < m ? a.vals[i0] : 0u;
+		v1 = i1 < e ? a.vals[i1] : 0u;
 	}
 	__device__ bool next(uint32_t& val, uint32_t& strand) {
 		if (i0 >= m && i1 >= e) return false;
-		bool take0 = i1 >= e || (i0 < m && a.vals[i0] < a.vals[i1]);
+		const bool take0 = i1 >= e || (i0 < m && v0 < v1);
 		if (take0) {
-			val = a.vals[i0++];
+			val = v0;
 			strand = 0;
+			if (++i0 < m) v0 = a.vals[i0];
 		} else {
-			val = a.vals[i1++];
+			val = v1;
 			strand = 1;
+			if (++i1 < e) v1 = a.vals[i1];
 		}
 		return true;
 	}
