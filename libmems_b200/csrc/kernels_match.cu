@@ -30,6 +30,9 @@
 // merge decision compares the full member lists.
 #include <algorithm>
 #include <chrono>
+#include <exception>
+#include <functional>
+#include <thread>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -1567,6 +1570,16 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	}
 
 	// ---- ORDER_REFERENCE: replay the reference's hash table over (hit, extended match) on the host
+	const bool trace = getenv("MEMS_TRACE") != nullptr;
+	auto t_mark = std::chrono::steady_clock::now();
+	auto mark = [&](const char* what) {
+		if (!trace) return;
+		cudaStreamSynchronize(c->stream);
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[mems trace] replay %-24s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+		t_mark = now;
+	};
+	mark("device stages + records");
 	DevBuf<uint32_t> rec_of_hit(c, n_hits), len32(c, n_hits), mem_off(c, n_hits);
 	{
 		KernelScope ks(c, "hit_record");
@@ -1594,6 +1607,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	MEMS_CUDA(cudaMemcpyAsync(h_strand.data(), mem_strand.p, (size_t)n_mem, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 
+	mark("members to host");
 	// emitted records in component order: record r starts at raw[rec_start[r]]
 	std::vector<size_t> rec_start;
 	for (size_t i = 0; i < n_flat; i += (size_t)raw[i] + 2) rec_start.push_back(i);
@@ -1608,10 +1622,12 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	table_size = T.size;
 	std::vector<std::vector<Entry*>>& table = T.buckets;
 	std::vector<std::unique_ptr<Entry>>& stored = T.stored;
-	std::vector<int64_t> probe_start;
-	for (uint32_t h = 0; h < n_hits; ++h) {
+	// A hit only ever touches the bucket its generalized offset selects, so the table is replayed bucket by bucket:
+	// hits are grouped by bucket in their original order (stable counting sort) and disjoint bucket ranges go to
+	// separate host threads.  The order of operations inside every bucket — all that the reference's result depends
+	// on — is unchanged.
+	auto build_probe = [&](uint32_t h, Entry& probe, std::vector<int64_t>& probe_start) {
 		const uint32_t m0 = h_off[h], m1 = h + 1 < n_hits ? h_off[h + 1] : n_mem;
-		Entry probe;
 		probe.seqcount = mode == MEMS_MODE_REPEAT ? (m1 - m0) : (uint32_t)a.n_seqs;
 		probe.len = L;
 		probe.mersize = L;
@@ -1624,30 +1640,104 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 		}
 		probe.start = probe_start.data();
 		e_calc_offset(probe);
-		const int64_t ts = (int64_t)table_size;
-		std::vector<Entry*>& bucket = table[(size_t)(((probe.offset % ts) + ts) % ts)];
-		size_t at = bucket_lower_bound(bucket, probe);
-		if (at != bucket.size() && !e_compare(*bucket[at], probe) && !e_compare(probe, *bucket[at])) {
-			++T.collisions;
-			continue;
+	};
+	const int64_t ts = (int64_t)table_size;
+	unsigned n_threads = 1;
+	if (n_hits >= 20000) {
+		n_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		if (const char* e = getenv("MEMS_HOST_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
+	}
+	auto run_parallel = [&](const std::function<void(unsigned)>& body) {
+		if (n_threads == 1) {
+			body(0);
+			return;
 		}
-		// "ExtendMatch": the extended form of this hit is the component the device computed for it
-		const int64_t* rec = raw + rec_start[h_rec[h]];
-		auto e = std::make_unique<Entry>();
-		e->seqcount = (uint32_t)rec[0];
-		e->len = rec[1];
-		e->mersize = 0;  // stored copies lose m_mersize (MatchHashEntry.cpp:118-126)
-		e->own.assign(rec + 2, rec + 2 + rec[0]);
-		e->start = e->own.data();
-		e_calc_offset(*e);
-		at = bucket_lower_bound(bucket, *e);
-		bucket.insert(bucket.begin() + at, e.get());
-		stored.push_back(std::move(e));
-		++T.mem_count;
+		std::vector<std::thread> pool;
+		std::vector<std::exception_ptr> errs(n_threads);
+		for (unsigned t = 0; t < n_threads; ++t)
+			pool.emplace_back([&, t] {
+				try {
+					body(t);
+				} catch (...) {
+					errs[t] = std::current_exception();
+				}
+			});
+		for (auto& th : pool) th.join();
+		for (auto& e : errs)
+			if (e) std::rethrow_exception(e);
+	};
+	// 1. bucket of every hit
+	std::vector<uint32_t> bucket_of(n_hits);
+	run_parallel([&](unsigned t) {
+		const uint32_t lo = (uint32_t)((uint64_t)n_hits * t / n_threads), hi = (uint32_t)((uint64_t)n_hits * (t + 1) / n_threads);
+		Entry probe;
+		std::vector<int64_t> probe_start;
+		for (uint32_t h = lo; h < hi; ++h) {
+			build_probe(h, probe, probe_start);
+			bucket_of[h] = (uint32_t)(((probe.offset % ts) + ts) % ts);
+		}
+	});
+	// 2. hits grouped by bucket, original order kept inside a bucket
+	std::vector<uint32_t> bucket_first(table_size + 1, 0), by_bucket(n_hits);
+	for (uint32_t h = 0; h < n_hits; ++h) ++bucket_first[bucket_of[h] + 1];
+	for (uint32_t bkt = 0; bkt < table_size; ++bkt) bucket_first[bkt + 1] += bucket_first[bkt];
+	{
+		std::vector<uint32_t> at(bucket_first.begin(), bucket_first.end() - 1);
+		for (uint32_t h = 0; h < n_hits; ++h) by_bucket[at[bucket_of[h]]++] = h;
+	}
+	// 3. bucket ranges holding about the same number of hits each
+	std::vector<uint32_t> range(n_threads + 1, table_size);
+	range[0] = 0;
+	for (unsigned t = 1; t < n_threads; ++t) {
+		const uint32_t want = (uint32_t)((uint64_t)n_hits * t / n_threads);
+		range[t] = (uint32_t)(std::lower_bound(bucket_first.begin(), bucket_first.end(), want) - bucket_first.begin());
+		if (range[t] > table_size) range[t] = table_size;
+		if (range[t] < range[t - 1]) range[t] = range[t - 1];
+	}
+	std::vector<std::vector<std::unique_ptr<Entry>>> stored_by(n_threads);
+	std::vector<uint64_t> collisions_by(n_threads, 0);
+	run_parallel([&](unsigned t) {
+		Entry probe;
+		std::vector<int64_t> probe_start;
+		for (uint32_t bkt = range[t]; bkt < range[t + 1]; ++bkt) {
+			std::vector<Entry*>& bucket = table[bkt];
+			for (uint32_t k = bucket_first[bkt]; k < bucket_first[bkt + 1]; ++k) {
+				const uint32_t h = by_bucket[k];
+				build_probe(h, probe, probe_start);
+				size_t at = bucket_lower_bound(bucket, probe);
+				if (at != bucket.size() && !e_compare(*bucket[at], probe) && !e_compare(probe, *bucket[at])) {
+					++collisions_by[t];
+					continue;
+				}
+				// "ExtendMatch": the extended form of this hit is the component the device computed for it
+				const int64_t* rec = raw + rec_start[h_rec[h]];
+				auto e = std::make_unique<Entry>();
+				e->seqcount = (uint32_t)rec[0];
+				e->len = rec[1];
+				e->mersize = 0;  // stored copies lose m_mersize (MatchHashEntry.cpp:118-126)
+				e->own.assign(rec + 2, rec + 2 + rec[0]);
+				e->start = e->own.data();
+				e_calc_offset(*e);
+				at = bucket_lower_bound(bucket, *e);
+				bucket.insert(bucket.begin() + at, e.get());
+				stored_by[t].push_back(std::move(e));
+			}
+		}
+	});
+	for (unsigned t = 0; t < n_threads; ++t) {
+		T.collisions += collisions_by[t];
+		T.mem_count += stored_by[t].size();
+		for (auto& e : stored_by[t]) stored.push_back(std::move(e));
 	}
 	out.mem_count = T.mem_count;
 	out.collisions = T.collisions;
+	mark("table replay");
 	// MemHash::GetMatchList (MemHash.h:183-203): buckets in order, front to back
+	{
+		size_t total = 0;
+		for (auto& e : stored) total += (size_t)e->seqcount + 2;
+		out.flat.vec.reserve(total);
+	}
 	for (auto& bucket : table)
 		for (Entry* e : bucket) {
 			out.flat.vec.push_back(e->seqcount);
@@ -1656,6 +1746,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 		}
 	out.flat.release();
 	out.n_matches = stored.size();
+	mark("output list");
 }
 
 static void emit_table(const HashTable& T, MatchResult& out) {
