@@ -83,6 +83,22 @@ struct Comm {
 	Window win[3];  // 0: seed records, 1: hits, 2: position-ordered keys of all sequences
 	bool windows_ok = true;     // false once IPC mapping failed on any rank: the NCCL send/recv path is used
 	uint32_t* d_barrier = nullptr;
+	// one copy stream per peer: the DMA copies of an exchange run side by side over the NVLink ports instead of
+	// one peer after the other
+	std::vector<cudaStream_t> peer_stream;
+	std::vector<cudaEvent_t> peer_done;
+	cudaEvent_t fork = nullptr;
+	void ensure_peer_streams() {
+		if (!peer_stream.empty() || world == 1) return;
+		peer_stream.assign(world, nullptr);
+		peer_done.assign(world, nullptr);
+		for (int p = 0; p < world; ++p) {
+			if (p == rank) continue;
+			MEMS_CUDA(cudaStreamCreateWithFlags(&peer_stream[p], cudaStreamNonBlocking));
+			MEMS_CUDA(cudaEventCreateWithFlags(&peer_done[p], cudaEventDisableTiming));
+		}
+		MEMS_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+	}
 	void free_window(int w) {
 		Window& x = win[w];
 		for (int p = 0; p < (int)x.peer.size(); ++p)
@@ -97,6 +113,11 @@ struct Comm {
 		free_window(1);
 		free_window(2);
 		if (d_barrier) cudaFree(d_barrier);
+		for (cudaStream_t st : peer_stream)
+			if (st) cudaStreamDestroy(st);
+		for (cudaEvent_t ev : peer_done)
+			if (ev) cudaEventDestroy(ev);
+		if (fork) cudaEventDestroy(fork);
 		if (side_comm) nccl().CommDestroy(side_comm);
 		if (comm) nccl().CommDestroy(comm);
 		if (side_stream) cudaStreamDestroy(side_stream);
@@ -267,20 +288,25 @@ void comm_window_barrier(Comm* c) {
 void comm_window_all_to_all(Comm* c, int w, int n_arrays, const void* const* d_send, const size_t* elem_bytes,
                             const size_t* region_off, const uint64_t* counts, bool barrier) {
 	const int W = c->world, R = c->rank;
-	for (int a = 0; a < n_arrays; ++a) {
-		const char* s = static_cast<const char*>(d_send[a]);
-		size_t so = 0;
-		for (int p = 0; p < W; ++p) {
-			const uint64_t n = counts[(size_t)R * W + p];
-			uint64_t before = 0;
-			for (int q = 0; q < R; ++q) before += counts[(size_t)q * W + p];
-			if (n) {
-				char* dst = static_cast<char*>(c->win[w].peer[p]) + region_off[a] + before * elem_bytes[a];
-				MEMS_CUDA(cudaMemcpyAsync(dst, s + so, n * elem_bytes[a], cudaMemcpyDefault, c->ctx->stream));
-			}
-			so += n * elem_bytes[a];
+	c->ensure_peer_streams();
+	if (W > 1) MEMS_CUDA(cudaEventRecord(c->fork, c->ctx->stream));
+	for (int i = 0; i < W; ++i) {
+		const int p = (R + i) % W;  // own slice first (main stream), then the peers, each on its own stream
+		cudaStream_t stream = p == R ? c->ctx->stream : c->peer_stream[p];
+		if (p != R) MEMS_CUDA(cudaStreamWaitEvent(stream, c->fork, 0));
+		uint64_t before = 0, so_elems = 0;
+		for (int q = 0; q < R; ++q) before += counts[(size_t)q * W + p];
+		for (int q = 0; q < p; ++q) so_elems += counts[(size_t)R * W + q];
+		const uint64_t n = counts[(size_t)R * W + p];
+		for (int a = 0; a < n_arrays && n; ++a) {
+			const char* src = static_cast<const char*>(d_send[a]) + so_elems * elem_bytes[a];
+			char* dst = static_cast<char*>(c->win[w].peer[p]) + region_off[a] + before * elem_bytes[a];
+			MEMS_CUDA(cudaMemcpyAsync(dst, src, n * elem_bytes[a], cudaMemcpyDefault, stream));
 		}
+		if (p != R) MEMS_CUDA(cudaEventRecord(c->peer_done[p], stream));
 	}
+	for (int p = 0; p < W; ++p)
+		if (p != R) MEMS_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->peer_done[p], 0));
 	if (barrier) comm_window_barrier(c);
 }
 
