@@ -1,8 +1,10 @@
-// comm.cu — the exchange steps of the sharded path over NCCL (NVLink 5 / NVSwitch between the B200s of a node).
+// comm.cu — the exchange steps of the sharded path between the B200s of a node (NVLink 5 / NVSwitch).
+// Bulk data (seed records by key range, hits by diagonal, position-ordered keys) travels peer-to-peer: every rank
+// owns exchange windows that all peers map through CUDA IPC, an exchange is DMA copies into the peers' windows
+// plus a barrier.  NCCL carries the small collectives (histogram / count all-gathers, the one-word barrier, the IPC
+// handles) and is the fallback transport where IPC is not available (all-to-all-v from grouped ncclSend/ncclRecv).
 // libnccl is bound at run time with dlopen: inside a torch process that is the NCCL torch already loaded, in a
-// plain C++ host the system libnccl.so.2.  Only four collectives are needed: a small all-reduce (digit
-// histogram), a small all-gather (count matrix), all-to-all-v built from grouped ncclSend/ncclRecv (seed records
-// by key range, hits by diagonal), and an all-gather-v built from grouped broadcasts (position-ordered keys).
+// plain C++ host the system libnccl.so.2.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -161,12 +163,6 @@ Comm* comm_create(std::shared_ptr<Ctx> ctx, const char* id128, int rank, int wor
 }
 
 void comm_destroy(Comm* c) { delete c; }
-
-// in-place sum of n u64 counters that live in device memory
-void comm_all_reduce_u64(Comm* c, uint64_t* d_buf, size_t n) {
-	if (c->world == 1) return;
-	check(nccl().AllReduce(d_buf, d_buf, n, ncclUint64, ncclSum, c->comm, c->ctx->stream), "ncclAllReduce");
-}
 
 // every rank contributes n u64 values; d_recv receives world * n (rank-major)
 void comm_all_gather_u64(Comm* c, const uint64_t* d_send, uint64_t* d_recv, size_t n) {

@@ -218,7 +218,6 @@ Comm* comm_create(std::shared_ptr<Ctx> ctx, const char* id128, int rank, int wor
 void comm_destroy(Comm* c);
 int Comm_rank(const Comm* c);
 int Comm_world(const Comm* c);
-void comm_all_reduce_u64(Comm* c, uint64_t* d_buf, size_t n);
 void comm_all_gather_u64(Comm* c, const uint64_t* d_send, uint64_t* d_recv, size_t n);
 void comm_all_to_all_v(Comm* c, const void* d_send, const uint64_t* send_counts, void* d_recv, const uint64_t* recv_counts,
                        size_t elem_bytes);

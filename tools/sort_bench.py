@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Time the SML build stages (extract + radix passes) on the GPU for one workload; used to compare
-kernel configurations (MEMS_SORT_VARIANT) and to fill the roofline table in DESIGN.md."""
+"""Time the SML build stages (pack, extract, radix passes) on the GPU for one workload: the numbers behind the
+roofline table in DESIGN.md and the quick check after a change to those kernels."""
 import json
 import sys
 import os
@@ -32,5 +32,5 @@ for _ in range(steps):
 prof = ctx.profile()
 out = {k: {"ms_per_launch": v["ms"] / v["launches"], "launches_per_step": v["launches"] / steps,
            "gbs": v["bytes"] / v["ms"] / 1e6 if v["ms"] > 0 and v["bytes"] else None} for k, v in prof.items()}
-print(json.dumps({"variant": os.environ.get("MEMS_SORT_VARIANT", "0"), "genomes": n_genomes, "length": length,
+print(json.dumps({"genomes": n_genomes, "length": length,
                   "weight": weight, "kernels": out}))
