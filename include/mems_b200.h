@@ -161,12 +161,24 @@ void mems_comm_destroy(mems_comm_t comm);
 int mems_shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count);
 /* owner rank of each of the 256 top-key-digit buckets given their global counts (host arithmetic) */
 int mems_shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256);
+/* the seed-record exchange as derived from the gathered histograms (hist_all[q * 256 + b], host arithmetic, the
+ * same on every rank): counts[q * world + p] = records rank q sends to rank p; for `rank`: src_elem[p] = start of its
+ * slice for p in its partitioned order, dst_elem[p] = start of that slice inside p's receive region; *max_recv = the
+ * largest receive region (ParallelMemHash's chunk bookkeeping, ParallelMemHash.cpp:75-82, made explicit) */
+int mems_shard_exchange_plan(const uint32_t* hist_all, int world, int rank, const uint8_t* owner256, uint64_t* counts,
+                             uint64_t* src_elem, uint64_t* dst_elem, uint64_t* max_recv);
 /* Collective: all ranks call it with the same n_seqs / lens / seed / params; seqs[g] must be valid for the
  * sequences of this rank's block (others may be NULL).  MEMS_MODE_MEMHASH, ORDER_ANY or ORDER_CANONICAL.
  * *out holds THIS rank's share of the distinct matches; the union over ranks is the MatchList. */
 int mems_find_matches_sharded(mems_ctx_t ctx, mems_comm_t comm, int n_seqs, const char* const* seqs,
                               const uint64_t* lens, uint64_t seed, const mems_match_params_t* params,
                               mems_matches_t* out);
+
+/* Environment switches read by the library (defaults are the measured best; the others exist for tests and
+ * experiments): MEMS_NO_PEER_WINDOWS=1 sharded exchanges through NCCL send/recv instead of CUDA-IPC exchange windows;
+ * MEMS_PEER_SCATTER=1 the partition kernel scatters straight into the peers' windows instead of partition + DMA copies;
+ * MEMS_NO_SIDE_COMM=1 no second NCCL communicator; MEMS_HOST_THREADS=n host threads of the reference-order table
+ * replay (default min(16, cores)); MEMS_TRACE=1 stage timings on stderr; MEMS_TEST_* shrink budgets in tests. */
 
 /* ---- measurement ---- */
 /* With profiling on, every kernel launch is bracketed by CUDA events on the context's stream. */

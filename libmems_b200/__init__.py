@@ -54,7 +54,7 @@ EXPORTS = [
     "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
     "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
-    "mems_shard_bucket_owners", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
+    "mems_shard_bucket_owners", "mems_shard_exchange_plan", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def load():
     lib.mems_shard_sequence_range.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                               ctypes.POINTER(ctypes.c_int)]
     lib.mems_shard_bucket_owners.argtypes = [_vp, ctypes.c_int, _vp]
+    lib.mems_shard_exchange_plan.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
     lib.mems_find_matches_sharded.argtypes = [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _u64,
                                               ctypes.POINTER(MatchParams), ctypes.POINTER(_vp)]
     lib.mems_profile_enable.argtypes = [_vp, ctypes.c_int]
@@ -155,6 +156,21 @@ def shard_bucket_owners(hist256, world):
     if rc:
         raise MemsError(rc, "bad shard arguments")
     return out
+
+
+def shard_exchange_plan(hist_all, world, rank, owners):
+    """Count matrix [sender, receiver], this rank's slice starts (source / destination) and the largest receive region
+    of the seed-record exchange, from the gathered (world x 256) top-digit histograms."""
+    h = np.ascontiguousarray(hist_all, dtype=np.uint32).reshape(world, 256)
+    o = np.ascontiguousarray(owners, dtype=np.uint8)
+    counts = np.zeros((world, world), np.uint64)
+    src, dst = np.zeros(world, np.uint64), np.zeros(world, np.uint64)
+    mx = ctypes.c_uint64()
+    rc = load().mems_shard_exchange_plan(h.ctypes.data, world, rank, o.ctypes.data, counts.ctypes.data, src.ctypes.data,
+                                         dst.ctypes.data, ctypes.byref(mx))
+    if rc:
+        raise MemsError(rc, "bad shard arguments")
+    return counts, src, dst, mx.value
 
 
 def comm_unique_id():

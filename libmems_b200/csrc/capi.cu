@@ -355,6 +355,17 @@ int mems_shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner2
 	return MEMS_OK;
 }
 
+int mems_shard_exchange_plan(const uint32_t* hist_all, int world, int rank, const uint8_t* owner256, uint64_t* counts,
+                             uint64_t* src_elem, uint64_t* dst_elem, uint64_t* max_recv) {
+	if (!hist_all || !owner256 || !counts || !src_elem || !dst_elem || !max_recv || world < 1 || world > 256 || rank < 0 ||
+	    rank >= world)
+		return fail(nullptr, MEMS_ERR_INVALID, "bad arguments");
+	for (int b = 0; b < 256; ++b)
+		if (owner256[b] >= world) return fail(nullptr, MEMS_ERR_INVALID, "owner out of range");
+	shard_exchange_plan(hist_all, world, rank, owner256, counts, src_elem, dst_elem, max_recv);
+	return MEMS_OK;
+}
+
 int mems_find_matches_sharded(mems_ctx_t ctx, mems_comm_t comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
                               uint64_t seed, const mems_match_params_t* params, mems_matches_t* out) {
 	if (!ctx) return fail(nullptr, MEMS_ERR_INVALID, "null context");

@@ -240,6 +240,9 @@ void comm_side_synchronize(Comm* c);
 void shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count);
 // owner rank of each of the 256 top-digit buckets, balanced by the global bucket histogram, contiguous ranges
 void shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256);
+// count matrix and slice offsets of the seed-record exchange, from the gathered histograms (see kernels_match.cu)
+void shard_exchange_plan(const uint32_t* hist_all, int world, int rank, const uint8_t* owner256, uint64_t* counts,
+                         uint64_t* src_elem, uint64_t* dst_elem, uint64_t* max_recv);
 
 // ---- kernels_match.cu ----
 // [SeqCount, Length, starts...] records on the host: either a page-locked buffer borrowed from the context

@@ -1852,6 +1852,31 @@ void shard_bucket_owners(const uint64_t* hist256, int world, uint8_t* owner256) 
 	}
 }
 
+// The record exchange as every rank derives it from the gathered top-digit histograms (hist_all[q * 256 + b] =
+// records of bucket b on rank q): counts[q * world + p] = records rank q sends to rank p; for THIS rank,
+// src_elem[p] = first element of its slice for rank p in its partitioned order (buckets of one owner are
+// contiguous) and dst_elem[p] = element at which that slice starts inside rank p's receive region (slices lie in
+// sender order); *max_recv = the largest receive region, which sizes the exchange windows identically everywhere.
+void shard_exchange_plan(const uint32_t* hist_all, int world, int rank, const uint8_t* owner256, uint64_t* counts,
+                         uint64_t* src_elem, uint64_t* dst_elem, uint64_t* max_recv) {
+	for (int i = 0; i < world * world; ++i) counts[i] = 0;
+	for (int q = 0; q < world; ++q)
+		for (int b = 0; b < 256; ++b) counts[(size_t)q * world + owner256[b]] += hist_all[(size_t)256 * q + b];
+	uint64_t mx = 0, at = 0;
+	for (int p = 0; p < world; ++p) {
+		uint64_t n = 0, before = 0;
+		for (int q = 0; q < world; ++q) {
+			if (q < rank) before += counts[(size_t)q * world + p];
+			n += counts[(size_t)q * world + p];
+		}
+		mx = n > mx ? n : mx;
+		src_elem[p] = at;
+		dst_elem[p] = before;
+		at += counts[(size_t)rank * world + p];
+	}
+	*max_recv = mx;
+}
+
 template <class KeyT>
 __global__ void scatter_members_kernel(MatchArgs a, const uint32_t* __restrict__ hid, const uint32_t* __restrict__ hit_start,
                                        const uint16_t* __restrict__ hit_len, const uint32_t* __restrict__ mem_off, uint32_t n_hits,
@@ -2011,13 +2036,10 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	std::vector<uint64_t> send_counts(W, 0), recv_counts(W, 0);
 	for (int b = 0; b < 256; ++b) send_counts[owner[b]] += h_hist32[b];
 	std::vector<uint64_t> rec_counts((size_t)W * W, 0);  // [sender][receiver], identical on every rank
-	for (int q = 0; q < W; ++q)
-		for (int b = 0; b < 256; ++b) rec_counts[(size_t)q * W + owner[b]] += h_all[(size_t)256 * q + b];
+	std::vector<uint64_t> slice_src(W), slice_dst(W);
 	uint64_t max_recv = 0, n_recv = 0;
+	shard_exchange_plan(h_all.data(), W, R, owner, rec_counts.data(), slice_src.data(), slice_dst.data(), &max_recv);
 	for (int p = 0; p < W; ++p) {
-		uint64_t n = 0;
-		for (int q = 0; q < W; ++q) n += rec_counts[(size_t)q * W + p];
-		max_recv = std::max(max_recv, n);
 		recv_counts[p] = rec_counts[(size_t)p * W + R];
 		n_recv += recv_counts[p];
 	}
@@ -2057,25 +2079,9 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		// digit b's run starts at index first_idx[b] of this rank's partitioned order and belongs at element
 		// (records of lower ranks for that owner) + (index inside this rank's slice for that owner) of the owner's region
 		uint64_t h_dst[512];
-		uint64_t slice_first[256];
-		std::vector<uint64_t> slice_start(W, 0);
-		{
-			uint64_t at = 0;
-			int cur_owner = -1;
-			for (int b = 0; b < 256; ++b) {
-				if ((int)owner[b] != cur_owner) {
-					cur_owner = owner[b];
-					slice_start[cur_owner] = at;
-				}
-				slice_first[b] = slice_start[cur_owner];
-				at += h_hist32[b];
-			}
-		}
 		for (int b = 0; b < 256; ++b) {
 			const int p = owner[b];
-			uint64_t before = 0;
-			for (int q = 0; q < R; ++q) before += rec_counts[(size_t)q * W + p];
-			const int64_t shift_elems = (int64_t)before - (int64_t)slice_first[b];  // destination index - partitioned index
+			const int64_t shift_elems = (int64_t)slice_dst[p] - (int64_t)slice_src[p];  // destination index - partitioned index
 			const uint64_t win = reinterpret_cast<uint64_t>(comm_window_peer(comm, 0, p));
 			h_dst[b] = win + rec_region[0] + (uint64_t)(shift_elems * (int64_t)K);
 			h_dst[256 + b] = win + rec_region[1] + (uint64_t)(shift_elems * 4);

@@ -1,5 +1,6 @@
 """Host-side sharding plan of the multi-GPU path, exercised with 2 gloo ranks on CPU: every rank derives the
-same sequence blocks and the same key-range owners from the all-reduced histogram (no GPU needed)."""
+same sequence blocks, the same key-range owners and the same exchange plan (count matrix, slice offsets into the
+peers' exchange windows) from the gathered histograms (no GPU needed)."""
 import os
 import socket
 import sys
@@ -42,6 +43,20 @@ def _worker(rank, world, port, out_dir):
     recv = np.array([int(mat[p][rank]) for p in range(world)])
     np.save(os.path.join(out_dir, "r%d.npy" % rank),
             np.concatenate([[first, count], owners.astype(np.int64), t.numpy(), send_counts, recv]))
+    # the exchange as the library plans it from the GATHERED histograms (what mems_find_matches_sharded does): every
+    # rank then "sends" its records — (rank, bucket, serial) triples in partitioned order — to the offsets of the plan
+    rows = [torch.zeros(256, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(rows, torch.from_numpy(hist.copy()))
+    hist_all = np.stack([r.numpy() for r in rows]).astype(np.uint32)
+    owners2 = m.shard_bucket_owners(hist_all.sum(axis=0).astype(np.uint64), world)
+    counts, src, dst, max_recv = m.shard_exchange_plan(hist_all, world, rank, owners2)
+    records = np.concatenate([np.stack([np.full(hist[b], rank), np.full(hist[b], b), np.arange(hist[b])], axis=1)
+                              for b in range(256)]).astype(np.int64)  # partitioned order = bucket order
+    for p in range(world):
+        n = int(counts[rank, p])
+        np.save(os.path.join(out_dir, "x_%d_to_%d.npy" % (rank, p)),
+                np.concatenate([[int(dst[p]), int(max_recv)], records[int(src[p]):int(src[p]) + n].ravel()]))
+    np.save(os.path.join(out_dir, "plan%d.npy" % rank), np.concatenate([counts.ravel().astype(np.int64), owners2.astype(np.int64)]))
     dist.destroy_process_group()
 
 
@@ -63,6 +78,36 @@ def test_two_rank_plan(tmp_path):
     for p in range(world):
         for q in range(world):
             assert send[p][q] == recv[q][p]
+
+
+def test_two_rank_exchange_plan_tiles_the_windows(tmp_path):
+    """Simulated exchange: writing every rank's slices at the planned offsets fills each receive region exactly —
+    no gap, no overlap, slices in sender order, and every record lands on the owner of its bucket."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    plans = [np.load(tmp_path / ("plan%d.npy" % k)) for k in range(world)]
+    assert np.array_equal(plans[0], plans[1])  # identical on every rank
+    counts = plans[0][:world * world].reshape(world, world)
+    owners = plans[0][world * world:]
+    for p in range(world):
+        n_recv = int(counts[:, p].sum())
+        region = np.full((n_recv, 3), -1, np.int64)
+        filled = np.zeros(n_recv, bool)
+        for q in range(world):
+            x = np.load(tmp_path / ("x_%d_to_%d.npy" % (q, p)))
+            at, max_recv, recs = int(x[0]), int(x[1]), x[2:].reshape(-1, 3)
+            assert max_recv == counts.sum(axis=0).max()
+            assert len(recs) == counts[q, p]
+            assert not filled[at:at + len(recs)].any()
+            region[at:at + len(recs)] = recs
+            filled[at:at + len(recs)] = True
+        assert filled.all()
+        assert np.all(owners[region[:, 1]] == p)  # only this rank's key range
+        assert np.all(np.diff(region[:, 0]) >= 0)  # slices in sender order
+        for q in range(world):
+            mine = region[region[:, 0] == q]
+            assert np.all(np.diff(mine[:, 1]) >= 0)  # each sender's slice still in bucket order
 
 
 def test_plan_edge_cases():
