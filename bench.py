@@ -347,6 +347,19 @@ def main():
             names = sorted({k for d in rank_kernel_ms for k in d})
             line["kernel_ms_max_over_ranks"] = {k: max(d.get(k, 0.0) for d in rank_kernel_ms) for k in names}
             line["kernel_ms_total_per_rank"] = [sum(d.values()) for d in rank_kernel_ms]
+            try:
+                # the seed-record exchange against NVLink 5 (900 GB/s per direction and GPU): bytes this rank sends to
+                # its peers, (world - 1) / world of its records, over the duration of the exchange incl. its barrier
+                ex = next((v for k, v in prof.items() if k.endswith("all_to_all_records")), None)
+                if ex and ex["ms"] > 0:
+                    sent = ex["bytes"] * (world - 1) / world
+                    gbs = sent / ex["ms"] / 1e6
+                    line["exchange"] = {"kernel": next(k for k in prof if k.endswith("all_to_all_records")),
+                                        "sent_bytes_per_step": sent / args.steps, "ms_per_step": ex["ms"] / args.steps,
+                                        "achieved": gbs, "peak": 900.0, "unit": "GB/s", "frac": gbs / 900.0,
+                                        "note": "rank 0; the time includes waiting for the slowest rank at the barrier"}
+            except Exception as e:  # noqa: BLE001 - never let a report field break the bench line
+                line["exchange"] = {"error": str(e)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(name)
         sys.stdout.flush()
