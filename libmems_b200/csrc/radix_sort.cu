@@ -7,12 +7,16 @@
 // in ascending position order.
 //
 // Per pass, one CTA per tile of kTile pairs:
-//   1. coalesced warp-striped load of the tile (each warp owns a contiguous 32*kItems chunk),
-//   2. per-warp digit ranking with __match_any_sync (no atomics, order preserving),
-//   3. per-digit decoupled look-back across tiles (thread d resolves digit d) against the digit
-//      histogram that extraction already produced — a tile never waits for more than its predecessors'
-//      256 counters, so the whole pass is a single read and a single write of the data,
-//   4. reorder through shared memory so every digit's run leaves the CTA as one contiguous segment.
+//   1. coalesced warp-striped load of the keys (each warp owns a contiguous 32*kItems chunk),
+//   2. per-warp digit ranking from ballots (no atomics, order preserving) against per-warp counters in
+//      shared memory,
+//   3. the tile's digit counts are published, the keys are reordered through shared memory (values go
+//      straight from global memory to their reordered slot with cp.async),
+//   4. per-digit decoupled look-back across tiles (thread d resolves digit d, a few predecessors per round)
+//      against the digit histogram that extraction already produced — a tile never waits for more than its
+//      predecessors' 256 counters, so the whole pass is a single read and a single write of the data,
+//   5. coalesced store: every digit's run leaves the CTA as one contiguous segment — into the second
+//      buffers, or (PEER) into per-digit destinations that may be other GPUs' exchange windows.
 // Tiles take their index from an atomic ticket, which guarantees that all predecessors of a running
 // tile are themselves running or finished (forward progress of the look-back).
 #include <cstdlib>
