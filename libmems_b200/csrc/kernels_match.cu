@@ -10,22 +10,24 @@
 // The extended result of a hit is the connected component of matching seed windows on the hit's
 // diagonal, where windows count as adjacent when they start <= L apart.  That
 // turns the sequential table into data-parallel steps:
-//   1. run scan     — one thread per union entry; run heads validate their run -> hit list (key order)
+//   1. run scan     — a warp per 32 union entries decides the runs that start in its first lanes from ballots -> hit list (key order)
 //   2. describe     — per hit: first member, 64-bit hash of its diagonal (member set, orientations,
 //                     offsets) -> sort key (diagonal hash | first-member position)
 //   3. sort         — hits by that key (radix_sort.cu): hits of one diagonal become contiguous, by position
 //   4. segments     — neighbours on the same diagonal <= L apart are connected without looking at sequence
 //   5. extend       — one warp per segment walks RIGHT from its last hit with the window test: a probe tests
 //                     128 windows at once (4 per lane, one load of the position-ordered key array per member
-//                     and window), the chain of matches <= L apart is followed bit-parallel in the ballot
-//                     mask; the walk ends when it reaches the next segment of its diagonal (link) or a gap
-//                     > L (component end).  Chains of linked segments are the components; only each chain's
-//                     first segment walks LEFT.  Walks that outlast a warp's budget go to 16-warp CTAs (2048
-//                     windows per round), the few that outlast those to the whole grid (cooperative launch)
+//                     and window), the chain of matches <= L apart is followed lane-parallel (each lane asks
+//                     "no match in my next L windows?", ballots find the first); the walk ends when it reaches
+//                     the next segment of its diagonal (link) or a gap > L (component end).  Chains of linked
+//                     segments are the components; only each chain's first segment walks LEFT.  Walks that
+//                     outlast a warp's budget go to 16-warp CTAs (8192 windows per round), the few that outlast
+//                     those to the whole grid (cooperative launch)
 //   6. emit         — components -> [SeqCount, Length, starts] records; policies: MemHash (+ MaskedMemHash
 //                     filter), RepeatHash, PairwiseMatchFinder; ORDER_REFERENCE replays the reference's hash
 //                     table on the host (optionally into a persistent table shared by several calls)
-//   sharded         — find_matches_sharded at the bottom: the same stages across ranks with two NCCL exchanges
+//   sharded         — find_matches_sharded at the bottom: the same stages across ranks with two exchanges
+//                     (peer-to-peer into CUDA-IPC exchange windows, NCCL as fallback)
 // Hash collisions between diagonals only split segments (more window tests), never merge them: every
 // merge decision compares the full member lists.
 #include <algorithm>
@@ -752,8 +754,8 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 // A diagonal shared by few sequences has few hits but can match for hundreds of kbp (the sequences agree
 // wherever the others carry a SNP), so a handful of walks are 10^3-10^4 probes long: as one warp each they
 // would be the critical path of the whole call.  Walks that exhaust their warp budget are finished here by
-// a 32-warp CTA: every round the warps probe 32 x 128 consecutive windows at once, each summarises its 128
-// bits (first match, end of the chain that starts there, last match) and thread 0 stitches the summaries.
+// a 16-warp CTA: every round each warp probes its own 4 x 128 consecutive windows and summarises them (first
+// match, end of the chain that starts there, last match); thread 0 stitches the 16 summaries.
 constexpr int kLongWarps = 16;   // warps per CTA: two CTAs share an SM, so one's barrier waits overlap the other's probes
 constexpr int kLongProbes = 4;   // consecutive probes a warp makes per round: the barriers and the stitch are paid once per
                                  // 8192 windows, and the warps' probe latencies overlap freely in between
