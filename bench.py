@@ -122,13 +122,18 @@ def run_reference(args, name):
     line = {"impl": "reference", "metric": "genome Mbp/s (SML build + MemHash match find)", "unit": "Mbp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "genomes": n_genomes, "genome_length": length, "seed_weight": weight}}
+            "config": {"workload": desc, "genomes": n_genomes,
+                       # our arm scales weakly: every genome is `gpus` times longer; the reference is timed on a bounded
+                       # sample of that workload (cpu_baseline.sample), its Mbp/s does not depend on the length
+                       "genome_length": length * (args.gpus if mode != "repeat" else 1), "seed_weight": weight,
+                       "seed_pattern": None}}
     if not Reference.available():
         line["unavailable"] = "oracle/_ref/libmems_ref.so not present (needs /root/reference at build time)"
         print(json.dumps(line))
         return
     R = Reference()
     seed = R.get_seed(weight)
+    line["config"]["seed_pattern"] = hex(seed)
     gs = make_genomes(name, sg, sl, seed=2)
     mbp = sum(len(g) for g in gs) / 1e6
     m = 1 if mode == "repeat" else 0
