@@ -46,9 +46,8 @@ REF_STEP_SAMPLE = {"c1": (2, 500_000), "c2": (8, 150_000), "c3": (1, 3_000_000),
 
 def make_genomes(name, n_genomes, length, seed):
     from libmems_b200 import synth
-    if WORKLOADS[name][3] == "repeat":
-        fam = max(2, int(200 * length / 100_000_000))
-        return [synth.repeat_genome(length, seed=seed, families=fam, copies=20)]
+    if name in synth.BASELINE_WORKLOADS:  # the inputs the full-size parity tests pin (tests/golden/full_*.json)
+        return synth.baseline_genomes(name, n_genomes, length, seed)
     return synth.genome_family(n_genomes, length, seed=seed)
 
 

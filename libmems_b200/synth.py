@@ -71,3 +71,33 @@ def repeat_genome(n, seed=1, families=200, copies=20, min_len=300, max_len=2300,
             p = int(rng.integers(0, n - ln))
             g[p:p + ln] = c
     return np.ascontiguousarray(g)
+
+
+# BASELINE.json configs at their stated sizes: (genomes, length, seed weight, mode, generator seed).  bench.py, the
+# full-size parity tests and tools/gen_golden_full.py all take their inputs from here, so the digests the
+# reference produced in the build container (tests/golden/full_*.json) describe exactly what the GPU is given.
+BASELINE_WORKLOADS = {
+    "c1": (2, 5_000_000, 15, "memhash", 2),
+    "c2": (8, 5_000_000, 15, "memhash", 2),
+    "c3": (1, 100_000_000, 19, "repeat", 2),
+}
+
+
+def baseline_genomes(name, n_genomes=None, length=None, seed=None):
+    """The synthetic sequences of a BASELINE config (optionally at another size: bounded CPU samples)."""
+    g, n, _, mode, s = BASELINE_WORKLOADS[name]
+    g = g if n_genomes is None else n_genomes
+    n = n if length is None else length
+    s = s if seed is None else seed
+    if mode == "repeat":
+        return [repeat_genome(n, seed=s, families=max(2, int(200 * n / 100_000_000)), copies=20)]
+    return genome_family(g, n, seed=s)
+
+
+def matchlist_digest(matches):
+    """SHA-256 over the int64 little-endian stream [SeqCount, Length, Start(0..)] of the matches in the given order."""
+    import hashlib
+    h = hashlib.sha256()
+    buf = np.fromiter((x for m in matches for x in m), dtype="<i8")
+    h.update(buf.tobytes())
+    return h.hexdigest()
