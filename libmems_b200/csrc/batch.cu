@@ -22,9 +22,12 @@ int bits_for(uint64_t max_value) {  // bits needed to store values 0..max_value
 
 static void layout_batch(Batch& b, const std::vector<uint64_t>& lens, uint32_t tag0 = 0, int force_pos_bits = 0,
                          int force_seq_bits = 0) {
+	// the per-sequence lists are one counting pass on the sequence tag (Batch::sorted_positions): 8 digit bits
+	if (lens.size() > 256)
+		throw Error(MEMS_ERR_UNSUPPORTED, "more than 256 sequences in one create call; build them in several batches");
 	b.n_seqs = (int)lens.size();
 	b.meta.resize(b.n_seqs);
-	uint64_t byte_off = 0, word_off = 0, seed_off = 0;
+	uint64_t byte_off = 0, word_off = kLeadWords, seed_off = 0;
 	uint32_t max_seeds = 0;
 	for (int g = 0; g < b.n_seqs; ++g) {
 		if (lens[g] > 0xffffffffull)
@@ -38,11 +41,12 @@ static void layout_batch(Batch& b, const std::vector<uint64_t>& lens, uint32_t t
 		m.tag = tag0 + (uint32_t)g;
 		m.pad_ = 0;
 		byte_off += (lens[g] + 15) / 16 * 16;
-		word_off += ((lens[g] + 15) / 16 + 2 + 3) / 4 * 4;  // keep every sequence 16-byte aligned
+		word_off += seq_packed_words(lens[g]);  // keeps every sequence 16-byte aligned
 		seed_off += m.n_seeds;
 		max_seeds = std::max(max_seeds, m.n_seeds);
 	}
 	b.n_total = seed_off;
+	b.total_words = word_off + kTailWords;
 	b.pos_bits = bits_for(max_seeds ? max_seeds - 1 : 0);
 	b.seq_bits = b.n_seqs > 1 ? bits_for((uint64_t)b.n_seqs - 1) : 0;
 	if (force_pos_bits) b.pos_bits = force_pos_bits;
@@ -94,11 +98,11 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 	if (n_seqs == 0) return b;
 	const SeqMeta& last = b->meta.back();
 	const uint64_t total_bytes = last.byte_off + ((uint64_t)last.n_bases + 15) / 16 * 16;
-	const uint64_t total_words = last.word_off + (((uint64_t)last.n_bases + 15) / 16 + 2 + 3) / 4 * 4;
 
 	b->d_meta = DevBuf<SeqMeta>(c, b->n_seqs);
 	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
-	b->packed = DevBuf<uint32_t>(c, total_words);
+	b->packed = DevBuf<uint32_t>(c, b->total_words);
+	MEMS_CUDA(cudaMemsetAsync(b->packed.p, 0, b->total_words * sizeof(uint32_t), c->stream));  // pads and alignment gaps
 	DevBuf<uint8_t> ascii(c, total_bytes + 16);
 	DevBuf<uint32_t> gap_flag(c, 1);
 	MEMS_CUDA(cudaMemsetAsync(gap_flag.p, 0, sizeof(uint32_t), c->stream));
@@ -107,6 +111,8 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 			// cudaMemcpyDefault: seqs[g] may be pageable or pinned host memory, or already a device pointer
 			MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyDefault, c->stream));
 	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
+	b->planes = DevBuf<uint2>(c, b->total_words / 2);
+	launch_planes(c, b->packed.p, b->planes.p, b->total_words);
 	uint32_t gap = 0;
 	MEMS_CUDA(cudaMemcpyAsync(&gap, gap_flag.p, sizeof gap, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
@@ -134,11 +140,10 @@ std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const s
 	std::vector<uint64_t> lens;
 	for (const SeqRef& s : seqs) lens.push_back(s.batch->meta[s.index].n_bases);
 	layout_batch(*b, lens);
-	const SeqMeta& last = b->meta.back();
-	const uint64_t total_words = last.word_off + (((uint64_t)last.n_bases + 15) / 16 + 2 + 3) / 4 * 4;
 	b->d_meta = DevBuf<SeqMeta>(c, b->n_seqs);
 	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
-	b->packed = DevBuf<uint32_t>(c, total_words);
+	b->packed = DevBuf<uint32_t>(c, b->total_words);
+	MEMS_CUDA(cudaMemsetAsync(b->packed.p, 0, b->total_words * sizeof(uint32_t), c->stream));
 	for (size_t g = 0; g < seqs.size(); ++g) {
 		const SeqMeta& src = seqs[g].batch->meta[seqs[g].index];
 		// the source lives on another context's stream: make sure its producer has finished
@@ -147,6 +152,8 @@ std::shared_ptr<Batch> build_batch_from_packed(std::shared_ptr<Ctx> ctx, const s
 		MEMS_CUDA(cudaMemcpyAsync(b->packed.p + b->meta[g].word_off, seqs[g].batch->packed.p + src.word_off,
 		                          words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
 	}
+	b->planes = DevBuf<uint2>(c, b->total_words / 2);
+	launch_planes(c, b->packed.p, b->planes.p, b->total_words);
 	extract_and_sort(*b);
 	return b;
 }

@@ -27,7 +27,19 @@ struct SeedDesc {
 	// the same runs as one shift + one mask each: mer |= (window >> run_net[r]) & run_mask[r]
 	uint8_t run_net[kMaxSeedRuns];     // rshift - lshift (always >= 64 - 2L >= 2)
 	uint64_t run_mask[kMaxSeedRuns];   // ((1 << run_bits) - 1) << run_lshift
+	// the pattern as the window test of match extension reads it (kernels_match.cu):
+	uint8_t off[32];     // offsets of the w cared bases inside a window, ascending
+	uint8_t mirror[32];  // mirror[i] = L-1 - off[w-1-i]: where cared base i of a window sits, seen from the other strand
+	int32_t palindromic; // mirror == off: a window and its reverse complement care about the same bases
+	int32_t pad_;
 };
+
+// Every batch's packed buffer starts with kLeadWords zero words and ends with kTailWords: the window test loads 64-base
+// chunks that may begin up to 63 bases before a sequence and end up to ~100 bases after it.
+constexpr uint64_t kLeadWords = 8, kTailWords = 16;
+// words one sequence of n bases occupies in a batch's packed buffer: its ceil(n/16) words + the reference's two pad
+// words (SortedMerList.cpp:306-311), rounded up so that the next sequence starts 16-byte aligned
+__host__ __device__ inline uint64_t seq_packed_words(uint64_t n_bases) { return ((n_bases + 15) / 16 + 2 + 3) / 4 * 4; }
 
 // One sequence of a batch, as laid out in device memory.
 struct SeqMeta {
@@ -135,6 +147,9 @@ void launch_pack(Ctx* c, const uint8_t* d_ascii, uint32_t* d_packed, const SeqMe
 void launch_extract(Ctx* c, const uint32_t* d_packed, const SeqMeta* d_meta, const SeqMeta* h_meta, int n_seqs,
                     const SeedDesc& sd, int pos_bits, bool key64, void* d_keys, uint32_t* d_vals, uint32_t* d_hist,
                     int n_passes, const int* pass_shift, const int* pass_bits);
+// Bit planes of a packed buffer: planes[i] = {high bits, low bits} of the 2-bit codes of bases 32i .. 32i+31
+// (bit j of a word <-> base 32i + j); n_words (a multiple of 2) packed words -> n_words / 2 entries.
+void launch_planes(Ctx* c, const uint32_t* d_packed, uint2* d_planes, uint64_t n_words);
 // mers at arbitrary positions of one sequence (reference 64-bit layout)
 void launch_seed_mers(Ctx* c, const uint32_t* d_words, uint32_t n_seeds, const SeedDesc& sd, const uint64_t* d_pos,
                       uint64_t n, uint64_t* d_fwd, uint64_t* d_dna);
@@ -188,7 +203,9 @@ struct Batch {
 	uint64_t n_total = 0;  // seeds in the union
 	std::vector<SeqMeta> meta;
 	DevBuf<SeqMeta> d_meta;
+	uint64_t total_words = 0;  // words of `packed`, lead and tail pad included
 	DevBuf<uint32_t> packed;
+	DevBuf<uint2> planes;      // bit planes of `packed` (launch_planes): what the window test of match extension reads
 	DevBuf<uint8_t> keys_by_pos;  // compact key of every seed position, in (seq, position) order (extraction output)
 	DevBuf<uint8_t> keys;      // union, ascending compact key (u32 or u64); ties in (seq, position) order
 	DevBuf<uint32_t> vals;     // union, (seq << pos_bits) | position

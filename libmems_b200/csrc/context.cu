@@ -136,6 +136,14 @@ SeedDesc make_seed_desc(uint64_t seed) {
 		ones_before += len;
 	}
 	sd.key_bits = 2 * sd.w + 1;
+	int n_off = 0;
+	for (int o = 0; o < sd.L; ++o)
+		if ((pat >> (sd.L - 1 - o)) & 1) sd.off[n_off++] = (uint8_t)o;
+	sd.palindromic = 1;
+	for (int k = 0; k < sd.w; ++k) {
+		sd.mirror[k] = (uint8_t)(sd.L - 1 - sd.off[sd.w - 1 - k]);
+		if (sd.mirror[k] != sd.off[k]) sd.palindromic = 0;
+	}
 	return sd;
 }
 

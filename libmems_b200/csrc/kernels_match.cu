@@ -62,7 +62,7 @@ struct MatchArgs {
 	int test_hash_bits;  // 0 = use the full diagonal hash; n > 0 keeps only n bits (tests force bucket collisions with it)
 	int warp_budget;     // probes one warp spends on a walk before a CTA takes over (kWarpProbeBudget; tests shrink it)
 	int cta_budget;      // rounds one CTA spends before the whole grid takes over (kCtaRoundBudget; tests shrink it)
-	const uint32_t* packed;
+	const uint2* planes;   // bit planes of the packed sequences (Batch::planes); SeqMeta::word_off * 16 = a sequence's first base
 	const SeqMeta* meta;
 };
 
@@ -426,44 +426,95 @@ __global__ void segment_compact_kernel(const uint32_t* __restrict__ is_head, con
 }
 
 // ------------------------------------------------------------------------------------------------ 5. extend
-// The window test of MatchFinder::ExtendMatch (MatchFinder.h:264-308) for the window k positions from a
-// hit (k < 0: towards the first member's start): every member's seed position must be valid, all masked
-// keys equal, and all (strand xor orientation) parities equal.  The reference recomputes two spaced-seed
-// mers per member and window (GetSeedMer, ~84 ns each); here the canonical key of every position is
-// already resident from extraction (Batch::keys_by_pos), so a member costs one 4/8-byte load:
-//     tagged(member, k) = keys_by_pos[base + (reverse ? -k : +k)] ^ reverse
-// and the window matches iff all tagged values are equal.  Position validity collapses to one interval
-// [kmin, kmax] per hit (intersection of the members' valid ranges).
+// The window test of MatchFinder::ExtendMatch (MatchFinder.h:264-308) for the window k positions from a hit
+// (k < 0: towards the first member's start): every member's seed position must be valid, all masked keys equal,
+// and all (strand xor orientation) parities equal.  The reference recomputes two spaced-seed mers per member and
+// window (GetSeedMer, ~84 ns each).  Here the test runs on the packed sequence itself, 32 windows per lane and
+// 1024 per warp and probe:
+//   * (canonical mer, strand) determines the forward mer and vice versa, so for a member in the first member's
+//     orientation "equal key and parity" means "equal forward mers": the w cared bases agree;
+//   * for a member in the opposite orientation it means "my reverse-complemented mer equals your forward mer, and
+//     that mer is not its own reverse complement" (the two would then carry the same strand flag; possible for even
+//     weights only) — with a palindromic pattern: the w cared bases of the two windows agree on opposite strands.
+// So per probe a lane loads, for every member, the 64 bases under its 32 windows from the bit planes of the packed
+// sequence (3 coalesced 64-bit loads; reverse members load the mirrored chunk and bit-reverse it), XORs them
+// against the first member's and ORs the result into one disagreement bit per base; the windows then are
+//   match(j) = AND over the w cared offsets o of agree(j + o)
+// — w funnel shifts and ANDs for 32 windows.  Non-palindromic patterns (two entries of the reference's table) compare
+// reverse members offset by offset instead (cared base i sits at another offset on the other strand), and the
+// self-reverse-complement exception is w/2 shifted XORs of the first member's own planes.  Position validity
+// collapses to one interval [kmin, kmax] per hit (intersection of the members' valid ranges).
 constexpr int kExtendWarps = 4;
 constexpr int kMemberTile = 64;  // members staged in shared memory per warp (MEMS_MAX_SEQS fits at once)
-constexpr uint32_t kReverseBit = 0x80000000u;
-constexpr int kWarpProbeBudget = 48;  // probes (of 128 windows) a single warp spends on one walk before deferring
+constexpr int kProbeWindows = 1024;  // windows one warp tests per probe
+constexpr int kWarpProbeBudget = 6;  // probes a single warp spends on one walk before deferring it to a whole CTA
+
+struct SeedShape {  // what the window test needs of the pattern (SeedDesc::off / mirror), in shared memory
+	uint8_t off[32], mirror[32];
+	int w, L;
+	bool palindromic;
+};
+__device__ __forceinline__ void load_seed_shape(SeedShape* sh, const SeedDesc& sd) {
+	if (threadIdx.x < 32) {
+		sh->off[threadIdx.x] = sd.off[threadIdx.x];
+		sh->mirror[threadIdx.x] = sd.mirror[threadIdx.x];
+	}
+	if (threadIdx.x == 0) {
+		sh->w = sd.w;
+		sh->L = sd.L;
+		sh->palindromic = sd.palindromic != 0;
+	}
+	__syncthreads();
+}
+
+struct Chunk {  // 64 consecutive bases as bit planes: bit t <-> base t of the chunk
+	uint32_t h0, h1, l0, l1;
+};
+// the chunk that starts at base `at` of the batch's base array (at >= 0: the buffer carries a lead pad)
+__device__ __forceinline__ Chunk load_chunk(const uint2* __restrict__ planes, int64_t at) {
+	const uint2* p = planes + (at >> 5);
+	const uint32_t sh = (uint32_t)at & 31u;
+	const uint2 a = p[0], b = p[1], c = p[2];
+	Chunk r;
+	r.h0 = __funnelshift_r(a.x, b.x, sh);
+	r.h1 = __funnelshift_r(b.x, c.x, sh);
+	r.l0 = __funnelshift_r(a.y, b.y, sh);
+	r.l1 = __funnelshift_r(b.y, c.y, sh);
+	return r;
+}
+// bases in reverse order (the complement is left to the caller's XOR)
+__device__ __forceinline__ Chunk reverse_chunk(const Chunk& c) {
+	Chunk r;
+	r.h0 = __brev(c.h1);
+	r.h1 = __brev(c.h0);
+	r.l0 = __brev(c.l1);
+	r.l1 = __brev(c.l0);
+	return r;
+}
 
 template <class KeyT>
 struct WarpHit {
 	const MatchArgs& a;
-	const KeyT* key_pos;
-	uint32_t* s_mem;  // this warp's kMemberTile slots: (seed_off + pos) | reverse << 31
+	const SeedShape& shape;
+	uint2* s_mem;  // this warp's kMemberTile slots: base index of the member's window 0 in the batch's base array
+	               // (.x low 32 bits, .y high bits), bit 31 of .y = opposite orientation to the first member
 	uint32_t s, len, sf;
 	int32_t kmin, kmax;  // valid window offsets (all |k| < 2^31: positions are < 2^30)
+	bool any_reverse;
 	int lane;
 #ifdef MEMS_WALK_STATS
 	uint32_t n_probes = 0;
 #endif
-	static constexpr int kProbe = 128;
-	// match bits of one probe, identical in every lane: bit i of word j = the window at distance 32*j + i + 1 matches
-	struct mask_t {
-		uint32_t w[4];
-	};
 
-	__device__ uint32_t member_entry(uint32_t j, int32_t& lo, int32_t& hi) const {
+	__device__ uint2 member_entry(uint32_t j, int32_t& lo, int32_t& hi) const {
 		const uint32_t val = a.vals[j];
 		const uint32_t o = strand_of<KeyT>(a.keys, j) ^ sf;
 		const SeqMeta m = a.meta[val >> a.pos_bits];
 		const int32_t p = (int32_t)(val & a.pos_mask), last = (int32_t)m.n_seeds - 1;
 		lo = o ? p - last : -p;
 		hi = o ? p : last - p;
-		return ((uint32_t)m.seed_off + (uint32_t)p) | (o ? kReverseBit : 0u);
+		const uint64_t base = m.word_off * 16ull + (uint64_t)p;
+		return make_uint2((uint32_t)base, (uint32_t)(base >> 32) | (o ? 0x80000000u : 0u));
 	}
 	__device__ void load_tile(uint32_t first) {
 		for (uint32_t t = lane; t < kMemberTile && first + t < len; t += 32) {
@@ -477,144 +528,147 @@ struct WarpHit {
 		len = hit_len;
 		sf = first_strand;
 		int32_t lo = INT32_MIN, hi = INT32_MAX;
+		bool rev = false;
 		for (uint32_t t = lane; t < len; t += 32) {  // one pass: valid range and the first member tile together
 			int32_t l2, h2;
-			const uint32_t e = member_entry(s + t, l2, h2);
+			const uint2 e = member_entry(s + t, l2, h2);
 			if (t < kMemberTile) s_mem[t] = e;
+			rev |= (e.y >> 31) != 0u;
 			lo = max(lo, l2);
 			hi = min(hi, h2);
 		}
 		kmin = __reduce_max_sync(0xffffffffu, lo);
 		kmax = __reduce_min_sync(0xffffffffu, hi);
+		any_reverse = __any_sync(0xffffffffu, rev);
 		__syncwarp();
 	}
-	// The four keys one member contributes to this lane's windows.  e = the member's s_mem entry, k_first = the
-	// lane's nearest window.  Reverse members run backwards; the walk direction flips that again: the product is
-	// warp-uniform, so each case is straight-line code with immediate load offsets (no address arithmetic per window).
-	__device__ __forceinline__ void member_keys(uint32_t e, int32_t k_first, int dir, const bool (&ok)[4], KeyT (&v)[4]) const {
-		const bool rev = (e & kReverseBit) != 0u;
-		const int32_t base = (int32_t)(e & ~kReverseBit);
-		const KeyT* ptr = key_pos + (ptrdiff_t)(rev ? base - k_first : base + k_first);
-		if ((dir > 0) != rev) {
-#pragma unroll
-			for (int j = 0; j < 4; ++j)
-				if (ok[j]) v[j] = ptr[32 * j];
-		} else {
-#pragma unroll
-			for (int j = 0; j < 4; ++j)
-				if (ok[j]) v[j] = ptr[-32 * j];
-		}
-	}
-	// Probe the windows at distances 1..n_win (<= 128) from k0 in direction dir (+1/-1): lane l tests distances
-	// l+1, l+33, l+65, l+97.  Members are taken four at a time and all 16 loads of a group are issued before
-	// any is compared, so a group costs one memory round trip; a compare is one LOP3 (difference OR-ed into the
-	// window's accumulator; reverse members compare against the reference with its strand bit flipped).
-	__device__ mask_t probe(int32_t k0, int dir, int n_win) {
-		bool ok[4];
-		KeyT ref[4], refx[4], diff[4];
-		const int32_t k_first = k0 + dir * (lane + 1);  // this lane's nearest window; the others are 32, 64, 96 further
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const int32_t k = k_first + dir * 32 * j;
-			ok[j] = lane + 32 * j < n_win && k >= kmin && k <= kmax;  // invalid windows are never loaded
-			ref[j] = 0;
-			diff[j] = 0;
-		}
+	// Probe the kProbeWindows windows at distances 1.. from k0 in direction dir (+1/-1): this lane's 32 windows are
+	// the distances 32*lane + 1 .. 32*lane + 32, bit j of the result = distance 32*lane + j + 1 matches.
+	__device__ uint32_t probe(int32_t k0, int dir) {
+#ifdef MEMS_WALK_STATS
+		++n_probes;
+#endif
+		const int L = shape.L, w = shape.w;
+		// the lane's windows in ascending window order: klo + j, j = 0..31
+		const int32_t klo = dir > 0 ? k0 + 1 + 32 * lane : k0 - 32 * (lane + 1);
+		uint32_t m = 0;  // valid windows
 		{
-			const uint32_t e0 = s_mem[0];
-			member_keys(e0, k_first, dir, ok, ref);
-			const KeyT r0 = (KeyT)(e0 >> 31);
-#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				ref[j] ^= r0;
-				refx[j] = ref[j] ^ (KeyT)1;
-			}
+			const int32_t j0 = max(kmin - klo, 0), j1 = min(kmax - klo, 31);
+			if (j0 <= j1) m = (0xffffffffu >> (31 - j1)) & (0xffffffffu << j0);
 		}
+		const bool live = m != 0u;  // lanes without a valid window load nothing (their addresses may lie outside the buffer)
+		if (!__any_sync(0xffffffffu, live)) return 0u;
+		Chunk ref{0, 0, 0, 0};
+		{
+			const uint2 e0 = s_mem[0];
+			const int64_t base0 = (int64_t)(((uint64_t)(e0.y & 0x7fffffffu) << 32) | e0.x);
+			if (live) ref = load_chunk(a.planes, base0 + klo);
+		}
+		uint32_t d0 = 0, d1 = 0;  // disagreement per base of the chunk, all members
 		for (uint32_t first = 0; first < len; first += kMemberTile) {
 			if (first) load_tile(first);
 			const uint32_t cnt = len - first < kMemberTile ? len - first : kMemberTile;
-			for (uint32_t t0 = first ? 0u : 1u; t0 < cnt; t0 += 4) {
-				KeyT v[4][4];
-				const uint32_t in_group = cnt - t0 < 4 ? cnt - t0 : 4;  // warp-uniform: the tail group is not padded
-#pragma unroll
-				for (int u = 0; u < 4; ++u)
-					if ((uint32_t)u < in_group) member_keys(s_mem[t0 + u], k_first, dir, ok, v[u]);
-#pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					if ((uint32_t)u < in_group) {
-						if (s_mem[t0 + u] & kReverseBit) {
-#pragma unroll
-							for (int j = 0; j < 4; ++j) diff[j] |= v[u][j] ^ refx[j];
-						} else {
-#pragma unroll
-							for (int j = 0; j < 4; ++j) diff[j] |= v[u][j] ^ ref[j];
-						}
+			for (uint32_t t = first ? 0u : 1u; t < cnt; ++t) {
+				const uint2 e = s_mem[t];
+				const int64_t base = (int64_t)(((uint64_t)(e.y & 0x7fffffffu) << 32) | e.x);
+				if (!(e.y >> 31)) {  // warp-uniform
+					if (live) {
+						const Chunk c = load_chunk(a.planes, base + klo);
+						d0 |= (c.h0 ^ ref.h0) | (c.l0 ^ ref.l0);
+						d1 |= (c.h1 ^ ref.h1) | (c.l1 ^ ref.l1);
 					}
-				}
-				if (t0 + 4 < cnt || first + kMemberTile < len) {  // more members to come: stop if nothing is left to decide
-					const bool alive = (ok[0] && diff[0] == 0) || (ok[1] && diff[1] == 0) || (ok[2] && diff[2] == 0) ||
-					                   (ok[3] && diff[3] == 0);
-					if (!__any_sync(0xffffffffu, alive)) {
-						t0 = cnt;
-						first = len;
+				} else {
+					// window klo + j of this member starts at base - (klo + j) and is read on the other strand: base t of the
+					// reversed chunk that ENDS at base - klo + L - 1 is the complement of what window j holds at offset t - j
+					if (live) {
+						const Chunk c = reverse_chunk(load_chunk(a.planes, base - klo + (L - 1) - 63));
+						if (shape.palindromic) {
+							d0 |= ~(c.h0 ^ ref.h0) | ~(c.l0 ^ ref.l0);
+							d1 |= ~(c.h1 ^ ref.h1) | ~(c.l1 ^ ref.l1);
+						} else {
+							// cared base i of the first member's window (offset off[i]) meets offset mirror[i] of this one
+							for (int i = 0; i < w; ++i) {
+								const uint32_t o = shape.off[i], q = shape.mirror[i];
+								const uint32_t x = ~(__funnelshift_r(c.h0, c.h1, q) ^ __funnelshift_r(ref.h0, ref.h1, o)) |
+								                   ~(__funnelshift_r(c.l0, c.l1, q) ^ __funnelshift_r(ref.l0, ref.l1, o));
+								m &= ~x;
+							}
+						}
 					}
 				}
 			}
 			if (len > kMemberTile) __syncwarp();
 		}
 		if (len > kMemberTile) load_tile(0);
-		mask_t m;
-#pragma unroll
-		for (int j = 0; j < 4; ++j) m.w[j] = __ballot_sync(0xffffffffu, ok[j] && diff[j] == 0);
-		return m;
-	}
-	__device__ static int highest_set(const mask_t& m) {  // 1-based distance of the highest set bit, 0 if none
-		if (m.w[3]) return 128 - __clz((int)m.w[3]);
-		if (m.w[2]) return 96 - __clz((int)m.w[2]);
-		if (m.w[1]) return 64 - __clz((int)m.w[1]);
-		return 32 - __clz((int)m.w[0]);
-	}
-	__device__ static int lowest_set(const mask_t& m) {  // 1-based distance of the lowest set bit, 0 if none
-		if (m.w[0]) return __ffs((int)m.w[0]);
-		if (m.w[1]) return 32 + __ffs((int)m.w[1]);
-		if (m.w[2]) return 64 + __ffs((int)m.w[2]);
-		return m.w[3] ? 96 + __ffs((int)m.w[3]) : 0;
-	}
-	// Follow the chain of matches inside one probe, starting from a match at distance `from` (0 = the window
-	// the walk stands on): consecutive matches may be at most L apart.  The chain's last match is the first
-	// window x >= from (x = from, or a match) whose next L windows x+1..x+L all mismatch; every lane tests that
-	// for its own four windows (one funnel shift + mask each) and four ballots find the first.  Only gaps that
-	// lie completely inside the n_win probed windows count: *ended tells whether one was found (the chain is
-	// over) or the probe simply ran out (continue from the returned distance, the last match seen).
-	__device__ int follow(const mask_t& m, int from, int L, int n_win, bool* ended) const {
-		const uint32_t l_mask = (1u << L) - 1u;  // L <= 31
-		if (from == 0 && L <= n_win && (m.w[0] & l_mask) == 0u) {
-			*ended = true;
-			return 0;
+		const uint32_t ok0 = ~d0, ok1 = ~d1;
+		for (int i = 0; i < w; ++i) m &= __funnelshift_r(ok0, ok1, shape.off[i]);
+		if (any_reverse && !(w & 1)) {
+			// a mer equal to its own reverse complement carries the same strand flag on both strands: never a match
+			// between opposite orientations.  Cared base i must be the complement of cared base w-1-i.
+			uint32_t self = 0xffffffffu;
+			for (int i = 0; i < w / 2; ++i) {
+				const uint32_t o = shape.off[i], q = shape.off[w - 1 - i];
+				self &= (__funnelshift_r(ref.h0, ref.h1, o) ^ __funnelshift_r(ref.h0, ref.h1, q)) &
+				        (__funnelshift_r(ref.l0, ref.l1, o) ^ __funnelshift_r(ref.l0, ref.l1, q));
+			}
+			m &= ~self;
 		}
-		mask_t brk;
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const int x = lane + 1 + 32 * j;
-			const uint32_t next = __funnelshift_rc(m.w[j], j < 3 ? m.w[j + 1] : 0u, lane + 1) & l_mask;
-			const bool here = ((m.w[j] >> lane) & 1u) ? x >= from : x == from;
-			brk.w[j] = __ballot_sync(0xffffffffu, here && next == 0u && x + L <= n_win);
+		return dir > 0 ? m : __brev(m);
+	}
+	// distance (1-based) of the highest / lowest set bit over the warp's words, 0 if none
+	__device__ int highest_set(uint32_t m) const {
+		const uint32_t b = __ballot_sync(0xffffffffu, m != 0u);
+		if (!b) return 0;
+		const int z = 31 - __clz((int)b);
+		return 32 * z + 32 - __clz((int)__shfl_sync(0xffffffffu, m, z));
+	}
+	__device__ int lowest_set(uint32_t m) const {
+		const uint32_t b = __ballot_sync(0xffffffffu, m != 0u);
+		if (!b) return 0;
+		const int z = __ffs((int)b) - 1;
+		return 32 * z + __ffs((int)__shfl_sync(0xffffffffu, m, z));
+	}
+	// Where a chain of matches at most L apart breaks inside one probe.  The chain starts at distance `from`
+	// (0 = the window the walk stands on, else a set bit of m); matches before `from` are ignored.  Every match covers
+	// the L distances after it; the chain ends at the match x whose reach x+1..x+L holds no further match, i.e.
+	// x + L + 1 is the first distance >= from that nothing covers.  Returns that first uncovered distance (<= kProbeWindows:
+	// the gap then lies completely inside the probed windows, the chain's last match is L + 1 before it), or 0 when the
+	// chain runs on to the end of the probe.  Lane-parallel: a lane smears its word and its predecessor's by 0..L bits.
+	__device__ int chain_break(uint32_t m, int from) const {
+		const int L = shape.L;
+		// matches before `from` do not count; distance 0 sits in bit 31 of lane 0's predecessor word
+		uint32_t cur = m;
+		if (from > 0) {
+			const int fl = (from - 1) >> 5, fb = (from - 1) & 31;
+			if (lane < fl) cur = 0u;
+			else if (lane == fl) cur &= 0xffffffffu << fb;
 		}
-		const int gap_after = lowest_set(brk);
-		if (gap_after) {
-			*ended = true;
-			return gap_after;
+		uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
+		if (lane == 0) prev = from == 0 ? 0x80000000u : 0u;
+		// cover = bits of OR_{s = 0..L} ((cur:prev) << s) that fall into cur's word: doubling, then one more step
+		uint32_t hi = cur, lo = prev;
+		int have = 1;  // shifts 0 .. have-1 are in
+		while (2 * have <= L + 1) {
+			hi |= __funnelshift_l(lo, hi, have);
+			lo |= lo << have;
+			have *= 2;
 		}
-		*ended = false;
-		const int last = highest_set(m);
-		return last > from ? last : from;
+		if (have < L + 1) hi |= __funnelshift_l(lo, hi, L + 1 - have);
+		uint32_t open = ~hi;  // distances nothing covers
+		if (from > 0) {       // ... from `from` on
+			const int fl = (from - 1) >> 5, fb = (from - 1) & 31;
+			if (lane < fl) open = 0u;
+			else if (lane == fl) open &= 0xffffffffu << fb;
+		}
+		return lowest_set(open);
 	}
 	// Walk from window k0 in direction dir over matching windows that start <= L apart, as far as they go
 	// (the closure loop of MatchFinder::ExtendMatch, MatchFinder.h:259-355).  If stop_dist >= 0 the walk ends as
 	// soon as it stands within L of that distance (the next segment of the diagonal) and *linked is set.
 	// Returns the distance walked.  After max_probes probes the walk gives up with *exhausted set: such
 	// walks (a handful per genome set, but up to hundreds of kbp long) are finished by whole CTAs, see cta_walk.
-	__device__ int32_t walk(int32_t k0, int dir, int L, int32_t stop_dist, bool* linked, int max_probes, bool* exhausted) {
+	__device__ int32_t walk(int32_t k0, int dir, int32_t stop_dist, bool* linked, int max_probes, bool* exhausted) {
+		const int L = shape.L;
 		int32_t walked = 0;
 		*linked = false;
 		*exhausted = false;
@@ -627,19 +681,20 @@ struct WarpHit {
 				*exhausted = true;
 				return walked;
 			}
-			int n_win = kProbe;  // never probe beyond the stop target
-			if (stop_dist >= 0 && stop_dist - walked < n_win) n_win = stop_dist - walked;
-			const mask_t m = probe(k0 + dir * walked, dir, n_win);
-#ifdef MEMS_WALK_STATS
-			++n_probes;
-#endif
-			bool ended;
-			walked += follow(m, 0, L, n_win, &ended);
-			if (stop_dist >= 0 && stop_dist <= walked + L) {
-				*linked = true;
+			uint32_t m = probe(k0 + dir * walked, dir);
+			if (stop_dist >= 0 && stop_dist - walked <= kProbeWindows) {
+				// the next segment's first hit is a matching window of this diagonal: nothing beyond it matters
+				const int t = stop_dist - walked - 1, tl = t >> 5, tb = t & 31;
+				if (lane > tl) m = 0u;
+				else if (lane == tl) m = (m & (0xffffffffu >> (31 - tb))) | (1u << tb);
+			}
+			const int open_at = chain_break(m, 0);
+			if (open_at) {
+				walked += open_at - L - 1;
+				if (stop_dist >= 0 && stop_dist <= walked + L) *linked = true;
 				return walked;
 			}
-			if (ended) return walked;
+			walked += highest_set(m);  // chain_break saw no gap: there is a match, and the chain goes on past the probe
 		}
 	}
 };
@@ -665,9 +720,11 @@ struct SegView {
 // no window within L matches (link = 0: reach = last matching window, the component's right end).
 template <class KeyT>
 __global__ void __launch_bounds__(kExtendWarps * 32)
-walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, uint32_t* __restrict__ seg_link,
+walk_right_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, uint32_t* __restrict__ seg_link,
                   uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
-	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
+	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
+	__shared__ SeedShape s_shape;
+	load_seed_shape(&s_shape, sd);
 	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
 	if (slot >= v.n_seg) return;
 	const uint32_t seg = v.order[slot];  // segments are visited in order of genome position (L2 locality)
@@ -675,13 +732,13 @@ walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView 
 	const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
 	const uint32_t h = v.hid[hi];
 	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+	WarpHit<KeyT> w{a, s_shape, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, false, (int)(threadIdx.x & 31)};
 	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 	int32_t c = (int32_t)((int64_t)(v.hkey[end - 1] & a.pos_mask) - x0);
 	const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
 	const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
 	bool linked, exhausted;
-	c += w.walk(c, +1, L, has_next ? next_at - c : -1, &linked, a.warp_budget, &exhausted);
+	c += w.walk(c, +1, has_next ? next_at - c : -1, &linked, a.warp_budget, &exhausted);
 	if (exhausted) {  // hand the rest of this walk to a whole CTA (long_walk_kernel)
 		if (w.lane == 0) {
 			const uint32_t at = atomicAdd(defer_count, 1u);
@@ -712,12 +769,14 @@ __global__ void chain_first_kernel(const uint32_t* __restrict__ seg_link, uint32
 // Left walk of every component's first segment, and scatter of both component ends.
 template <class KeyT>
 __global__ void __launch_bounds__(kExtendWarps * 32)
-walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint32_t* __restrict__ seg_link,
+walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint32_t* __restrict__ seg_link,
                  const uint32_t* __restrict__ seg_reach, const uint32_t* __restrict__ first,
                  const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
                  uint32_t* __restrict__ comp_right, uint8_t* __restrict__ comp_suspect, uint2* __restrict__ defer,
                  uint32_t* __restrict__ defer_count) {
-	__shared__ uint32_t s_mem[kExtendWarps][kMemberTile];
+	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
+	__shared__ SeedShape s_shape;
+	load_seed_shape(&s_shape, sd);
 	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
 	if (slot >= v.n_seg) return;
 	const uint32_t seg = v.order[slot];
@@ -733,10 +792,10 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 	const uint32_t hi = v.seg_head[seg];
 	const uint32_t h = v.hid[hi];
 	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-	WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, lane};
+	WarpHit<KeyT> w{a, s_shape, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, false, lane};
 	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 	bool linked, exhausted;
-	const int32_t c = -w.walk(0, -1, L, -1, &linked, a.warp_budget, &exhausted);
+	const int32_t c = -w.walk(0, -1, -1, &linked, a.warp_budget, &exhausted);
 	if (lane == 0) comp_rep[comp] = hi;
 	if (exhausted) {
 		if (lane == 0) {
@@ -752,16 +811,14 @@ walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v
 
 // ---- long walks -------------------------------------------------------------------------------------
 // A diagonal shared by few sequences has few hits but can match for hundreds of kbp (the sequences agree
-// wherever the others carry a SNP), so a handful of walks are 10^3-10^4 probes long: as one warp each they
+// wherever the others carry a SNP), so a handful of walks are 10^2-10^4 probes long: as one warp each they
 // would be the critical path of the whole call.  Walks that exhaust their warp budget are finished here by
-// a 16-warp CTA: every round each warp probes its own 4 x 128 consecutive windows and summarises them (first
-// match, end of the chain that starts there, last match); thread 0 stitches the 16 summaries.
+// a 16-warp CTA: every round each warp probes its own kProbeWindows consecutive windows and summarises them
+// (first match, end of the chain that starts there, last match); thread 0 stitches the 16 summaries.
 constexpr int kLongWarps = 16;   // warps per CTA: two CTAs share an SM, so one's barrier waits overlap the other's probes
-constexpr int kLongProbes = 4;   // consecutive probes a warp makes per round: the barriers and the stitch are paid once per
-                                 // 8192 windows, and the warps' probe latencies overlap freely in between
-constexpr int kWarpSpan = 128 * kLongProbes;
-constexpr int kLongSpan = kLongWarps * kWarpSpan;
-constexpr int kCtaRoundBudget = 48; // rounds one CTA spends on a walk before the whole grid takes it over
+constexpr int kWarpSpan = kProbeWindows;
+constexpr int kLongSpan = kLongWarps * kWarpSpan;  // 16384 windows between barriers
+constexpr int kCtaRoundBudget = 24; // rounds one CTA spends on a walk before the whole grid takes it over
 
 struct ChainSummary {
 	int first, chain_end, last;  // 1-based distances inside the summarised span, 0 = no match
@@ -791,33 +848,22 @@ __device__ inline ChainSummary combine_summaries(const int4* child, int n, int u
 	return r;
 }
 
-// Summary of the kWarpSpan windows after k_base (distances 1..kWarpSpan), probe by probe: first match, last match
-// of the chain that starts at the first match, last match overall.
+// Summary of the kWarpSpan windows after k_base (distances 1..kWarpSpan): first match, last match of the chain that
+// starts at the first match, last match overall.
 template <class KeyT>
-__device__ __forceinline__ int4 warp_span_summary(WarpHit<KeyT>& w, int32_t k_base, int dir, int L) {
-	typedef typename WarpHit<KeyT>::mask_t mask_t;
-	int4 child[kLongProbes];
-#pragma unroll
-	for (int p = 0; p < kLongProbes; ++p) {
-		const mask_t m = w.probe(k_base + dir * 128 * p, dir, 128);
-		const int f = WarpHit<KeyT>::lowest_set(m), l = WarpHit<KeyT>::highest_set(m);
-		int ce = 0;
-		if (f) {
-			bool ended;
-			ce = w.follow(m, f, L, 128, &ended);
-			if (!ended) ce = l;
-		}
-		child[p] = make_int4(f, ce, l, 0);
-	}
-	const ChainSummary cs = combine_summaries(child, kLongProbes, 128, L);
-	return make_int4(cs.first, cs.chain_end, cs.last, 0);
+__device__ __forceinline__ int4 warp_span_summary(WarpHit<KeyT>& w, int32_t k_base, int dir) {
+	const uint32_t m = w.probe(k_base, dir);
+	const int f = w.lowest_set(m);
+	if (!f) return make_int4(0, 0, 0, 0);
+	const int l = w.highest_set(m);
+	const int open_at = w.chain_break(m, f);
+	return make_int4(f, open_at ? open_at - w.shape.L - 1 : l, l, 0);
 }
 
 template <class KeyT>
-__device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_t stop_dist, bool* linked, int4* s_sum,
+__device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int32_t stop_dist, bool* linked, int4* s_sum,
                             int32_t* s_result, int max_rounds, bool* exhausted) {
-	typedef typename WarpHit<KeyT>::mask_t mask_t;
-	const int warp = threadIdx.x >> 5;
+	const int warp = threadIdx.x >> 5, L = w.shape.L;
 	int32_t walked = 0;
 	*exhausted = false;
 	for (int round = 0;; ++round) {
@@ -826,7 +872,7 @@ __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_
 			*linked = false;
 			return walked;
 		}
-		const int4 mine = warp_span_summary<KeyT>(w, k0 + dir * (walked + kWarpSpan * warp), dir, L);
+		const int4 mine = warp_span_summary<KeyT>(w, k0 + dir * (walked + kWarpSpan * warp), dir);
 		if (w.lane == 0) s_sum[warp] = mine;
 		__syncthreads();
 		if (threadIdx.x == 0) {
@@ -862,15 +908,18 @@ __device__ int32_t cta_walk(WarpHit<KeyT>& w, int32_t k0, int dir, int L, int32_
 
 template <class KeyT>
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
-long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ defer,
+long_walk_right_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint2* __restrict__ defer,
                        const uint32_t* __restrict__ defer_count, uint32_t* __restrict__ next_item,
                        uint32_t* __restrict__ seg_link, uint32_t* __restrict__ seg_reach, uint2* __restrict__ giant,
                        uint32_t* __restrict__ giant_count) {
-	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
+	__shared__ uint2 s_mem[kLongWarps][kMemberTile];
+	__shared__ SeedShape s_shape;
 	__shared__ int4 s_sum[kLongWarps];
 	__shared__ int32_t s_result[2];
 	__shared__ uint32_t s_item;
 	const uint32_t n_defer = *defer_count;
+	if (n_defer == 0) return;
+	load_seed_shape(&s_shape, sd);
 	while (true) {  // walks differ in length by orders of magnitude: CTAs pull them from a queue
 		if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1u);
 		__syncthreads();
@@ -883,12 +932,12 @@ long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, Seg
 		const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
 		const uint32_t h = v.hid[hi];
 		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-		WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+		WarpHit<KeyT> w{a, s_shape, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, false, (int)(threadIdx.x & 31)};
 		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 		const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
 		const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
 		bool linked, exhausted;
-		c += cta_walk<KeyT>(w, c, +1, L, has_next ? next_at - c : -1, &linked, s_sum, s_result, a.cta_budget, &exhausted);
+		c += cta_walk<KeyT>(w, c, +1, has_next ? next_at - c : -1, &linked, s_sum, s_result, a.cta_budget, &exhausted);
 		if (threadIdx.x == 0) {
 			if (exhausted) {
 				giant[atomicAdd(giant_count, 1u)] = make_uint2(seg, (uint32_t)c);
@@ -902,15 +951,18 @@ long_walk_right_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, Seg
 
 template <class KeyT>
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
-long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ defer,
+long_walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint2* __restrict__ defer,
                       const uint32_t* __restrict__ defer_count, uint32_t* __restrict__ next_item,
                       const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_left, uint2* __restrict__ giant,
                       uint32_t* __restrict__ giant_count) {
-	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
+	__shared__ uint2 s_mem[kLongWarps][kMemberTile];
+	__shared__ SeedShape s_shape;
 	__shared__ int4 s_sum[kLongWarps];
 	__shared__ int32_t s_result[2];
 	__shared__ uint32_t s_item;
 	const uint32_t n_defer = *defer_count;
+	if (n_defer == 0) return;
+	load_seed_shape(&s_shape, sd);
 	while (true) {
 		if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1u);
 		__syncthreads();
@@ -922,10 +974,10 @@ long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegV
 		const uint32_t hi = v.seg_head[seg];
 		const uint32_t h = v.hid[hi];
 		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-		WarpHit<KeyT> w{a, key_pos, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+		WarpHit<KeyT> w{a, s_shape, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, false, (int)(threadIdx.x & 31)};
 		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 		bool linked, exhausted;
-		c -= cta_walk<KeyT>(w, c, -1, L, -1, &linked, s_sum, s_result, a.cta_budget, &exhausted);
+		c -= cta_walk<KeyT>(w, c, -1, -1, &linked, s_sum, s_result, a.cta_budget, &exhausted);
 		if (threadIdx.x == 0) {
 			if (exhausted) giant[atomicAdd(giant_count, 1u)] = make_uint2(seg, (uint32_t)c);
 			else comp_left[first_excl[seg]] = (uint32_t)(x0 + c);
@@ -938,20 +990,23 @@ long_walk_left_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegV
 // The few walks that outlast a CTA's budget too (two sequences that agree for Mbp while the others differ) are
 // finished by the WHOLE GRID, one walk at a time: every CTA probes its own span of kLongSpan windows, the
 // per-CTA summaries meet in global memory, CTA 0 stitches them (same rule as inside a CTA) and a grid-wide
-// barrier publishes the result.  One round covers gridDim x 2048 windows (~600 k on a B200), so the longest
+// barrier publishes the result.  One round covers gridDim x 16384 windows (~4.8 M on a B200), so the longest
 // diagonal of a genome set costs a handful of rounds instead of being the critical path of the whole call.
 template <class KeyT>
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
-giant_walk_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView v, const uint2* __restrict__ giant,
+giant_walk_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint2* __restrict__ giant,
                   const uint32_t* __restrict__ giant_count, int dir, const uint32_t* __restrict__ first_excl,
                   uint32_t* __restrict__ seg_link, uint32_t* __restrict__ seg_reach, uint32_t* __restrict__ comp_left,
                   int4* __restrict__ g_sum, int32_t* __restrict__ g_state) {
-	typedef typename WarpHit<KeyT>::mask_t mask_t;
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-	__shared__ uint32_t s_mem[kLongWarps][kMemberTile];
+	__shared__ uint2 s_mem[kLongWarps][kMemberTile];
+	__shared__ SeedShape s_shape;
 	__shared__ int4 s_sum[kLongWarps];
 	const int warp = threadIdx.x >> 5;
 	const uint32_t n_items = *giant_count;
+	if (n_items == 0) return;  // grid-uniform
+	load_seed_shape(&s_shape, sd);
+	const int L = s_shape.L;
 	for (uint32_t it = 0; it < n_items; ++it) {
 		const uint32_t seg = giant[it].x;
 		const int32_t c0 = (int32_t)giant[it].y;
@@ -959,14 +1014,14 @@ giant_walk_kernel(MatchArgs a, const KeyT* __restrict__ key_pos, int L, SegView 
 		const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
 		const uint32_t h = v.hid[hi];
 		const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-		WarpHit<KeyT> w{a, key_pos, s_mem[warp], 0, 0, 0, 0, 0, (int)(threadIdx.x & 31)};
+		WarpHit<KeyT> w{a, s_shape, s_mem[warp], 0, 0, 0, 0, 0, false, (int)(threadIdx.x & 31)};
 		w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 		const bool has_next = dir > 0 && seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
 		const int32_t stop_dist = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) - c0 : -1;
 		int32_t walked = 0;
 		int state = 0;
 		while (!state) {
-			const int4 mine = warp_span_summary<KeyT>(w, c0 + dir * (walked + kLongSpan * (int32_t)blockIdx.x + kWarpSpan * warp), dir, L);
+			const int4 mine = warp_span_summary<KeyT>(w, c0 + dir * (walked + kLongSpan * (int32_t)blockIdx.x + kWarpSpan * warp), dir);
 			if (w.lane == 0) s_sum[warp] = mine;
 			__syncthreads();
 			if (threadIdx.x == 0) {
@@ -1345,9 +1400,10 @@ static void find_pair_hits(Ctx* c, const MatchArgs& a, HitSet& hits, DevBuf<uint
 
 // ---- stage B: hits (members readable through a.keys / a.vals) -> extended, distinct matches
 template <class KeyT>
-static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT* key_pos, int L, HitSet& hits, int order,
+static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const SeedDesc& sd, HitSet& hits, int order,
                         uint32_t table_size, MatchResult& out, HashTable* persistent = nullptr) {
 	Ctx* c = ctx.get();
+	const int L = sd.L;
 	const int mode = a.mode;
 	const uint32_t n_hits = hits.n;
 	DevBuf<uint32_t>& hit_start = hits.start;
@@ -1423,8 +1479,8 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	DevBuf<int4> g_sum(c, giant_grid);
 	DevBuf<int32_t> g_state(c, 2);
 	auto launch_giant = [&](int dir, uint32_t* count, uint32_t* comp_left_p) {
-		const KeyT* kp_arg = key_pos;
-		int L_arg = L, dir_arg = dir;
+		SeedDesc sd_arg = sd;
+		int dir_arg = dir;
 		MatchArgs a_arg = a;
 		SegView v_arg = v_for_giant;
 		const uint2* giant_p = giant.p;
@@ -1434,7 +1490,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 		uint32_t* reach_p = seg_reach.p;
 		int4* sum_p = g_sum.p;
 		int32_t* state_p = g_state.p;
-		void* args[] = {&a_arg, &kp_arg, &L_arg, &v_arg, &giant_p, &count_p, &dir_arg, &fe_p, &link_p, &reach_p, &comp_left_p,
+		void* args[] = {&a_arg, &sd_arg, &v_arg, &giant_p, &count_p, &dir_arg, &fe_p, &link_p, &reach_p, &comp_left_p,
 		                &sum_p, &state_p};
 		KernelScope ks(c, dir > 0 ? "giant_walk_right" : "giant_walk_left");
 		MEMS_CUDA(cudaLaunchCooperativeKernel((void*)giant_walk_kernel<KeyT>, dim3(giant_grid), dim3(kLongWarps * 32), args, 0,
@@ -1443,13 +1499,13 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	const uint32_t walk_blocks = (n_seg + kExtendWarps - 1) / kExtendWarps, seg_blocks = (n_seg + 255) / 256;
 	{
 		KernelScope ks(c, "walk_right");
-		walk_right_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(a, key_pos, L, v, seg_link.p, seg_reach.p,
+		walk_right_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(a, sd, v, seg_link.p, seg_reach.p,
 		                                                                          defer.p, defer_count);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
 		KernelScope ks(c, "long_walk_right");
-		long_walk_right_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, key_pos, L, v, defer.p, defer_count,
+		long_walk_right_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, sd, v, defer.p, defer_count,
 		                                                                           queue_heads.p, seg_link.p, seg_reach.p, giant.p, queue_heads.p + 2);
 		MEMS_CUDA(cudaGetLastError());
 	}
@@ -1482,13 +1538,13 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const KeyT
 	{
 		KernelScope ks(c, "walk_left");
 		walk_left_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(
-		    a, key_pos, L, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, comp_suspect.p,
+		    a, sd, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, comp_suspect.p,
 		    defer.p, defer_count + 1);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
 		KernelScope ks(c, "long_walk_left");
-		long_walk_left_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, key_pos, L, v, defer.p, defer_count + 1,
+		long_walk_left_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, sd, v, defer.p, defer_count + 1,
 		                                                                          queue_heads.p + 1, first_excl.p, comp_left.p, giant.p, queue_heads.p + 3);
 		MEMS_CUDA(cudaGetLastError());
 	}
@@ -1788,7 +1844,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.seq_set = 0;
 	for (int g = 0; g < b.n_seqs; ++g)
 		if ((seq_mask >> (b.n_seqs - 1 - g)) & 1) a.seq_set |= 1ull << g;
-	a.packed = b.packed.p;
+	a.planes = b.planes.p;
 	a.meta = b.d_meta.p;
 	HitSet hits;
 	DevBuf<uint32_t> pvals;
@@ -1807,7 +1863,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		if (persistent) emit_table(*persistent, out);  // nothing new: the result is still the whole table
 		return;
 	}
-	extend_hits<KeyT>(b.ctx, a, reinterpret_cast<const KeyT*>(b.keys_by_pos.p), b.sd.L, hits, order, table_size, out, persistent);
+	extend_hits<KeyT>(b.ctx, a, b.sd, hits, order, table_size, out, persistent);
 }
 
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
@@ -1946,7 +2002,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	};
 	// ---- global layout (identical on every rank)
 	std::vector<SeqMeta> gmeta(n_seqs);
-	uint64_t seed_off = 0;
+	uint64_t seed_off = 0, word_off = kLeadWords;  // the same packed layout as one batch of all sequences would have
 	uint32_t max_seeds = 0;
 	for (int g = 0; g < n_seqs; ++g) {
 		if (lens[g] > 0xffffffffull) throw Error(MEMS_ERR_UNSUPPORTED, "sequence longer than 2^32-1 bases");
@@ -1955,10 +2011,13 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		m.n_bases = (uint32_t)lens[g];
 		m.n_seeds = lens[g] >= (uint64_t)sd.L ? (uint32_t)(lens[g] - sd.L + 1) : 0u;
 		m.seed_off = seed_off;
+		m.word_off = word_off;
 		m.tag = (uint32_t)g;
 		seed_off += m.n_seeds;
+		word_off += seq_packed_words(lens[g]);
 		max_seeds = std::max(max_seeds, m.n_seeds);
 	}
+	const uint64_t words_total = word_off + kTailWords;
 	const uint64_t s_total = seed_off;
 	const int pos_bits = bits_for(max_seeds ? max_seeds - 1 : 0);
 	const int seq_bits = n_seqs > 1 ? bits_for((uint64_t)n_seqs - 1) : 0;
@@ -1976,7 +2035,8 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	const uint64_t n_loc = local->n_total;
 	SortPlan top;  // one digit: the top 8 key bits
 	top.n_passes = 1;
-	top.bits[0] = sd.key_bits < 8 ? sd.key_bits : 8;
+	// the top bits of the MASKED key (never the strand flag in bit 0: both strands of a seed belong to one owner)
+	top.bits[0] = sd.key_bits - 1 < 8 ? sd.key_bits - 1 : 8;
 	top.shift[0] = sd.key_bits - top.bits[0];
 	DevBuf<uint8_t> keys_loc(c, n_loc * K);
 	DevBuf<uint32_t> vals_loc(c, n_loc), hist_top(c, 256);
@@ -1984,9 +2044,9 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	if (n_loc)
 		launch_extract(c, local->packed.p, local->d_meta.p, local->meta.data(), count, sd, pos_bits, K == 8, keys_loc.p,
 		               vals_loc.p, hist_top.p, 1, top.shift, top.bits);
-	DevBuf<uint8_t> key_pos_own;  // (declared before the guard: released only after the side stream is done with it)
-	uint8_t* key_pos_all_p = nullptr;
-	struct SideGuard {  // whatever way this function is left, the side stream must be done with keys_loc / key_pos_all
+	DevBuf<uint2> planes_own;  // (declared before the guard: released only after the side stream is done with it)
+	const uint2* planes_all_p = nullptr;
+	struct SideGuard {  // whatever way this function is left, the side stream must be done with local->planes / planes_all
 		Comm* c;
 		~SideGuard() { comm_side_synchronize(c); }
 	} side_guard{comm};
@@ -2004,31 +2064,38 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		for (int p = 0; p < W; ++p) g_hist[b] += h_all[(size_t)256 * p + b];
 	}
 	DevBuf<uint64_t> d_u64(c, 256 + (size_t)4 * W * W + 4 * W);
-	// ---- position-ordered keys of ALL sequences on every rank (window tests read any sequence): started on the
-	// side communicator, needed only by the extension at the end
-	// (written straight into every peer's window over NVLink; NCCL all-gather where CUDA IPC is not available).
+	// ---- the packed sequences (as bit planes, 0.25 B per base) of ALL sequences on every rank: the window tests of the
+	// extension read any sequence.  Started on the side stream, needed only at the end; written straight into every
+	// peer's window over NVLink (NCCL send/recv where CUDA IPC is not available).
 	// Only now: a peer may write this rank's window once this rank has left the previous call, and the histogram
 	// all-gather above is the first point that proves it.
-	const bool direct_keys = !getenv("MEMS_NO_PEER_WINDOWS") && comm_window_reserve(comm, 2, s_total * K);
+	const bool direct_planes = !getenv("MEMS_NO_PEER_WINDOWS") && comm_window_reserve(comm, 2, words_total * 4);
 	{
 		std::vector<uint64_t> bytes(W), offs(W);
 		for (int p = 0; p < W; ++p) {
 			int f, n;
 			shard_sequence_range(n_seqs, p, W, &f, &n);
-			uint64_t cnt = 0;
-			for (int g = f; g < f + n; ++g) cnt += gmeta[g].n_seeds;
-			bytes[p] = cnt * K;
-			offs[p] = (n ? gmeta[f].seed_off : 0) * K;
+			uint64_t words = 0;
+			for (int g = f; g < f + n; ++g) words += seq_packed_words(lens[g]);
+			bytes[p] = words * 4;
+			offs[p] = (n ? gmeta[f].word_off : kLeadWords) * 4;
 		}
-		KernelScope ks(c, direct_keys ? "peer_all_gather_keys" : "nccl_all_gather_keys", (double)s_total * K);
-		if (direct_keys) {
-			key_pos_all_p = static_cast<uint8_t*>(comm_window_local(comm, 2));
-			comm_window_all_gather(comm, 2, keys_loc.p, bytes[R], offs[R]);
+		// this rank's block has the global layout shifted to start behind its own lead pad
+		const uint2* mine = count ? local->planes.p + kLeadWords / 2 : nullptr;
+		KernelScope ks(c, direct_planes ? "peer_all_gather_planes" : "nccl_all_gather_planes", (double)words_total * 4);
+		uint2* dst;
+		if (direct_planes) {
+			dst = static_cast<uint2*>(comm_window_local(comm, 2));
+			comm_window_all_gather(comm, 2, mine, bytes[R], offs[R]);
 		} else {
-			key_pos_own = DevBuf<uint8_t>(c, s_total * K);
-			key_pos_all_p = key_pos_own.p;
-			comm_all_gather_v(comm, keys_loc.p, key_pos_all_p, bytes.data(), offs.data());
+			planes_own = DevBuf<uint2>(c, words_total / 2);
+			dst = planes_own.p;
+			comm_all_gather_v(comm, mine, dst, bytes.data(), offs.data());
 		}
+		// lead and tail pad: chunks of the window test may reach into them (their content never decides a window)
+		MEMS_CUDA(cudaMemsetAsync(dst, 0, kLeadWords * 4, c->stream));
+		MEMS_CUDA(cudaMemsetAsync(reinterpret_cast<uint32_t*>(dst) + (words_total - kTailWords), 0, kTailWords * 4, c->stream));
+		planes_all_p = dst;
 	}
 
 	mark("pack+extract+histogram");
@@ -2153,7 +2220,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
 	a1.warp_budget = kWarpProbeBudget;
 	a1.cta_budget = kCtaRoundBudget;
-	a1.packed = nullptr;
+	a1.planes = nullptr;
 	a1.meta = d_gmeta.p;
 	HitSet hits1;
 	if (n_recv >= 2) find_hits<KeyT>(c, a1, hits1);
@@ -2280,7 +2347,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	mark("all-to-all hits");
 	// ---- 7. this rank's diagonals: segments, walks, components
 	comm_all_gather_v_wait(comm);  // the gathered keys are needed from here on
-	if (direct_keys) comm_window_barrier(comm);  // ... on every rank: the peers' copies into this rank's window are done
+	if (direct_planes) comm_window_barrier(comm);  // ... on every rank: the peers' copies into this rank's window are done
 	out.n_hits = n2;
 	if (n2 == 0) return;
 	HitSet hits2;
@@ -2300,7 +2367,8 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a2.keys = keys2.p;
 	a2.vals = r_mval_p;
 	a2.n = (uint32_t)n_mem2;
-	extend_hits<KeyT>(ctx, a2, reinterpret_cast<const KeyT*>(key_pos_all_p), sd.L, hits2, order, 40000u, out);
+	a2.planes = planes_all_p;
+	extend_hits<KeyT>(ctx, a2, sd, hits2, order, 40000u, out);
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 	mark("extend + emit + D2H");
 }

@@ -70,6 +70,35 @@ void launch_pack(Ctx* c, const uint8_t* d_ascii, uint32_t* d_packed, const SeqMe
 }
 
 // ------------------------------------------------------------------------------------------------
+// bit planes: the 2-bit codes of 32 consecutive bases as one word of high bits and one of low bits, base j of the
+// group in bit j.  Same bytes as the packed words, re-laid for the window test of match extension: XOR-ing two
+// members' planes gives one disagreement bit per base without any 2-bit fold (kernels_match.cu, WarpHit::probe).
+__device__ __forceinline__ uint32_t plane16(uint32_t w) {  // bits 0,2,..,30 of w (base 15 first) -> bit b = base b
+	w &= 0x55555555u;
+	w = (w | (w >> 1)) & 0x33333333u;
+	w = (w | (w >> 2)) & 0x0f0f0f0fu;
+	w = (w | (w >> 4)) & 0x00ff00ffu;
+	w = (w | (w >> 8)) & 0x0000ffffu;
+	return __brev(w) >> 16;
+}
+
+__global__ void __launch_bounds__(256)
+planes_kernel(const uint2* __restrict__ packed2, uint2* __restrict__ planes, uint64_t n) {
+	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const uint2 w = packed2[i];  // bases 32i..32i+15 in w.x, 32i+16..32i+31 in w.y (MSB-first pairs)
+	planes[i] = make_uint2(plane16(w.x >> 1) | (plane16(w.y >> 1) << 16), plane16(w.x) | (plane16(w.y) << 16));
+}
+
+void launch_planes(Ctx* c, const uint32_t* d_packed, uint2* d_planes, uint64_t n_words) {
+	const uint64_t n = n_words / 2;
+	if (n == 0) return;
+	KernelScope ks(c, "planes", (double)n_words * 8.0);
+	planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint2*>(d_packed), d_planes, n);
+	MEMS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
 // extract: one thread per 8 consecutive seed positions of one sequence, chosen so that the thread's 8 slots of
 // the union arrays start on a 16-byte boundary: keys and values leave as 128-bit stores.  The thread reads the
 // four packed words under its positions once (coalesced, L1 serves the overlap between neighbours), shifts them
