@@ -558,11 +558,18 @@ struct WarpHit {
 		}
 		const bool live = m != 0u;  // lanes without a valid window load nothing (their addresses may lie outside the buffer)
 		if (!__any_sync(0xffffffffu, live)) return 0u;
+		// Every member is read in the orientation of the hit's first member: members of the other orientation load the
+		// mirrored chunk and reverse it (the complement is folded into the XOR).  The reference the others are compared
+		// with is simply the first union entry, whichever orientation it has; cared base i of a window sits at offset
+		// off[i] for members of the first orientation and at mirror[i] for the others (the same for palindromic patterns).
+		const uint2 e0 = s_mem[0];
+		const bool ref_rev = (e0.y >> 31) != 0u;
+		const uint8_t* ref_off = ref_rev ? shape.mirror : shape.off;
+		const uint8_t* oth_off = ref_rev ? shape.off : shape.mirror;
 		Chunk ref{0, 0, 0, 0};
-		{
-			const uint2 e0 = s_mem[0];
+		if (live) {
 			const int64_t base0 = (int64_t)(((uint64_t)(e0.y & 0x7fffffffu) << 32) | e0.x);
-			if (live) ref = load_chunk(a.planes, base0 + klo);
+			ref = ref_rev ? reverse_chunk(load_chunk(a.planes, base0 - klo + (L - 1) - 63)) : load_chunk(a.planes, base0 + klo);
 		}
 		uint32_t d0 = 0, d1 = 0;  // disagreement per base of the chunk, all members
 		for (uint32_t first = 0; first < len; first += kMemberTile) {
@@ -571,29 +578,23 @@ struct WarpHit {
 			for (uint32_t t = first ? 0u : 1u; t < cnt; ++t) {
 				const uint2 e = s_mem[t];
 				const int64_t base = (int64_t)(((uint64_t)(e.y & 0x7fffffffu) << 32) | e.x);
-				if (!(e.y >> 31)) {  // warp-uniform
-					if (live) {
-						const Chunk c = load_chunk(a.planes, base + klo);
-						d0 |= (c.h0 ^ ref.h0) | (c.l0 ^ ref.l0);
-						d1 |= (c.h1 ^ ref.h1) | (c.l1 ^ ref.l1);
-					}
+				const bool rev = (e.y >> 31) != 0u;  // warp-uniform
+				if (!live) continue;
+				// window klo + j of a reverse member starts at base - (klo + j) and is read on the other strand: base t of
+				// the reversed chunk that ENDS at base - klo + L - 1 is (the complement of) what window j holds at offset t - j
+				const Chunk c = rev ? reverse_chunk(load_chunk(a.planes, base - klo + (L - 1) - 63)) : load_chunk(a.planes, base + klo);
+				if (rev == ref_rev) {
+					d0 |= (c.h0 ^ ref.h0) | (c.l0 ^ ref.l0);
+					d1 |= (c.h1 ^ ref.h1) | (c.l1 ^ ref.l1);
+				} else if (shape.palindromic) {
+					d0 |= ~(c.h0 ^ ref.h0) | ~(c.l0 ^ ref.l0);
+					d1 |= ~(c.h1 ^ ref.h1) | ~(c.l1 ^ ref.l1);
 				} else {
-					// window klo + j of this member starts at base - (klo + j) and is read on the other strand: base t of the
-					// reversed chunk that ENDS at base - klo + L - 1 is the complement of what window j holds at offset t - j
-					if (live) {
-						const Chunk c = reverse_chunk(load_chunk(a.planes, base - klo + (L - 1) - 63));
-						if (shape.palindromic) {
-							d0 |= ~(c.h0 ^ ref.h0) | ~(c.l0 ^ ref.l0);
-							d1 |= ~(c.h1 ^ ref.h1) | ~(c.l1 ^ ref.l1);
-						} else {
-							// cared base i of the first member's window (offset off[i]) meets offset mirror[i] of this one
-							for (int i = 0; i < w; ++i) {
-								const uint32_t o = shape.off[i], q = shape.mirror[i];
-								const uint32_t x = ~(__funnelshift_r(c.h0, c.h1, q) ^ __funnelshift_r(ref.h0, ref.h1, o)) |
-								                   ~(__funnelshift_r(c.l0, c.l1, q) ^ __funnelshift_r(ref.l0, ref.l1, o));
-								m &= ~x;
-							}
-						}
+					for (int i = 0; i < w; ++i) {
+						const uint32_t o = ref_off[i], q = oth_off[i];
+						const uint32_t x = ~(__funnelshift_r(c.h0, c.h1, q) ^ __funnelshift_r(ref.h0, ref.h1, o)) |
+						                   ~(__funnelshift_r(c.l0, c.l1, q) ^ __funnelshift_r(ref.l0, ref.l1, o));
+						m &= ~x;
 					}
 				}
 			}
@@ -601,13 +602,13 @@ struct WarpHit {
 		}
 		if (len > kMemberTile) load_tile(0);
 		const uint32_t ok0 = ~d0, ok1 = ~d1;
-		for (int i = 0; i < w; ++i) m &= __funnelshift_r(ok0, ok1, shape.off[i]);
+		for (int i = 0; i < w; ++i) m &= __funnelshift_r(ok0, ok1, ref_off[i]);
 		if (any_reverse && !(w & 1)) {
 			// a mer equal to its own reverse complement carries the same strand flag on both strands: never a match
 			// between opposite orientations.  Cared base i must be the complement of cared base w-1-i.
 			uint32_t self = 0xffffffffu;
 			for (int i = 0; i < w / 2; ++i) {
-				const uint32_t o = shape.off[i], q = shape.off[w - 1 - i];
+				const uint32_t o = ref_off[i], q = ref_off[w - 1 - i];
 				self &= (__funnelshift_r(ref.h0, ref.h1, o) ^ __funnelshift_r(ref.h0, ref.h1, q)) &
 				        (__funnelshift_r(ref.l0, ref.l1, o) ^ __funnelshift_r(ref.l0, ref.l1, q));
 			}
@@ -629,11 +630,11 @@ struct WarpHit {
 		return 32 * z + __ffs((int)__shfl_sync(0xffffffffu, m, z));
 	}
 	// Where a chain of matches at most L apart breaks inside one probe.  The chain starts at distance `from`
-	// (0 = the window the walk stands on, else a set bit of m); matches before `from` are ignored.  Every match covers
-	// the L distances after it; the chain ends at the match x whose reach x+1..x+L holds no further match, i.e.
-	// x + L + 1 is the first distance >= from that nothing covers.  Returns that first uncovered distance (<= kProbeWindows:
-	// the gap then lies completely inside the probed windows, the chain's last match is L + 1 before it), or 0 when the
-	// chain runs on to the end of the probe.  Lane-parallel: a lane smears its word and its predecessor's by 0..L bits.
+	// (0 = the window the walk stands on, else a set bit of m); matches before `from` are ignored.  A distance d is
+	// "open" when none of the L windows before it (d-L .. d-1) matches; the chain's last match x is followed by L
+	// mismatches, so the first open distance after `from` is x + L + 1 (whether or not that window itself matches).
+	// Returns it (<= kProbeWindows: the gap then lies completely inside the probed windows), or 0 when the chain runs
+	// on to the end of the probe.  Lane-parallel: a lane smears its word and its predecessor's by 1..L bits.
 	__device__ int chain_break(uint32_t m, int from) const {
 		const int L = shape.L;
 		// matches before `from` do not count; distance 0 sits in bit 31 of lane 0's predecessor word
@@ -645,18 +646,18 @@ struct WarpHit {
 		}
 		uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
 		if (lane == 0) prev = from == 0 ? 0x80000000u : 0u;
-		// cover = bits of OR_{s = 0..L} ((cur:prev) << s) that fall into cur's word: doubling, then one more step
-		uint32_t hi = cur, lo = prev;
-		int have = 1;  // shifts 0 .. have-1 are in
-		while (2 * have <= L + 1) {
+		// reach = bits of OR_{s = 1..L} ((cur:prev) << s) that fall into cur's word: shift by one, double, one more step
+		uint32_t hi = __funnelshift_l(prev, cur, 1), lo = prev << 1;
+		int have = 1;  // shifts 1 .. have are in
+		while (2 * have <= L) {
 			hi |= __funnelshift_l(lo, hi, have);
 			lo |= lo << have;
 			have *= 2;
 		}
-		if (have < L + 1) hi |= __funnelshift_l(lo, hi, L + 1 - have);
-		uint32_t open = ~hi;  // distances nothing covers
-		if (from > 0) {       // ... from `from` on
-			const int fl = (from - 1) >> 5, fb = (from - 1) & 31;
+		if (have < L) hi |= __funnelshift_l(lo, hi, L - have);
+		uint32_t open = ~hi;  // distances whose L predecessors hold no match ...
+		{                      // ... after `from`
+			const int fl = from >> 5, fb = from & 31;
 			if (lane < fl) open = 0u;
 			else if (lane == fl) open &= 0xffffffffu << fb;
 		}
