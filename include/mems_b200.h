@@ -128,6 +128,7 @@ typedef struct {
 	uint64_t n_segments;  /* groups of hits connected without a window test (extension work items) */
 	uint32_t seq_count;   /* sequences searched */
 	uint32_t seed_length;
+	double host_replay_ms; /* host time of the reference-order table replay (ORDER_REFERENCE / RepeatHash), else 0 */
 } mems_matches_info_t;
 
 /* MemHash/RepeatHash/PairwiseMatchFinder::FindMatches (MemHash.cpp:109-127) over n_smls sorted mer

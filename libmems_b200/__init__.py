@@ -39,7 +39,8 @@ class MatchParams(ctypes.Structure):
 
 class MatchesInfo(ctypes.Structure):
     _fields_ = [("n_matches", _u64), ("n_flat", _u64), ("n_hits", _u64), ("mem_count", _u64), ("collisions", _u64),
-                ("max_run", _u64), ("n_segments", _u64), ("seq_count", ctypes.c_uint32), ("seed_length", ctypes.c_uint32)]
+                ("max_run", _u64), ("n_segments", _u64), ("seq_count", ctypes.c_uint32), ("seed_length", ctypes.c_uint32),
+                ("host_replay_ms", ctypes.c_double)]
 
 
 class ProfileEntry(ctypes.Structure):
@@ -272,7 +273,7 @@ class Context:
         keep = _MatchHandle(self.lib, h)
         info = MatchesInfo()
         self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
-        d = {k: int(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        d = {k: (float if k == "host_replay_ms" else int)(getattr(info, k)) for k, _ in MatchesInfo._fields_}
         if info.n_flat == 0:
             return np.zeros(0, np.int64), d
         # zero-copy view of the library's (page-locked) result buffer; it lives as long as the array does
@@ -302,7 +303,7 @@ class Context:
         keep = _MatchHandle(self.lib, h)
         info = MatchesInfo()
         self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
-        d = {k: int(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        d = {k: (float if k == "host_replay_ms" else int)(getattr(info, k)) for k, _ in MatchesInfo._fields_}
         if info.n_flat == 0:
             return np.zeros(0, np.int64), d
         view = np.ctypeslib.as_array(self.lib.mems_matches_data(h), shape=(int(info.n_flat),))

@@ -106,10 +106,13 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 	DevBuf<uint8_t> ascii(c, total_bytes + 16);
 	DevBuf<uint32_t> gap_flag(c, 1);
 	MEMS_CUDA(cudaMemsetAsync(gap_flag.p, 0, sizeof(uint32_t), c->stream));
-	for (int g = 0; g < n_seqs; ++g)
-		if (lens[g])
-			// cudaMemcpyDefault: seqs[g] may be pageable or pinned host memory, or already a device pointer
-			MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyDefault, c->stream));
+	{
+		CopyScope cs(c, "copy_in_sequences", (double)total_bytes);
+		for (int g = 0; g < n_seqs; ++g)
+			if (lens[g])
+				// cudaMemcpyDefault: seqs[g] may be pageable or pinned host memory, or already a device pointer
+				MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyDefault, c->stream));
+	}
 	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
 	b->planes = DevBuf<uint2>(c, b->total_words / 2);
 	launch_planes(c, b->packed.p, b->planes.p, b->total_words);

@@ -309,6 +309,7 @@ int mems_matches_info(mems_matches_t m, mems_matches_info_t* out) {
 	out->n_segments = m->r.n_segments;
 	out->seq_count = m->r.seq_count;
 	out->seed_length = m->r.seed_length;
+	out->host_replay_ms = m->r.host_replay_ms;
 	return MEMS_OK;
 }
 

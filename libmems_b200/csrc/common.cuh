@@ -136,6 +136,18 @@ struct KernelScope {
 	}
 };
 
+// a copy between host and device, timed like a kernel when profiling is on (names start with "copy_"; not a launch)
+struct CopyScope {
+	Ctx* c;
+	const char* name;
+	CopyScope(Ctx* ctx, const char* nm, double bytes) : c(ctx), name(nm) {
+		if (c->profiling) c->prof_begin(nm, bytes);
+	}
+	~CopyScope() {
+		if (c->profiling) c->prof_end(name);
+	}
+};
+
 SeedDesc make_seed_desc(uint64_t seed);  // throws Error(MEMS_ERR_INVALID/UNSUPPORTED)
 
 // ---- kernels_sml.cu ----
@@ -283,6 +295,7 @@ struct MatchResult {
 	FlatRecords flat;
 	uint64_t n_matches = 0, n_hits = 0, mem_count = 0, collisions = 0, max_run = 0, n_segments = 0;
 	uint32_t seq_count = 0, seed_length = 0;
+	double host_replay_ms = 0;
 };
 // The reference's MemHash::mem_table replayed on the host (ORDER_REFERENCE): buckets of stored, extended matches.
 // Persistent instances let several FindMatches calls (different seed patterns) accumulate into one table

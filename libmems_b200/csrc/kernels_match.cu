@@ -1572,7 +1572,10 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	out.flat.pinned = (int64_t*)c->pinned_get((size_t)n_flat * sizeof(int64_t), &out.flat.pinned_cap);
 	out.flat.pinned_n = n_flat;
 	const int64_t* raw = out.flat.pinned;
-	MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+	{
+		CopyScope cs(c, "copy_out_matches", (double)n_flat * sizeof(int64_t));
+		MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+	}
 
 	if (order != MEMS_ORDER_REFERENCE) {
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
@@ -1629,6 +1632,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	}
 
 	// ---- ORDER_REFERENCE: replay the reference's hash table over (hit, extended match) on the host
+	const auto t_replay = std::chrono::steady_clock::now();
 	const bool trace = getenv("MEMS_TRACE") != nullptr;
 	auto t_mark = std::chrono::steady_clock::now();
 	auto mark = [&](const char* what) {
@@ -1806,6 +1810,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	out.flat.release();
 	out.n_matches = stored.size();
 	mark("output list");
+	out.host_replay_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_replay).count();
 }
 
 static void emit_table(const HashTable& T, MatchResult& out) {
