@@ -179,7 +179,7 @@ int mems_find_matches_sharded(mems_ctx_t ctx, mems_comm_t comm, int n_seqs, cons
  * experiments): MEMS_NO_PEER_WINDOWS=1 sharded exchanges through NCCL send/recv instead of CUDA-IPC exchange windows;
  * MEMS_PEER_SCATTER=1 the partition kernel scatters straight into the peers' windows instead of partition + DMA copies;
  * MEMS_NO_SIDE_COMM=1 no second NCCL communicator; MEMS_HOST_THREADS=n host threads of the reference-order table
- * replay (default min(16, cores)); MEMS_TRACE=1 stage timings on stderr; MEMS_TEST_* shrink budgets in tests. */
+ * replay (default min(16, cores)); MEMS_TRACE=1 stage timings on stderr. */
 
 /* ---- measurement ---- */
 /* With profiling on, every kernel launch is bracketed by CUDA events on the context's stream. */
@@ -195,6 +195,13 @@ typedef struct {
 int mems_profile_get(mems_ctx_t ctx, mems_profile_entry_t* entries, int cap, int* n);
 /* kernels launched on this context since creation / last reset (counted even with profiling off) */
 uint64_t mems_launch_count(mems_ctx_t ctx);
+
+/* ---- testing ----
+ * Shrinks internal budgets of ONE context so that small inputs reach the rare paths: hash_bits > 0 keeps only that many
+ * bits of the diagonal hash (bucket collisions, de-dup of marked components); walk_budget > 0 = probes / rounds a walk
+ * gets before it moves on to the CTA-wide and grid-wide walkers.  0 restores production behaviour.  Results are the
+ * same either way. */
+int mems_test_hooks(mems_ctx_t ctx, int hash_bits, int walk_budget);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ EXPORTS = [
     "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_shard_exchange_plan", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
+    "mems_test_hooks",
 ]
 
 _lib = None
@@ -118,6 +119,7 @@ def load():
     lib.mems_profile_get.argtypes = [_vp, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.mems_launch_count.argtypes = [_vp]
     lib.mems_launch_count.restype = _u64
+    lib.mems_test_hooks.argtypes = [_vp, ctypes.c_int, ctypes.c_int]
     _lib = lib
     return lib
 
@@ -327,6 +329,10 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.mems_launch_count(self.h))
+
+    def set_test_hooks(self, hash_bits=0, walk_budget=0):
+        """Testing only: shrink the diagonal hash / the walk budgets of this context (see mems_test_hooks)."""
+        self._check(self.lib.mems_test_hooks(self.h, int(hash_bits), int(walk_budget)))
 
 
 class HashTable:

@@ -116,20 +116,47 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
 	b->planes = DevBuf<uint2>(c, b->total_words / 2);
 	launch_planes(c, b->packed.p, b->planes.p, b->total_words);
-	uint32_t gap = 0;
-	MEMS_CUDA(cudaMemcpyAsync(&gap, gap_flag.p, sizeof gap, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
-	if (gap)
+	// the flag travels to the host behind the pack; whoever queued the rest of the build calls check_gap()
+	b->h_gap = c->host_words_get();
+	b->gap_ready = c->get_event();
+	MEMS_CUDA(cudaMemcpyAsync(b->h_gap, gap_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaEventRecord(b->gap_ready, c->stream));
+	return b;
+}
+
+bool Batch::take_gap_flag() {
+	if (!gap_ready) return false;
+	Ctx* c = ctx.get();
+	const cudaError_t e = cudaEventSynchronize(gap_ready);
+	const bool gap = e == cudaSuccess && *h_gap != 0u;
+	c->event_put(gap_ready);
+	c->host_words_put(h_gap);
+	gap_ready = nullptr;
+	h_gap = nullptr;
+	MEMS_CUDA(e);
+	return gap;
+}
+
+void Batch::check_gap() {
+	if (take_gap_flag())
 		throw Error(MEMS_ERR_GAP, "Gap in genome sequence: input sequences must be unaligned and ungapped "
 		                          "(SortedMerList.cpp:433-437)");
-	return b;
+}
+
+Batch::~Batch() {
+	if (gap_ready) {
+		cudaEventSynchronize(gap_ready);  // the copy into h_gap must have landed before the word is reused
+		ctx->event_put(gap_ready);
+		ctx->host_words_put(h_gap);
+	}
 }
 
 std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
                                               const uint64_t* lens, uint64_t seed) {
 	if (n_seqs < 1) throw Error(MEMS_ERR_INVALID, "need at least one sequence");
 	auto b = prepare_batch_from_ascii(ctx, n_seqs, seqs, lens, seed, 0, 0, 0);
-	extract_and_sort(*b);
+	extract_and_sort(*b);  // queued behind the pack; the GPU works on it while the host looks at the gap flag
+	b->check_gap();
 	return b;
 }
 

@@ -429,4 +429,11 @@ int mems_profile_get(mems_ctx_t ctx, mems_profile_entry_t* entries, int cap, int
 
 uint64_t mems_launch_count(mems_ctx_t ctx) { return ctx ? ctx->c->launch_count : 0; }
 
+int mems_test_hooks(mems_ctx_t ctx, int hash_bits, int walk_budget) {
+	if (!ctx || hash_bits < 0 || hash_bits > 63 || walk_budget < 0) return fail(nullptr, MEMS_ERR_INVALID, "bad arguments");
+	ctx->c->test_hash_bits = hash_bits;
+	ctx->c->test_walk_budget = walk_budget;
+	return MEMS_OK;
+}
+
 }  // extern "C"

@@ -83,6 +83,9 @@ struct Ctx {
 	std::map<std::string, ProfEntry> prof;
 	std::vector<cudaEvent_t> free_events;
 	std::string last_error;
+	// test hooks (mems_test_hooks): 0 = production behaviour
+	int test_hash_bits = 0;    // keep only this many bits of the diagonal hash (forces bucket collisions)
+	int test_walk_budget = 0;  // probes / rounds before a walk moves on to the next larger walker
 
 	void* alloc(size_t bytes);  // stream-ordered
 	void free(void* p);
@@ -90,6 +93,11 @@ struct Ctx {
 	std::vector<std::pair<void*, size_t>> pinned_free;
 	void* pinned_get(size_t bytes, size_t* capacity);
 	void pinned_put(void* p, size_t capacity);
+	// small page-locked words for counters the host waits on (asynchronous D2H needs page-locked memory)
+	std::vector<uint32_t*> host_words_free;
+	uint32_t* host_words_get();  // 16 uint32
+	void host_words_put(uint32_t* p);
+	void event_put(cudaEvent_t e) { free_events.push_back(e); }
 	cudaEvent_t get_event();
 	void prof_begin(const char* name, double bytes);
 	void prof_end(const char* name);
@@ -218,6 +226,14 @@ struct Batch {
 	uint64_t total_words = 0;  // words of `packed`, lead and tail pad included
 	DevBuf<uint32_t> packed;
 	DevBuf<uint2> planes;      // bit planes of `packed` (launch_planes): what the window test of match extension reads
+	// '-' in a sequence (SortedMerList.cpp:433-437 throws): pack_kernel raises a flag that is copied to page-locked host
+	// memory behind the pack; check_gap() waits for that copy only — the work queued after it keeps the GPU busy meanwhile
+	uint32_t* h_gap = nullptr;
+	cudaEvent_t gap_ready = nullptr;
+	bool gap_pending() const { return gap_ready != nullptr; }
+	bool take_gap_flag();  // waits for the flag, releases event and host word; true = a gap was seen
+	void check_gap();      // take_gap_flag() and throw MEMS_ERR_GAP if set
+	~Batch();
 	DevBuf<uint8_t> keys_by_pos;  // compact key of every seed position, in (seq, position) order (extraction output)
 	DevBuf<uint8_t> keys;      // union, ascending compact key (u32 or u64); ties in (seq, position) order
 	DevBuf<uint32_t> vals;     // union, (seq << pos_bits) | position

@@ -42,6 +42,21 @@ void Ctx::pinned_put(void* p, size_t capacity) {
 	pinned_free.push_back({p, capacity});
 }
 
+uint32_t* Ctx::host_words_get() {
+	if (!host_words_free.empty()) {
+		uint32_t* p = host_words_free.back();
+		host_words_free.pop_back();
+		return p;
+	}
+	uint32_t* p = nullptr;
+	MEMS_CUDA(cudaHostAlloc((void**)&p, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+	return p;
+}
+
+void Ctx::host_words_put(uint32_t* p) {
+	if (p) host_words_free.push_back(p);
+}
+
 cudaEvent_t Ctx::get_event() {
 	if (!free_events.empty()) {
 		cudaEvent_t e = free_events.back();
@@ -95,6 +110,7 @@ Ctx::~Ctx() {
 		}
 	for (auto e : free_events) cudaEventDestroy(e);
 	for (auto& pb : pinned_free) cudaFreeHost(pb.first);
+	for (uint32_t* p : host_words_free) cudaFreeHost(p);
 	if (own_stream && stream) cudaStreamDestroy(stream);
 }
 

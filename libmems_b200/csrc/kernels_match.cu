@@ -355,6 +355,29 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 	}
 }
 
+// described hits (their keys came with them): identity permutation + the digit histograms of the sort
+__global__ void __launch_bounds__(256)
+hit_histogram_kernel(const uint64_t* __restrict__ hkey, uint32_t n_hits, uint32_t* __restrict__ hid, uint32_t* __restrict__ hist,
+                     SortPlan plan) {
+	__shared__ uint32_t s_hist[kMaxHitPasses * 256];
+	for (int i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) s_hist[i] = 0;
+	__syncthreads();
+	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += gridDim.x * blockDim.x) {
+		const uint64_t key = hkey[h];
+		hid[h] = h;
+#pragma unroll
+		for (int q = 0; q < kMaxHitPasses; ++q) {
+			if (q >= plan.n_passes) break;
+			atomicAdd(&s_hist[q * 256 + ((uint32_t)(key >> plan.shift[q]) & ((1u << plan.bits[q]) - 1u))], 1u);
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) {
+		uint32_t v = s_hist[i];
+		if (v) atomicAdd(&hist[i], v);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ 4. segments
 // same diagonal: same member sequences, same relative orientations, same offsets to the first member
 template <class KeyT>
@@ -1111,6 +1134,16 @@ __global__ void emit_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hke
 	}
 }
 
+// the (few) components next to a foreign diagonal of their hash bucket, with the offset of their record: the host
+// compares just these for duplicates
+__global__ void suspect_list_kernel(const uint8_t* __restrict__ comp_suspect, const uint32_t* __restrict__ rec_off, uint32_t n_comp,
+                                    uint2* __restrict__ list, uint32_t cap, uint32_t* __restrict__ count) {
+	const uint32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (comp >= n_comp || !comp_suspect[comp]) return;
+	const uint32_t at = atomicAdd(count, 1u);
+	if (at < cap) list[at] = make_uint2(comp, rec_off[comp]);
+}
+
 // hit members in merged order, for the host-side table emulation (ORDER_REFERENCE)
 template <class KeyT>
 __global__ void gather_members_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len,
@@ -1402,7 +1435,7 @@ static void find_pair_hits(Ctx* c, const MatchArgs& a, HitSet& hits, DevBuf<uint
 // ---- stage B: hits (members readable through a.keys / a.vals) -> extended, distinct matches
 template <class KeyT>
 static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const SeedDesc& sd, HitSet& hits, int order,
-                        uint32_t table_size, MatchResult& out, HashTable* persistent = nullptr) {
+                        uint32_t table_size, MatchResult& out, HashTable* persistent = nullptr, uint64_t* given_hkey = nullptr) {
 	Ctx* c = ctx.get();
 	const int L = sd.L;
 	const int mode = a.mode;
@@ -1413,23 +1446,29 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(uint32_t), c->stream));
 
 	// ---- 2. describe + 3. sort by (diagonal hash, first-member position)
+	// (given_hkey: the hits arrive described — sharded path, where the key travelled with the hit through the
+	// diagonal exchange; only the identity permutation and the digit histograms are made here)
 	SortPlan plan = make_sort_plan(64);
-	DevBuf<uint64_t> hk_a(c, n_hits), hk_b(c, n_hits);
+	DevBuf<uint64_t> hk_a(c, given_hkey ? 0 : n_hits), hk_b(c, n_hits);
 	DevBuf<uint32_t> hid_a(c, n_hits), hid_b(c, n_hits), hist(c, (size_t)plan.n_passes * 256);
 	MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)plan.n_passes * 256 * sizeof(uint32_t), c->stream));
 	const uint32_t hit_blocks = (n_hits + 255) / 256;
-	{
+	const uint32_t describe_blocks = std::min(hit_blocks, (uint32_t)c->sm_count * 8u);
+	if (given_hkey) {
+		KernelScope ks(c, "hit_histogram", (double)n_hits * 8.0);
+		hit_histogram_kernel<<<describe_blocks, 256, 0, c->stream>>>(given_hkey, n_hits, hid_a.p, hist.p, plan);
+		MEMS_CUDA(cudaGetLastError());
+	} else {
 		KernelScope ks(c, "hit_describe");
-		const uint32_t describe_blocks = std::min(hit_blocks, (uint32_t)c->sm_count * 8u);
 		hit_describe_kernel<KeyT><<<describe_blocks, 256, 0, c->stream>>>(a, hit_start.p, hit_len.p, n_hits, hk_a.p, hid_a.p,
 		                                                                  hist.p, plan);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	void* kp[2] = {hk_a.p, hk_b.p};
+	void* kp[2] = {given_hkey ? given_hkey : hk_a.p, hk_b.p};
 	uint32_t* vp[2] = {hid_a.p, hid_b.p};
 	const int r = radix_sort_pairs(c, true, kp, vp, n_hits, plan, hist.p, "hit_sort_pass");
-	const uint64_t* hkey = r ? hk_b.p : hk_a.p;
-	const uint32_t* hid = r ? hid_b.p : hid_a.p;
+	const uint64_t* hkey = (const uint64_t*)kp[r];
+	const uint32_t* hid = vp[r];
 
 	// ---- 4. segments
 	DevBuf<uint8_t> flags(c, n_hits), suspect(c, n_hits);
@@ -1559,6 +1598,19 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, rec_size.p, rec_off.p, n_comp, scalars.p + 5);
+	const uint32_t sus_cap = 1u << 16;
+	DevBuf<uint2> sus_list(c, collision_seen ? sus_cap : 1);
+	DevBuf<uint32_t> sus_count(c, 1);
+	uint32_t h_sus_count = 0;
+	if (collision_seen) {
+		MEMS_CUDA(cudaMemsetAsync(sus_count.p, 0, sizeof(uint32_t), c->stream));
+		KernelScope ks(c, "suspect_list");
+		suspect_list_kernel<<<comp_blocks, 256, 0, c->stream>>>(comp_suspect.p, rec_off.p, n_comp, sus_list.p, sus_cap, sus_count.p);
+		MEMS_CUDA(cudaGetLastError());
+		MEMS_CUDA(cudaMemcpyAsync(&h_sus_count, sus_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	}
+	if (mode != MEMS_MODE_REPEAT && (uint64_t)n_comp * (uint64_t)(a.n_seqs + 2) > 0xffffffffull)
+		throw Error(MEMS_ERR_UNSUPPORTED, "match list larger than 2^32 values; search fewer sequences per call");
 	const uint32_t n_flat = d2h_u32(c, scalars.p + 5);
 	DevBuf<int64_t> d_flat(c, n_flat);
 	{
@@ -1586,15 +1638,24 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		std::vector<char> drop;
 		size_t n_drop = 0;
 		if (collision_seen) {
-			std::vector<uint8_t> h_suspect(n_comp);
-			MEMS_CUDA(cudaMemcpyAsync(h_suspect.data(), comp_suspect.p, n_comp, cudaMemcpyDeviceToHost, c->stream));
-			MEMS_CUDA(cudaStreamSynchronize(c->stream));
-			std::vector<std::pair<Rec, uint32_t>> sus;  // (record, component index)
-			size_t at = 0;
-			for (uint32_t k = 0; k < n_comp; ++k) {
-				if (h_suspect[k]) sus.push_back({Rec{raw + at}, k});
-				at += (size_t)raw[at] + 2;
+			uint32_t n_sus = h_sus_count;
+			std::vector<uint2> h_list(n_sus);
+			if (n_sus > sus_cap) {  // more than the list holds (never seen outside the forced-collision tests): take them all
+				std::vector<uint8_t> h_suspect(n_comp);
+				MEMS_CUDA(cudaMemcpyAsync(h_suspect.data(), comp_suspect.p, n_comp, cudaMemcpyDeviceToHost, c->stream));
+				MEMS_CUDA(cudaStreamSynchronize(c->stream));
+				h_list.clear();
+				size_t at = 0;
+				for (uint32_t k = 0; k < n_comp; ++k) {
+					if (h_suspect[k]) h_list.push_back(make_uint2(k, (uint32_t)at));
+					at += (size_t)raw[at] + 2;
+				}
+			} else if (n_sus) {
+				MEMS_CUDA(cudaMemcpyAsync(h_list.data(), sus_list.p, (size_t)n_sus * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+				MEMS_CUDA(cudaStreamSynchronize(c->stream));
 			}
+			std::vector<std::pair<Rec, uint32_t>> sus;  // (record, component index)
+			for (const uint2& e : h_list) sus.push_back({Rec{raw + e.y}, e.x});
 			std::sort(sus.begin(), sus.end(), [](const std::pair<Rec, uint32_t>& x, const std::pair<Rec, uint32_t>& y) {
 				return rec_less(x.first, y.first) || (!rec_less(y.first, x.first) && x.second < y.second);
 			});
@@ -1844,9 +1905,9 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.n_seqs = b.n_seqs;
 	a.mode = mode;
 	// the reference's "match number" puts sequence 0 in the most significant of n_seqs bits; here bit g = sequence g
-	a.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
-	a.warp_budget = getenv("MEMS_TEST_WALK_BUDGET") ? atoi(getenv("MEMS_TEST_WALK_BUDGET")) : kWarpProbeBudget;
-	a.cta_budget = getenv("MEMS_TEST_WALK_BUDGET") ? atoi(getenv("MEMS_TEST_WALK_BUDGET")) : kCtaRoundBudget;
+	a.test_hash_bits = c->test_hash_bits;
+	a.warp_budget = c->test_walk_budget ? c->test_walk_budget : kWarpProbeBudget;
+	a.cta_budget = c->test_walk_budget ? c->test_walk_budget : kCtaRoundBudget;
 	a.seq_set = 0;
 	for (int g = 0; g < b.n_seqs; ++g)
 		if ((seq_mask >> (b.n_seqs - 1 - g)) & 1) a.seq_set |= 1ull << g;
@@ -1941,18 +2002,35 @@ void shard_exchange_plan(const uint32_t* hist_all, int world, int rank, const ui
 	*max_recv = mx;
 }
 
+constexpr uint32_t kMemberStrandBit = 0x80000000u;  // exchanged members: (sequence << pos_bits | position) | strand << 31
+
+// The hits in destination (diagonal-hash) order, packed for the exchange: length word of every hit (with the
+// first-member strand flag hit_describe left in it) and its members as ONE word each — the union value with the
+// strand in bit 31 — in union order (strand-0 members first, each part ascending).  A warp takes 32 consecutive
+// hits; their member lists leave one after the other as contiguous pieces.
 template <class KeyT>
-__global__ void scatter_members_kernel(MatchArgs a, const uint32_t* __restrict__ hid, const uint32_t* __restrict__ hit_start,
-                                       const uint16_t* __restrict__ hit_len, const uint32_t* __restrict__ mem_off, uint32_t n_hits,
-                                       uint32_t* __restrict__ out_len, uint32_t* __restrict__ out_val, uint8_t* __restrict__ out_strand) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // hit i in diagonal-hash order
-	if (i >= n_hits) return;
-	const uint32_t h = hid[i], s = hit_start[h], len = hit_len[h] & ~kFirstStrandBit;
-	out_len[i] = len;
-	uint32_t at = mem_off[i];
-	for (uint32_t j = s; j < s + len; ++j, ++at) {  // union order: strand 0 members first, each part ascending
-		out_val[at] = a.vals[j];
-		out_strand[at] = (uint8_t)strand_of<KeyT>(a.keys, j);
+__global__ void __launch_bounds__(256)
+pack_hits_kernel(MatchArgs a, const uint32_t* __restrict__ hid, const uint32_t* __restrict__ hit_start,
+                 const uint16_t* __restrict__ hit_len, const uint32_t* __restrict__ mem_off, uint32_t n_hits,
+                 uint16_t* __restrict__ out_len, uint32_t* __restrict__ out_mem) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t i0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
+	if (i0 >= n_hits) return;
+	const uint32_t i = i0 + lane;
+	uint32_t s = 0, len = 0, off = 0;
+	if (i < n_hits) {
+		const uint32_t h = hid[i];
+		const uint16_t l = hit_len[h];
+		s = hit_start[h];
+		len = l & ~kFirstStrandBit;
+		off = mem_off[i];
+		out_len[i] = l;
+	}
+	const uint32_t cnt = n_hits - i0 < 32u ? n_hits - i0 : 32u;
+	for (uint32_t k = 0; k < cnt; ++k) {
+		const uint32_t sk = __shfl_sync(0xffffffffu, s, k), lk = __shfl_sync(0xffffffffu, len, k);
+		const uint32_t ok = __shfl_sync(0xffffffffu, off, k);
+		for (uint32_t t = lane; t < lk; t += 32) out_mem[ok + t] = a.vals[sk + t] | (strand_of<KeyT>(a.keys, sk + t) << 31);
 	}
 }
 
@@ -1962,31 +2040,63 @@ __global__ void sorted_len_kernel(const uint32_t* __restrict__ hid, const uint16
 	if (i < n_hits) out[i] = hit_len[hid[i]] & ~kFirstStrandBit;
 }
 
-// first index of the hit keys (grouped by their top 8 hash bits) that belongs to rank d: rank d owns the buckets
-// [ceil(256 d / world), ceil(256 (d+1) / world))
-__global__ void hit_bounds_kernel(const uint64_t* __restrict__ hkey, uint32_t n_hits, int world, uint32_t* __restrict__ bound) {
+// What this rank sends to every rank d: hits [bound[d], bound[d+1]) of the hit keys grouped by their top 8 hash bits
+// (rank d owns the buckets [ceil(256 d / world), ceil(256 (d+1) / world))) and the members of those hits.
+// counts[d] = hits, counts[world + d] = members.
+__global__ void hit_send_counts_kernel(const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ mem_off, uint32_t n_hits,
+                                       const uint32_t* __restrict__ last_len, int world, uint64_t* __restrict__ counts) {
+	__shared__ uint32_t s_bound[257], s_mbound[257];
 	const int d = threadIdx.x;
-	if (d > world) return;
-	if (d == world) {
-		bound[d] = n_hits;
-		return;
+	if (d <= world) {
+		uint32_t lo = n_hits;
+		if (d < world) {
+			const uint64_t t = (uint64_t)((256 * d + world - 1) / world);  // first bucket of rank d
+			uint32_t hi = n_hits;
+			lo = 0;
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi) / 2;
+				if ((hkey[mid] >> 56) < t) lo = mid + 1;
+				else hi = mid;
+			}
+		}
+		s_bound[d] = lo;
+		// members before hit `lo`: its offset, or the total (offset of the last hit + its length) at the end
+		s_mbound[d] = lo < n_hits ? mem_off[lo] : (n_hits ? mem_off[n_hits - 1] + *last_len : 0u);
 	}
-	const uint64_t t = (uint64_t)((256 * d + world - 1) / world);  // first bucket of rank d
-	uint32_t lo = 0, hi = n_hits;
-	while (lo < hi) {
-		const uint32_t mid = (lo + hi) / 2;
-		if ((hkey[mid] >> 56) < t) lo = mid + 1;
-		else hi = mid;
+	__syncthreads();
+	if (d < world) {
+		counts[d] = s_bound[d + 1] - s_bound[d];
+		counts[world + d] = s_mbound[d + 1] - s_mbound[d];
 	}
-	bound[d] = lo;
 }
 
+// length of the last hit in sorted order (with mem_off of that hit: the member total)
+__global__ void last_len_kernel(const uint32_t* __restrict__ slen, uint32_t n_hits, uint32_t* __restrict__ out) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) *out = n_hits ? slen[n_hits - 1] : 0u;
+}
+
+// received hits: length words -> u32 lengths (scanned into the hits' first member index) + the u16 words the
+// extension reads; received members -> union value and a key array that carries just the strand bit
 template <class KeyT>
-__global__ void received_hits_kernel(const uint32_t* __restrict__ len32, const uint8_t* __restrict__ strand, uint32_t n_hits,
-                                     uint32_t n_mem, uint16_t* __restrict__ hit_len, KeyT* __restrict__ keys) {
+__global__ void received_hits_kernel(const uint16_t* __restrict__ len16, uint32_t* __restrict__ mem, uint32_t n_hits, uint32_t n_mem,
+                                     uint32_t* __restrict__ len32, uint16_t* __restrict__ hit_len, KeyT* __restrict__ keys) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n_hits) hit_len[i] = (uint16_t)len32[i];
-	if (i < n_mem) keys[i] = (KeyT)strand[i];  // the kernels downstream read only the strand bit of a member's key
+	if (i < n_hits) {
+		const uint16_t l = len16[i];
+		hit_len[i] = l;
+		len32[i] = l & ~kFirstStrandBit;
+	}
+	if (i < n_mem) {
+		const uint32_t v = mem[i];
+		keys[i] = (KeyT)(v >> 31);  // the kernels downstream read only the strand bit of a member's key
+		mem[i] = v & ~kMemberStrandBit;
+	}
+}
+
+// A failure on one rank (a '-' in its sequences, a limit exceeded) must fail the call on EVERY rank, or the others
+// would wait forever in the next collective: each collective step first agrees on a status word.
+static void throw_agreed(int code, int rank_of_error, const char* what) {
+	throw Error(code, std::string(what) + " (reported by rank " + std::to_string(rank_of_error) + "; every rank of the sharded call fails together)");
 }
 
 template <class KeyT>
@@ -2006,7 +2116,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		if (R == 0 || ms > 6.0) fprintf(stderr, "[mems trace r%d] %-28s %8.3f ms\n", R, what, ms);
 		t_last = now;
 	};
-	// ---- global layout (identical on every rank)
+	// ---- global layout (identical on every rank; argument errors are therefore the same everywhere)
 	std::vector<SeqMeta> gmeta(n_seqs);
 	uint64_t seed_off = 0, word_off = kLeadWords;  // the same packed layout as one batch of all sequences would have
 	uint32_t max_seeds = 0;
@@ -2027,17 +2137,30 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	const uint64_t s_total = seed_off;
 	const int pos_bits = bits_for(max_seeds ? max_seeds - 1 : 0);
 	const int seq_bits = n_seqs > 1 ? bits_for((uint64_t)n_seqs - 1) : 0;
-	if (pos_bits + seq_bits > 32) throw Error(MEMS_ERR_UNSUPPORTED, "sequence count x longest sequence exceeds the 32-bit tag");
+	if (pos_bits + seq_bits > 31)
+		throw Error(MEMS_ERR_UNSUPPORTED, "sequence count x longest sequence exceeds 31 bits (the exchanged hit members carry their strand in bit 31)");
 	if (s_total >= (1ull << 31)) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^31-1 seed positions in total");
 	out.seq_count = (uint32_t)n_seqs;
 	out.seed_length = (uint32_t)sd.L;
 
-	// ---- 1. this rank's block of sequences: pack, extract, top-digit histogram
+	// ---- 1. this rank's block of sequences: pack, extract, top-digit histogram.  Local failures are collected in
+	// `my_error` and agreed on with the histogram all-gather below.
 	int first, count;
 	shard_sequence_range(n_seqs, R, W, &first, &count);
-	for (int g = first; g < first + count; ++g)
-		if (lens[g] && !seqs[g]) throw Error(MEMS_ERR_INVALID, "a sequence of this rank's block is missing");
-	auto local = prepare_batch_from_ascii(ctx, count, seqs + first, lens + first, seed, (uint32_t)first, pos_bits, seq_bits ? seq_bits : 0);
+	int my_error = MEMS_OK;
+	std::string my_error_text;
+	std::shared_ptr<Batch> local;
+	try {
+		for (int g = first; g < first + count; ++g)
+			if (lens[g] && !seqs[g]) throw Error(MEMS_ERR_INVALID, "a sequence of this rank's block is missing");
+		local = prepare_batch_from_ascii(ctx, count, seqs + first, lens + first, seed, (uint32_t)first, pos_bits, seq_bits ? seq_bits : 0);
+	} catch (const Error& e) {
+		if (e.code == MEMS_ERR_CUDA || e.code == MEMS_ERR_NCCL) throw;  // the device is gone: nothing left to agree with
+		my_error = e.code;
+		my_error_text = e.what();
+		local = prepare_batch_from_ascii(ctx, 0, seqs, lens, seed, 0, pos_bits, seq_bits ? seq_bits : 0);  // an empty block
+		count = 0;
+	}
 	const uint64_t n_loc = local->n_total;
 	SortPlan top;  // one digit: the top 8 key bits
 	top.n_passes = 1;
@@ -2045,8 +2168,8 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	top.bits[0] = sd.key_bits - 1 < 8 ? sd.key_bits - 1 : 8;
 	top.shift[0] = sd.key_bits - top.bits[0];
 	DevBuf<uint8_t> keys_loc(c, n_loc * K);
-	DevBuf<uint32_t> vals_loc(c, n_loc), hist_top(c, 256);
-	MEMS_CUDA(cudaMemsetAsync(hist_top.p, 0, 256 * sizeof(uint32_t), c->stream));
+	DevBuf<uint32_t> vals_loc(c, n_loc), hist_top(c, 256 + 2);  // [256], [257] (as one u64 slot): this rank's status word
+	MEMS_CUDA(cudaMemsetAsync(hist_top.p, 0, 258 * sizeof(uint32_t), c->stream));
 	if (n_loc)
 		launch_extract(c, local->packed.p, local->d_meta.p, local->meta.data(), count, sd, pos_bits, K == 8, keys_loc.p,
 		               vals_loc.p, hist_top.p, 1, top.shift, top.bits);
@@ -2056,20 +2179,36 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		Comm* c;
 		~SideGuard() { comm_side_synchronize(c); }
 	} side_guard{comm};
-	// every rank's top-digit histogram to every rank in one all-gather: the sum gives the owners of the key ranges,
-	// row p gives what rank p will send here — no separate all-reduce and no count exchange, one host sync
-	DevBuf<uint32_t> hist_all(c, (size_t)256 * W);
-	comm_all_gather_u64(comm, reinterpret_cast<const uint64_t*>(hist_top.p), reinterpret_cast<uint64_t*>(hist_all.p), 128);
-	std::vector<uint32_t> h_all((size_t)256 * W);
-	MEMS_CUDA(cudaMemcpyAsync(h_all.data(), hist_all.p, h_all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	// the pack has long finished by now: a '-' in this rank's sequences joins the status word
+	if (my_error == MEMS_OK && local->take_gap_flag()) {
+		my_error = MEMS_ERR_GAP;
+		my_error_text = "Gap in genome sequence: input sequences must be unaligned and ungapped (SortedMerList.cpp:433-437)";
+	}
+	{
+		const uint32_t status[2] = {(uint32_t)my_error, 0u};
+		MEMS_CUDA(cudaMemcpyAsync(hist_top.p + 256, status, sizeof status, cudaMemcpyHostToDevice, c->stream));
+	}
+	// every rank's top-digit histogram (+ status word) to every rank in one all-gather: the sum gives the owners of the
+	// key ranges, row p gives what rank p will send here — no separate all-reduce and no count exchange, one host sync
+	DevBuf<uint32_t> hist_all(c, (size_t)258 * W);
+	comm_all_gather_u64(comm, reinterpret_cast<const uint64_t*>(hist_top.p), reinterpret_cast<uint64_t*>(hist_all.p), 129);
+	std::vector<uint32_t> h_raw((size_t)258 * W), h_all((size_t)256 * W);
+	MEMS_CUDA(cudaMemcpyAsync(h_raw.data(), hist_all.p, h_raw.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	for (int p = 0; p < W; ++p) {
+		const int code = (int)h_raw[(size_t)258 * p + 256];
+		if (code != MEMS_OK) {
+			if (p == R) throw Error(my_error, my_error_text);
+			throw_agreed(code, p, code == MEMS_ERR_GAP ? "Gap in genome sequence on another rank" : "another rank failed before the exchange");
+		}
+		memcpy(&h_all[(size_t)256 * p], &h_raw[(size_t)258 * p], 256 * sizeof(uint32_t));
+	}
 	const uint32_t* h_hist32 = h_all.data() + (size_t)256 * R;
 	uint64_t g_hist[256];
 	for (int b = 0; b < 256; ++b) {
 		g_hist[b] = 0;
 		for (int p = 0; p < W; ++p) g_hist[b] += h_all[(size_t)256 * p + b];
 	}
-	DevBuf<uint64_t> d_u64(c, 256 + (size_t)4 * W * W + 4 * W);
 	// ---- the packed sequences (as bit planes, 0.25 B per base) of ALL sequences on every rank: the window tests of the
 	// extension read any sequence.  Started on the side stream, needed only at the end; written straight into every
 	// peer's window over NVLink (NCCL send/recv where CUDA IPC is not available).
@@ -2118,21 +2257,8 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		recv_counts[p] = rec_counts[(size_t)p * W + R];
 		n_recv += recv_counts[p];
 	}
-	if (n_recv > radix_max_items()) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30-1 seed records on one rank");
-	// k values per rank to every rank; all[(p * k + j) * W + d] = value j of what rank p holds for rank d
-	auto exchange_counts = [&](int k, const std::vector<uint64_t>* mine) {
-		uint64_t* d_send = d_u64.p + 256;
-		uint64_t* d_all = d_send + (size_t)k * W;
-		std::vector<uint64_t> flat((size_t)k * W);
-		for (int j = 0; j < k; ++j)
-			for (int p = 0; p < W; ++p) flat[(size_t)j * W + p] = mine[j][p];
-		MEMS_CUDA(cudaMemcpyAsync(d_send, flat.data(), flat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-		comm_all_gather_u64(comm, d_send, d_all, (size_t)k * W);
-		std::vector<uint64_t> all((size_t)k * W * W);
-		MEMS_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-		MEMS_CUDA(cudaStreamSynchronize(c->stream));
-		return all;
-	};
+	// a limit every rank evaluates identically (max_recv is the largest receive region of ANY rank): all throw together
+	if (max_recv > radix_max_items()) throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30-1 seed records on one rank");
 	auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
 	// ---- 3. partition the local records by top digit and deliver every key range to its owner.
 	// With exchange windows (CUDA IPC mappings of the peers' receive buffers) the delivery is peer-to-peer over
@@ -2146,14 +2272,16 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	const size_t rec_region[2] = {0, align256(max_recv * K)};
 	const bool direct = !getenv("MEMS_NO_PEER_WINDOWS") && comm_window_reserve(comm, 0, rec_region[1] + align256(max_recv * 4));
 	const bool scatter = direct && getenv("MEMS_PEER_SCATTER") != nullptr;
-	DevBuf<uint8_t> rk_own, rk_b(c, n_recv * K);
-	DevBuf<uint32_t> rv_own, rv_b(c, n_recv);
+	// (all buffers of the exchanges live to the end of the call: nothing has to wait for the stream just to free them)
+	DevBuf<uint8_t> rk_own, rk_b(c, n_recv * K), keys_part;
+	DevBuf<uint32_t> rv_own, rv_b(c, n_recv), vals_part;
+	DevBuf<uint64_t> d_dst;
+	uint64_t h_dst[512];
 	uint8_t* rk_a_p;
 	uint32_t* rv_a_p;
 	if (scatter) {
 		// digit b's run starts at index first_idx[b] of this rank's partitioned order and belongs at element
 		// (records of lower ranks for that owner) + (index inside this rank's slice for that owner) of the owner's region
-		uint64_t h_dst[512];
 		for (int b = 0; b < 256; ++b) {
 			const int p = owner[b];
 			const int64_t shift_elems = (int64_t)slice_dst[p] - (int64_t)slice_src[p];  // destination index - partitioned index
@@ -2161,7 +2289,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 			h_dst[b] = win + rec_region[0] + (uint64_t)(shift_elems * (int64_t)K);
 			h_dst[256 + b] = win + rec_region[1] + (uint64_t)(shift_elems * 4);
 		}
-		DevBuf<uint64_t> d_dst(c, 512);
+		d_dst = DevBuf<uint64_t>(c, 512);
 		MEMS_CUDA(cudaMemcpyAsync(d_dst.p, h_dst, sizeof h_dst, cudaMemcpyHostToDevice, c->stream));
 		void* kp[2] = {keys_loc.p, nullptr};
 		uint32_t* vp[2] = {vals_loc.p, nullptr};
@@ -2170,12 +2298,11 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 			KernelScope ks(c, "peer_barrier");
 			comm_window_barrier(comm);
 		}
-		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // h_dst / d_dst go out of scope
 		rk_a_p = static_cast<uint8_t*>(comm_window_local(comm, 0)) + rec_region[0];
 		rv_a_p = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(comm_window_local(comm, 0)) + rec_region[1]);
 	} else {
-		DevBuf<uint8_t> keys_part(c, n_loc * K);
-		DevBuf<uint32_t> vals_part(c, n_loc);
+		keys_part = DevBuf<uint8_t>(c, n_loc * K);
+		vals_part = DevBuf<uint32_t>(c, n_loc);
 		void* kp[2] = {keys_loc.p, keys_part.p};
 		uint32_t* vp[2] = {vals_loc.p, vals_part.p};
 		radix_sort_pairs(c, K == 8, kp, vp, n_loc, top, hist_top.p, "shard_partition_pass");
@@ -2194,9 +2321,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 			void* rcv[2] = {rk_a_p, rv_a_p};
 			comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, send_counts.data(), recv_counts.data());
 		}
-		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // keys_part / vals_part go out of scope
 	}
-	vals_loc.reset();
 	mark("all-to-all records");
 	DevBuf<SeqMeta> d_gmeta(c, n_seqs);
 	MEMS_CUDA(cudaMemcpyAsync(d_gmeta.p, gmeta.data(), sizeof(SeqMeta) * n_seqs, cudaMemcpyHostToDevice, c->stream));
@@ -2223,9 +2348,9 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.n_seqs = n_seqs;
 	a1.mode = mode;
 	a1.seq_set = 0;
-	a1.test_hash_bits = getenv("MEMS_TEST_HASH_BITS") ? atoi(getenv("MEMS_TEST_HASH_BITS")) : 0;
-	a1.warp_budget = kWarpProbeBudget;
-	a1.cta_budget = kCtaRoundBudget;
+	a1.test_hash_bits = c->test_hash_bits;
+	a1.warp_budget = c->test_walk_budget ? c->test_walk_budget : kWarpProbeBudget;
+	a1.cta_budget = c->test_walk_budget ? c->test_walk_budget : kCtaRoundBudget;
 	a1.planes = nullptr;
 	a1.meta = d_gmeta.p;
 	HitSet hits1;
@@ -2234,18 +2359,18 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 
 	mark("sort + run scan");
 	// ---- 6. describe the hits and group them by the top 8 bits of their diagonal hash (one counting pass: the owner
-	// re-sorts what it receives anyway); contiguous ranges of those 256 buckets go to their owner rank
+	// sorts what it receives anyway); contiguous ranges of those 256 buckets go to their owner rank.  The hash key
+	// travels with the hit, so the owner does not describe it again.
 	const uint32_t n1 = hits1.n;
 	SortPlan hplan;
 	hplan.n_passes = 1;
 	hplan.shift[0] = 56;
 	hplan.bits[0] = 8;
-	DevBuf<uint64_t> hk_a(c, n1), hk_b(c, n1);
-	DevBuf<uint32_t> hid_a(c, n1), hid_b(c, n1), slen(c, n1), moff(c, n1), bound(c, W + 1), scal(c, 2);
+	DevBuf<uint64_t> hk_a(c, n1), hk_b(c, n1), d_counts(c, (size_t)2 * W * (W + 1));
+	DevBuf<uint32_t> hid_a(c, n1), hid_b(c, n1), slen(c, n1), moff(c, n1), scal(c, 2);
 	const uint64_t* hkey = hk_a.p;
 	const uint32_t* hid = hid_a.p;
-	uint32_t n_mem1 = 0;
-	std::vector<uint32_t> h_bound(W + 1, 0), h_mbound(W + 1, 0);
+	MEMS_CUDA(cudaMemsetAsync(d_counts.p, 0, (size_t)2 * W * sizeof(uint64_t), c->stream));
 	if (n1) {
 		DevBuf<uint32_t> hist(c, (size_t)hplan.n_passes * 256);
 		MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)hplan.n_passes * 256 * sizeof(uint32_t), c->stream));
@@ -2260,46 +2385,33 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		const int r = radix_sort_pairs(c, true, kp, vp, n1, hplan, hist.p, "hit_partition_pass");
 		hkey = r ? hk_b.p : hk_a.p;
 		hid = r ? hid_b.p : hid_a.p;
-		KernelScope ks(c, "shard_hits");
-		sorted_len_kernel<<<hb, 256, 0, c->stream>>>(hid, hits1.len.p, n1, slen.p);
-		MEMS_CUDA(cudaGetLastError());
-		exclusive_scan_u32(c, slen.p, moff.p, n1, scal.p);
-		hit_bounds_kernel<<<1, 32 * ((W + 32) / 32), 0, c->stream>>>(hkey, n1, W, bound.p);
-		MEMS_CUDA(cudaGetLastError());
-		MEMS_CUDA(cudaMemcpyAsync(&n_mem1, scal.p, 4, cudaMemcpyDeviceToHost, c->stream));
-		MEMS_CUDA(cudaMemcpyAsync(h_bound.data(), bound.p, (W + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-		MEMS_CUDA(cudaStreamSynchronize(c->stream));
-		std::vector<uint32_t> h_moff(W + 1, n_mem1);
-		for (int d = 0; d < W; ++d)
-			if (h_bound[d] < n1) MEMS_CUDA(cudaMemcpyAsync(&h_moff[d], moff.p + h_bound[d], 4, cudaMemcpyDeviceToHost, c->stream));
-		MEMS_CUDA(cudaStreamSynchronize(c->stream));
-		h_mbound = h_moff;
+		{
+			KernelScope ks(c, "shard_hit_lengths", (double)n1 * 10.0);
+			sorted_len_kernel<<<hb, 256, 0, c->stream>>>(hid, hits1.len.p, n1, slen.p);
+			MEMS_CUDA(cudaGetLastError());
+		}
+		exclusive_scan_u32(c, slen.p, moff.p, n1, scal.p);  // scal[0] = members in total
 	}
-	DevBuf<uint32_t> s_mval(c, n_mem1);
-	DevBuf<uint8_t> s_mstr(c, n_mem1);
+	// what every rank sends to every rank, as one all-gather of 2 W counts per rank and ONE host sync
 	if (n1) {
-		KernelScope ks(c, "shard_hits");
-		scatter_members_kernel<KeyT><<<(n1 + 255) / 256, 256, 0, c->stream>>>(a1, hid, hits1.start.p, hits1.len.p, moff.p, n1,
-		                                                                        slen.p, s_mval.p, s_mstr.p);
+		KernelScope ks(c, "shard_hit_counts");
+		last_len_kernel<<<1, 32, 0, c->stream>>>(slen.p, n1, scal.p + 1);
+		MEMS_CUDA(cudaGetLastError());
+		hit_send_counts_kernel<<<1, 32 * ((W + 32) / 32), 0, c->stream>>>(hkey, moff.p, n1, scal.p + 1, W, d_counts.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	mark("hit describe/sort/pack");
+	comm_all_gather_u64(comm, d_counts.p, d_counts.p + 2 * W, (size_t)2 * W);
+	std::vector<uint64_t> h_counts((size_t)2 * W * W);
+	MEMS_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p + 2 * W, h_counts.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 	std::vector<uint64_t> hs(W), hr(W), ms(W), mr(W);
-	for (int d = 0; d < W; ++d) {
-		hs[d] = h_bound[d + 1] - h_bound[d];
-		ms[d] = h_mbound[d + 1] - h_mbound[d];
-	}
 	std::vector<uint64_t> hit_counts((size_t)W * W), mem_counts((size_t)W * W);
-	{
-		const std::vector<uint64_t> mine[2] = {hs, ms};
-		const std::vector<uint64_t> all = exchange_counts(2, mine);  // hit and member counts in one round
-		for (int p = 0; p < W; ++p)
-			for (int d = 0; d < W; ++d) {
-				hit_counts[(size_t)p * W + d] = all[((size_t)p * 2 + 0) * W + d];
-				mem_counts[(size_t)p * W + d] = all[((size_t)p * 2 + 1) * W + d];
-			}
-	}
-	uint64_t n2 = 0, n_mem2 = 0, max_n2 = 0, max_mem2 = 0;
+	for (int p = 0; p < W; ++p)
+		for (int d = 0; d < W; ++d) {
+			hit_counts[(size_t)p * W + d] = h_counts[(size_t)p * 2 * W + d];
+			mem_counts[(size_t)p * W + d] = h_counts[(size_t)p * 2 * W + W + d];
+		}
+	uint64_t n2 = 0, n_mem2 = 0, max_n2 = 0, max_mem2 = 0, n_mem1 = 0;
 	for (int d = 0; d < W; ++d) {
 		uint64_t a = 0, b = 0;
 		for (int p = 0; p < W; ++p) {
@@ -2308,6 +2420,9 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		}
 		max_n2 = std::max(max_n2, a);
 		max_mem2 = std::max(max_mem2, b);
+		hs[d] = hit_counts[(size_t)R * W + d];
+		ms[d] = mem_counts[(size_t)R * W + d];
+		n_mem1 += ms[d];
 	}
 	for (int p = 0; p < W; ++p) {
 		hr[p] = hit_counts[(size_t)p * W + R];
@@ -2315,66 +2430,82 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		n2 += hr[p];
 		n_mem2 += mr[p];
 	}
-	if (n_mem2 >= (1ull << 31)) throw Error(MEMS_ERR_UNSUPPORTED, "too many hit members on one rank");
-	const size_t hit_region[3] = {0, align256(max_n2 * 4), align256(max_n2 * 4) + align256(max_mem2 * 4)};
-	const bool direct_hits = direct && comm_window_reserve(comm, 1, hit_region[2] + align256(max_mem2));
-	DevBuf<uint32_t> r_len_own, r_mval_own;
-	DevBuf<uint8_t> r_mstr_own;
-	uint32_t *r_len_p, *r_mval_p;
-	uint8_t* r_mstr_p;
+	// evaluated identically on every rank (the largest receiver of ANY rank): all throw together
+	if (max_mem2 >= (1ull << 31) || max_n2 > radix_max_items()) throw Error(MEMS_ERR_UNSUPPORTED, "too many hits or hit members on one rank");
+	DevBuf<uint16_t> s_len16(c, n1);
+	DevBuf<uint32_t> s_mem(c, n_mem1);
+	if (n1) {
+		KernelScope ks(c, "shard_pack_hits", (double)n1 * 12.0 + (double)n_mem1 * 12.0);
+		const uint32_t warps = (n1 + 31) / 32;
+		pack_hits_kernel<KeyT><<<(warps + 7) / 8, 256, 0, c->stream>>>(a1, hid, hits1.start.p, hits1.len.p, moff.p, n1, s_len16.p, s_mem.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	mark("hit describe/sort/pack");
+	// window 1: [hash keys u64][length words u16][members u32], every region sized for the largest receiver
+	const size_t hit_region[3] = {0, align256(max_n2 * 8), align256(max_n2 * 8) + align256(max_n2 * 2)};
+	const bool direct_hits = direct && comm_window_reserve(comm, 1, hit_region[2] + align256(max_mem2 * 4));
+	DevBuf<uint64_t> r_key_own;
+	DevBuf<uint16_t> r_len_own;
+	DevBuf<uint32_t> r_mem_own;
+	uint64_t* r_key_p;
+	uint16_t* r_len_p;
+	uint32_t* r_mem_p;
 	{
-		KernelScope ks(c, direct_hits ? "peer_all_to_all_hits" : "nccl_all_to_all_hits", (double)n1 * 4 + (double)n_mem1 * 5);
+		KernelScope ks(c, direct_hits ? "peer_all_to_all_hits" : "nccl_all_to_all_hits", (double)n1 * 10 + (double)n_mem1 * 4);
 		if (direct_hits) {
 			uint8_t* base = static_cast<uint8_t*>(comm_window_local(comm, 1));
-			r_len_p = reinterpret_cast<uint32_t*>(base + hit_region[0]);
-			r_mval_p = reinterpret_cast<uint32_t*>(base + hit_region[1]);
-			r_mstr_p = base + hit_region[2];
-			const void* s1[1] = {slen.p};
-			const size_t e1[1] = {4};
-			comm_window_all_to_all(comm, 1, 1, s1, e1, hit_region, hit_counts.data(), false);
-			const void* s2[2] = {s_mval.p, s_mstr.p};
-			const size_t e2[2] = {4, 1};
-			comm_window_all_to_all(comm, 1, 2, s2, e2, hit_region + 1, mem_counts.data(), true);
+			r_key_p = reinterpret_cast<uint64_t*>(base + hit_region[0]);
+			r_len_p = reinterpret_cast<uint16_t*>(base + hit_region[1]);
+			r_mem_p = reinterpret_cast<uint32_t*>(base + hit_region[2]);
+			const void* s1[2] = {hkey, s_len16.p};
+			const size_t e1[2] = {8, 2};
+			comm_window_all_to_all(comm, 1, 2, s1, e1, hit_region, hit_counts.data(), false);
+			const void* s2[1] = {s_mem.p};
+			const size_t e2[1] = {4};
+			comm_window_all_to_all(comm, 1, 1, s2, e2, hit_region + 2, mem_counts.data(), true);
 		} else {
-			r_len_own = DevBuf<uint32_t>(c, n2);
-			r_mval_own = DevBuf<uint32_t>(c, n_mem2);
-			r_mstr_own = DevBuf<uint8_t>(c, n_mem2);
+			r_key_own = DevBuf<uint64_t>(c, n2);
+			r_len_own = DevBuf<uint16_t>(c, n2);
+			r_mem_own = DevBuf<uint32_t>(c, n_mem2);
+			r_key_p = r_key_own.p;
 			r_len_p = r_len_own.p;
-			r_mval_p = r_mval_own.p;
-			r_mstr_p = r_mstr_own.p;
-			comm_all_to_all_v(comm, slen.p, hs.data(), r_len_p, hr.data(), 4);
-			const void* snd[2] = {s_mval.p, s_mstr.p};
-			void* rcv[2] = {r_mval_p, r_mstr_p};
-			const size_t eb[2] = {4, 1};
-			comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, ms.data(), mr.data());
+			r_mem_p = r_mem_own.p;
+			const void* snd[2] = {hkey, s_len16.p};
+			void* rcv[2] = {r_key_p, r_len_p};
+			const size_t eb[2] = {8, 2};
+			comm_all_to_all_v_multi(comm, 2, snd, rcv, eb, hs.data(), hr.data());
+			comm_all_to_all_v(comm, s_mem.p, ms.data(), r_mem_p, mr.data(), 4);
 		}
 	}
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers below go out of scope
 	mark("all-to-all hits");
 	// ---- 7. this rank's diagonals: segments, walks, components
-	comm_all_gather_v_wait(comm);  // the gathered keys are needed from here on
+	comm_all_gather_v_wait(comm);  // the gathered planes are needed from here on
 	if (direct_planes) comm_window_barrier(comm);  // ... on every rank: the peers' copies into this rank's window are done
 	out.n_hits = n2;
-	if (n2 == 0) return;
+	if (n2 == 0) {
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // the send buffers go out of scope
+		return;
+	}
 	HitSet hits2;
 	hits2.n = (uint32_t)n2;
 	hits2.start = DevBuf<uint32_t>(c, n2);
 	hits2.len = DevBuf<uint16_t>(c, n2);
 	DevBuf<KeyT> keys2(c, n_mem2);
-	exclusive_scan_u32(c, r_len_p, hits2.start.p, n2, nullptr);
+	DevBuf<uint32_t> len32(c, n2);
 	{
-		KernelScope ks(c, "shard_hits");
+		KernelScope ks(c, "shard_received_hits", (double)n2 * 8.0 + (double)n_mem2 * (8.0 + sizeof(KeyT)));
 		const uint32_t nmax = (uint32_t)std::max<uint64_t>(n2, n_mem2);
-		received_hits_kernel<KeyT><<<(nmax + 255) / 256, 256, 0, c->stream>>>(r_len_p, r_mstr_p, (uint32_t)n2, (uint32_t)n_mem2,
+		received_hits_kernel<KeyT><<<(nmax + 255) / 256, 256, 0, c->stream>>>(r_len_p, r_mem_p, (uint32_t)n2, (uint32_t)n_mem2, len32.p,
 		                                                                        hits2.len.p, keys2.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
+	exclusive_scan_u32(c, len32.p, hits2.start.p, n2, nullptr);
 	MatchArgs a2 = a1;
 	a2.keys = keys2.p;
-	a2.vals = r_mval_p;
+	a2.vals = r_mem_p;
 	a2.n = (uint32_t)n_mem2;
 	a2.planes = planes_all_p;
-	extend_hits<KeyT>(ctx, a2, sd, hits2, order, 40000u, out);
+	extend_hits<KeyT>(ctx, a2, sd, hits2, order, 40000u, out, nullptr, r_key_p);
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 	mark("extend + emit + D2H");
 }

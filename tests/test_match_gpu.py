@@ -174,15 +174,15 @@ def test_masked_memhash_vs_oracle(ctx, orc):
         assert info["collisions"] == winfo["collisions"] and info["n_hits"] == winfo["hits"]
 
 
-def test_diagonal_hash_collisions_are_harmless(orc, monkeypatch):
-    """Force many diagonals into few hash buckets (MEMS_TEST_HASH_BITS): segments get split by foreign entries,
+def test_diagonal_hash_collisions_are_harmless(orc):
+    """Force many diagonals into few hash buckets (mems_test_hooks): segments get split by foreign entries,
     some components are found twice, and the de-dup of the marked components must restore the exact MatchList."""
     seed = mems.get_seed(11)
     gs = synth.genome_family(5, 40000, seed=51, snp_rate=0.03, n_indels=6, max_indel=30)
     want, winfo = orc.find_matches(0, gs, seed)
     for bits in (1, 3, 6):
-        monkeypatch.setenv("MEMS_TEST_HASH_BITS", str(bits))
         c = gpu_context()
+        c.set_test_hooks(hash_bits=bits)
         smls = c.create_smls(gs, seed)
         flat, info = c.find_matches(smls)  # ORDER_ANY: device order, distinct
         got = mems.flat_to_matches(flat)
@@ -223,11 +223,11 @@ def test_multi_seed_accumulation(ctx, orc, it):
     assert mems.flat_to_matches(flat) == orc.find_matches(0, gs, seeds[0])[0]
 
 
-def test_grid_wide_walks(orc, monkeypatch):
+def test_grid_wide_walks(orc):
     """With the warp and CTA budgets shrunk to 2, the long diagonals of the sparse-hit inputs are finished by the
     grid-cooperative walker (all CTAs on one walk, grid barrier per round), including the linking case."""
-    monkeypatch.setenv("MEMS_TEST_WALK_BUDGET", "2")
     c = gpu_context()
+    c.set_test_hooks(walk_budget=1)
     seed = mems.get_seed(15)
     rng = np.random.default_rng(98)
     T = synth.random_genome(40_000, rng)
