@@ -84,6 +84,9 @@ int mems_sml_create(mems_ctx_t ctx, const char* seq, uint64_t n, uint64_t seed, 
 int mems_sml_create_batch(mems_ctx_t ctx, int n_seqs, const char* const* seqs, const uint64_t* lens,
                           uint64_t seed, mems_sml_t* out);
 void mems_sml_destroy(mems_sml_t sml);
+/* MemorySML::Clone / DNAMemorySML::Clone (MemorySML.cpp:36-38): a second handle to the same sorted list (the device
+ * data is shared and lives until the last handle is destroyed). */
+int mems_sml_clone(mems_sml_t sml, mems_sml_t* out);
 int mems_sml_info(mems_sml_t sml, mems_sml_info_t* out);
 /* MemorySML::Read / operator[] (MemorySML.cpp:62-94): entries [offset, offset+count) of the sorted
  * list as (position, canonical mer).  Either output may be NULL.  *n_read receives the count. */
@@ -116,6 +119,8 @@ typedef struct {
 	                        ClearSequences() + FindMatches() loop (ProgressiveAligner.cpp:619-653) */
 	uint64_t seq_mask;   /* MaskedMemHash::SetMask (MaskedMemHash.h:22-32): with MEMS_MODE_MEMHASH keep only hits whose
 	                        sequence set equals this mask, sequence 0 = most significant of n_smls bits; 0 = no filter */
+	const uint64_t* start_points; /* NULL, or n_smls indices: MemHash::FindMatchesFromPosition (MemHash.cpp:117-127,
+	                        MatchFinder.cpp:137-164) — sorted mer list g is searched from its entry start_points[g] on */
 } mems_match_params_t;
 
 typedef struct {
@@ -140,6 +145,13 @@ int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls,
 int mems_table_create(uint32_t table_size /* 0 = 40000 */, mems_table_t* out);
 void mems_table_clear(mems_table_t t);
 void mems_table_destroy(mems_table_t t);
+/* MemHash::AddHashEntry (MemHash.cpp:209-251) for a match that is already extended — what MemHash::LoadFile
+ * (MemHash.cpp:266-305) does per line of a .mems file: *inserted = 0 if the table already holds a match that
+ * contains it on its diagonal (a collision), else 1.  mersize = the seed weight MatchFinder had when the line was
+ * read (MatchFinder::mer_size; DNA_MER_SIZE before any search). */
+int mems_table_add(mems_table_t t, uint32_t seq_count, uint64_t length, const int64_t* starts, uint32_t mersize, int* inserted);
+/* The table's content in the reference's output order (MemHash::GetMatchList, MemHash.h:183-203) as a match list. */
+int mems_table_matches(mems_table_t t, mems_matches_t* out);
 int mems_matches_info(mems_matches_t m, mems_matches_info_t* out);
 /* Flat records [SeqCount, Length, Start(0) .. Start(SeqCount-1)] per match; starts are 1-based,
  * negative = reverse strand, 0 = NO_MATCH (AbstractMatch.h:27, UngappedLocalAlignment.h:201-206). */
@@ -157,6 +169,8 @@ typedef struct mems_comm* mems_comm_t;
 /* rank 0 creates the 128-byte NCCL id and hands it to the other ranks by any host channel */
 int mems_comm_unique_id(char* id_out /* 128 bytes */);
 int mems_comm_create(mems_ctx_t ctx, const char* id /* 128 bytes */, int rank, int world, mems_comm_t* out);
+/* Collective: every rank must call it (the ranks agree that nobody maps anybody's exchange window any more before
+ * the windows are freed).  After a failed collective call the communicator must not be used for further calls. */
 void mems_comm_destroy(mems_comm_t comm);
 /* the block of sequences [first, first+count) rank `rank` must supply (host arithmetic) */
 int mems_shard_sequence_range(int n_seqs, int rank, int world, int* first, int* count);

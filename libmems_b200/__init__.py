@@ -34,7 +34,7 @@ class SmlInfo(ctypes.Structure):
 
 class MatchParams(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int), ("order", ctypes.c_int), ("table_size", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32), ("table", _vp), ("seq_mask", _u64)]
+                ("reserved", ctypes.c_uint32), ("table", _vp), ("seq_mask", _u64), ("start_points", _vp)]
 
 
 class MatchesInfo(ctypes.Structure):
@@ -52,8 +52,8 @@ EXPORTS = [
     "mems_get_seed", "mems_get_solid_seed", "mems_get_seed_length", "mems_get_seed_weight",
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
-    "mems_sml_destroy", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
+    "mems_sml_destroy", "mems_sml_clone", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
+    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_shard_exchange_plan", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
     "mems_test_hooks",
@@ -89,6 +89,7 @@ def load():
     lib.mems_sml_create_batch.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _u64,
                                           ctypes.POINTER(_vp)]
     lib.mems_sml_destroy.argtypes = [_vp]
+    lib.mems_sml_clone.argtypes = [_vp, ctypes.POINTER(_vp)]
     lib.mems_sml_info.argtypes = [_vp, ctypes.POINTER(SmlInfo)]
     lib.mems_sml_read.argtypes = [_vp, _u64, _u64, _vp, _vp, ctypes.POINTER(_u64)]
     lib.mems_sml_seed_mers.argtypes = [_vp, _vp, _u64, _vp, _vp]
@@ -100,6 +101,8 @@ def load():
     lib.mems_table_create.argtypes = [ctypes.c_uint32, ctypes.POINTER(_vp)]
     lib.mems_table_clear.argtypes = [_vp]
     lib.mems_table_destroy.argtypes = [_vp]
+    lib.mems_table_add.argtypes = [_vp, ctypes.c_uint32, _u64, _vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+    lib.mems_table_matches.argtypes = [_vp, ctypes.POINTER(_vp)]
     lib.mems_matches_info.argtypes = [_vp, ctypes.POINTER(MatchesInfo)]
     lib.mems_matches_copy.argtypes = [_vp, _vp]
     lib.mems_matches_data.argtypes = [_vp]
@@ -264,12 +267,14 @@ class Context:
         return [SortedMerList(self, _vp(out[i])) for i in range(n)]
 
     # -- match finding --------------------------------------------------------------------------------
-    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0, table=None):
-        """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches.  Returns (matches, info) where
-        matches is a list of tuples (SeqCount, Length, Start(0), ...)."""
+    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0, table=None, start_points=None):
+        """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches (start_points: FindMatchesFromPosition).  Returns
+        (flat, info): flat = int64 records [SeqCount, Length, Start(0), ...] (see flat_to_matches)."""
         n = len(smls)
         arr = (_vp * n)(*[s.h for s in smls])
-        params = MatchParams(mode, order, table_size, 0, table.h if table is not None else None, seq_mask)
+        sp = (_u64 * n)(*[int(x) for x in start_points]) if start_points is not None else None
+        params = MatchParams(mode, order, table_size, 0, table.h if table is not None else None, seq_mask,
+                             ctypes.cast(sp, _vp) if sp is not None else None)
         h = _vp()
         self._check(self.lib.mems_find_matches(self.h, n, arr, ctypes.byref(params), ctypes.byref(h)))
         keep = _MatchHandle(self.lib, h)
@@ -298,7 +303,7 @@ class Context:
         parts = [(_host_ptr(s) if s is not None else (0, 0, None)) for s in seqs]
         ptrs = (_vp * n)(*[p[0] for p in parts])
         ls = (_u64 * n)(*[int(x) for x in lens])
-        params = MatchParams(mode, order, 0, 0, None, 0)
+        params = MatchParams(mode, order, 0, 0, None, 0, None)
         h = _vp()
         self._check(self.lib.mems_find_matches_sharded(self.h, comm.h, n, ptrs, ls, seed, ctypes.byref(params),
                                                        ctypes.byref(h)))
@@ -348,6 +353,29 @@ class HashTable:
 
     def clear(self):
         self.lib.mems_table_clear(self.h)
+
+    def add(self, match, mersize=0):
+        """AddHashEntry of an already extended match (SeqCount, Length, starts...); True if it was inserted."""
+        st = (ctypes.c_int64 * int(match[0]))(*[int(x) for x in match[2:]])
+        ins = ctypes.c_int()
+        rc = self.lib.mems_table_add(self.h, int(match[0]), int(match[1]), st, int(mersize), ctypes.byref(ins))
+        if rc:
+            raise MemsError(rc, "bad table entry")
+        return bool(ins.value)
+
+    def matches(self):
+        """The table's content in the reference's output order, as a list of tuples."""
+        h = _vp()
+        rc = self.lib.mems_table_matches(self.h, ctypes.byref(h))
+        if rc:
+            raise MemsError(rc, "cannot list table")
+        info = MatchesInfo()
+        self.lib.mems_matches_info(h, ctypes.byref(info))
+        flat = np.zeros(0, np.int64)
+        if info.n_flat:
+            flat = np.ctypeslib.as_array(self.lib.mems_matches_data(h), shape=(int(info.n_flat),)).copy()
+        self.lib.mems_matches_destroy(h)
+        return flat_to_matches(flat)
 
     def __del__(self):
         try:
@@ -406,6 +434,12 @@ class SortedMerList:
 
     def sml_length(self):
         return self.info["sml_length"]
+
+    def clone(self):
+        """MemorySML::Clone: another handle to the same device-resident list."""
+        h = _vp()
+        self.ctx._check(self.ctx.lib.mems_sml_clone(self.h, ctypes.byref(h)))
+        return SortedMerList(self.ctx, h)
 
     def read(self, offset=0, count=None):
         """MemorySML::Read: (positions, mers) of sorted-list entries [offset, offset+count)."""

@@ -125,6 +125,11 @@ void mems_sml_destroy(mems_sml_t sml) {
 	delete sml;
 }
 
+int mems_sml_clone(mems_sml_t sml, mems_sml_t* out) {
+	if (!sml || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	return guarded(nullptr, [&] { *out = new mems_sml{sml->batch, sml->index}; });
+}
+
 int mems_sml_info(mems_sml_t sml, mems_sml_info_t* out) {
 	if (!sml || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
 	const Batch& b = *sml->batch;
@@ -297,6 +302,23 @@ void mems_table_clear(mems_table_t t) {
 }
 
 void mems_table_destroy(mems_table_t t) { delete t; }
+
+int mems_table_add(mems_table_t t, uint32_t seq_count, uint64_t length, const int64_t* starts, uint32_t mersize, int* inserted) {
+	if (!t || !starts || seq_count == 0) return fail(nullptr, MEMS_ERR_INVALID, "bad arguments");
+	return guarded(nullptr, [&] {
+		const bool ins = table_add_entry(t->t, seq_count, (int64_t)length, starts, (int64_t)mersize);
+		if (inserted) *inserted = ins ? 1 : 0;
+	});
+}
+
+int mems_table_matches(mems_table_t t, mems_matches_t* out) {
+	if (!t || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	return guarded(nullptr, [&] {
+		auto* m = new mems_matches();
+		table_list(t->t, m->r);
+		*out = m;
+	});
+}
 
 int mems_matches_info(mems_matches_t m, mems_matches_info_t* out) {
 	if (!m || !out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");

@@ -101,19 +101,35 @@ struct Comm {
 		}
 		MEMS_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
 	}
-	void free_window(int w) {
+	// CUDA IPC contract: exported memory may be freed only after every importer has closed its mapping.  Releasing a
+	// window is therefore two-phase and collective: all ranks close their mappings of the peers' buffers, a barrier
+	// proves it, then every rank frees its own buffer.
+	void close_peer_mappings(int w) {
 		Window& x = win[w];
 		for (int p = 0; p < (int)x.peer.size(); ++p)
 			if (p != rank && x.peer[p]) cudaIpcCloseMemHandle(x.peer[p]);
 		x.peer.clear();
+	}
+	void free_local(int w) {
+		Window& x = win[w];
 		if (x.local) cudaFree(x.local);
 		x.local = nullptr;
 		x.bytes = 0;
 	}
+	void host_barrier() {  // every rank has reached this point (and its earlier stream work is done)
+		if (world == 1 || !comm || !d_barrier) return;
+		if (nccl().AllReduce(d_barrier, d_barrier + 8, 1, ncclUint32, ncclSum, comm, ctx->stream) == ncclSuccess)
+			cudaStreamSynchronize(ctx->stream);
+	}
 	~Comm() {
-		free_window(0);
-		free_window(1);
-		free_window(2);
+		// collective (mems_comm_destroy): close, barrier, free
+		bool any = false;
+		for (int w = 0; w < 3; ++w) {
+			any = any || win[w].local != nullptr;
+			close_peer_mappings(w);
+		}
+		if (any) host_barrier();
+		for (int w = 0; w < 3; ++w) free_local(w);
 		if (d_barrier) cudaFree(d_barrier);
 		for (cudaStream_t st : peer_stream)
 			if (st) cudaStreamDestroy(st);
@@ -215,17 +231,21 @@ bool comm_window_reserve(Comm* c, int w, size_t bytes) {
 	Comm::Window& x = c->win[w];
 	if (x.local && x.bytes >= bytes) return true;
 	MEMS_CUDA(cudaStreamSynchronize(c->ctx->stream));
-	c->free_window(w);
+	if (c->world > 1 && !c->d_barrier) {
+		MEMS_CUDA(cudaMalloc(&c->d_barrier, 256));
+		MEMS_CUDA(cudaMemset(c->d_barrier, 0, 256));
+	}
+	if (x.local) {  // growing: every rank takes this branch in the same call (the size is derived identically everywhere)
+		c->close_peer_mappings(w);
+		c->host_barrier();
+		c->free_local(w);
+	}
 	const size_t want = (bytes + bytes / 4 + (1u << 20)) & ~(size_t)0xfffff;  // head room, 1 MiB granules
 	MEMS_CUDA(cudaMalloc(&x.local, want));
 	x.bytes = want;
 	x.peer.assign(c->world, nullptr);
 	x.peer[c->rank] = x.local;
 	if (c->world == 1) return true;
-	if (!c->d_barrier) {
-		MEMS_CUDA(cudaMalloc(&c->d_barrier, 256));
-		MEMS_CUDA(cudaMemset(c->d_barrier, 0, 256));
-	}
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
 	struct Slot {
 		cudaIpcMemHandle_t h;
@@ -259,8 +279,10 @@ bool comm_window_reserve(Comm* c, int w, size_t bytes) {
 	check(nccl().AllReduce(d_ok.p, d_ok.p, 1, ncclUint64, ncclMin, c->comm, c->ctx->stream), "ncclAllReduce");
 	MEMS_CUDA(cudaMemcpyAsync(&ok, d_ok.p, 8, cudaMemcpyDeviceToHost, c->ctx->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->ctx->stream));
-	if (!ok) {
-		c->free_window(w);
+	if (!ok) {  // agreed by all ranks: the same two-phase release
+		c->close_peer_mappings(w);
+		c->host_barrier();
+		c->free_local(w);
 		c->windows_ok = false;
 		return false;
 	}

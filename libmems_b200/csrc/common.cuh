@@ -329,7 +329,11 @@ struct HashTable {
 	uint64_t mem_count = 0, collisions = 0;
 };
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
-                           HashTable* persistent = nullptr);
+                           HashTable* persistent = nullptr, const uint64_t* start_points = nullptr);
+// MemHash::AddHashEntry for an already extended match (MemHash::LoadFile); true = inserted, false = collision
+bool table_add_entry(HashTable& T, uint32_t seq_count, int64_t length, const int64_t* starts, int64_t mersize);
+// the table's content in output order (buckets in order, front to back)
+void table_list(const HashTable& T, MatchResult& out);
 void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
                           uint64_t seed, int mode, int order, MatchResult& out);
 

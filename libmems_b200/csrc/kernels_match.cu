@@ -1886,9 +1886,56 @@ static void emit_table(const HashTable& T, MatchResult& out) {
 	out.collisions = T.collisions;
 }
 
+// ---- MemHash::FindMatchesFromPosition: sorted mer list g takes part from its entry start_points[g] on
+// (MatchFinder.cpp:137-164 reads SML g from that index).  The union is a stable merge of the per-sequence lists, so
+// "index >= start" of a sequence's list is "(key, position) >= the list's entry at start": one threshold per sequence.
+template <class KeyT>
+__global__ void start_thresholds_kernel(const uint32_t* __restrict__ positions, const KeyT* __restrict__ key_pos,
+                                        const SeqMeta* __restrict__ meta, const uint64_t* __restrict__ start, int n_seqs,
+                                        uint32_t pos_mask, KeyT* __restrict__ thr_key, uint32_t* __restrict__ thr_val,
+                                        uint8_t* __restrict__ thr_mode) {
+	const int g = threadIdx.x;
+	if (g >= n_seqs) return;
+	const SeqMeta m = meta[g];
+	const uint64_t s = start[g];
+	if (s == 0) {
+		thr_mode[g] = 0;  // everything
+	} else if (s >= m.n_seeds) {
+		thr_mode[g] = 2;  // nothing
+	} else {
+		const uint32_t v = positions[m.seed_off + s];
+		thr_mode[g] = 1;
+		thr_val[g] = v;
+		thr_key[g] = key_pos[m.seed_off + (v & pos_mask)];
+	}
+}
+
+template <class KeyT>
+__global__ void start_keep_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n, int pos_bits,
+                                  const KeyT* __restrict__ thr_key, const uint32_t* __restrict__ thr_val,
+                                  const uint8_t* __restrict__ thr_mode, uint32_t* __restrict__ keep) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t v = vals[i], g = v >> pos_bits;
+	const uint8_t mode = thr_mode[g];
+	const KeyT k = keys[i];
+	keep[i] = mode == 0 || (mode == 1 && (k > thr_key[g] || (k == thr_key[g] && v >= thr_val[g]))) ? 1u : 0u;
+}
+
+template <class KeyT>
+__global__ void start_compact_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n,
+                                     const uint32_t* __restrict__ keep, const uint32_t* __restrict__ at,
+                                     KeyT* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && keep[i]) {
+		out_keys[at[i]] = keys[i];
+		out_vals[at[i]] = vals[i];
+	}
+}
+
 template <class KeyT>
 static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
-                               HashTable* persistent) {
+                               HashTable* persistent, const uint64_t* start_points) {
 	Ctx* c = b.ctx.get();
 	out.seq_count = (uint32_t)b.n_seqs;
 	out.seed_length = (uint32_t)b.sd.L;
@@ -1913,6 +1960,41 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		if ((seq_mask >> (b.n_seqs - 1 - g)) & 1) a.seq_set |= 1ull << g;
 	a.planes = b.planes.p;
 	a.meta = b.d_meta.p;
+	DevBuf<KeyT> fkeys;
+	DevBuf<uint32_t> fvals;
+	bool from_position = false;
+	for (int g = 0; start_points && g < b.n_seqs; ++g) from_position = from_position || start_points[g] != 0;
+	if (from_position) {
+		const uint32_t* positions = b.sorted_positions();
+		DevBuf<uint64_t> d_start(c, b.n_seqs);
+		DevBuf<KeyT> thr_key(c, b.n_seqs);
+		DevBuf<uint32_t> thr_val(c, b.n_seqs), keep(c, a.n), at(c, a.n), total(c, 1);
+		DevBuf<uint8_t> thr_mode(c, b.n_seqs);
+		MEMS_CUDA(cudaMemcpyAsync(d_start.p, start_points, sizeof(uint64_t) * b.n_seqs, cudaMemcpyHostToDevice, c->stream));
+		KernelScope ks(c, "start_points");
+		start_thresholds_kernel<KeyT><<<1, 256, 0, c->stream>>>(positions, reinterpret_cast<const KeyT*>(b.keys_by_pos.p), b.d_meta.p,
+		                                                          d_start.p, b.n_seqs, a.pos_mask, thr_key.p, thr_val.p, thr_mode.p);
+		MEMS_CUDA(cudaGetLastError());
+		const uint32_t blocks = (a.n + 255) / 256;
+		start_keep_kernel<KeyT><<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const KeyT*>(a.keys), a.vals, a.n, a.pos_bits, thr_key.p,
+		                                                       thr_val.p, thr_mode.p, keep.p);
+		MEMS_CUDA(cudaGetLastError());
+		exclusive_scan_u32(c, keep.p, at.p, a.n, total.p);
+		const uint32_t n_keep = d2h_u32(c, total.p);
+		fkeys = DevBuf<KeyT>(c, n_keep);
+		fvals = DevBuf<uint32_t>(c, n_keep);
+		start_compact_kernel<KeyT><<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const KeyT*>(a.keys), a.vals, a.n, keep.p, at.p,
+		                                                          fkeys.p, fvals.p);
+		MEMS_CUDA(cudaGetLastError());
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // d_start was filled from caller memory; the scratch dies with this scope
+		a.keys = fkeys.p;
+		a.vals = fvals.p;
+		a.n = n_keep;
+		if (n_keep < 2) {
+			if (persistent) emit_table(*persistent, out);
+			return;
+		}
+	}
 	HitSet hits;
 	DevBuf<uint32_t> pvals;
 	DevBuf<KeyT> pkeys;
@@ -1934,15 +2016,45 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 }
 
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
-                           HashTable* persistent) {
+                           HashTable* persistent, const uint64_t* start_points) {
 	if (persistent && order != MEMS_ORDER_REFERENCE) throw Error(MEMS_ERR_INVALID, "a persistent table needs MEMS_ORDER_REFERENCE");
 	if (seq_mask && mode != MEMS_MODE_MEMHASH) throw Error(MEMS_ERR_INVALID, "seq_mask applies to MEMS_MODE_MEMHASH only");
 	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
 	if (b.key64)
-		find_matches_typed<uint64_t>(b, mode, order, table_size, seq_mask, out, persistent);
+		find_matches_typed<uint64_t>(b, mode, order, table_size, seq_mask, out, persistent, start_points);
 	else
-		find_matches_typed<uint32_t>(b, mode, order, table_size, seq_mask, out, persistent);
+		find_matches_typed<uint32_t>(b, mode, order, table_size, seq_mask, out, persistent, start_points);
 }
+
+bool table_add_entry(HashTable& T, uint32_t seq_count, int64_t length, const int64_t* starts, int64_t mersize) {
+	if (T.buckets.empty()) {
+		if (!T.size) T.size = 40000u;
+		T.buckets.resize(T.size);
+	}
+	auto e = std::make_unique<Entry>();
+	e->seqcount = seq_count;
+	e->len = length;
+	e->mersize = mersize;
+	e->own.assign(starts, starts + seq_count);
+	e->start = e->own.data();
+	e_calc_offset(*e);
+	const int64_t ts = (int64_t)T.size;
+	std::vector<Entry*>& bucket = T.buckets[(size_t)(((e->offset % ts) + ts) % ts)];
+	size_t at = bucket_lower_bound(bucket, *e);
+	if (at != bucket.size() && !e_compare(*bucket[at], *e) && !e_compare(*e, *bucket[at])) {
+		++T.collisions;
+		return false;
+	}
+	// (the reference would call ExtendMatch here: a no-op for LoadFile, which runs before any sequence is added)
+	e->mersize = 0;  // stored copies lose m_mersize (MatchHashEntry.cpp:118-126)
+	at = bucket_lower_bound(bucket, *e);
+	bucket.insert(bucket.begin() + at, e.get());
+	T.stored.push_back(std::move(e));
+	++T.mem_count;
+	return true;
+}
+
+void table_list(const HashTable& T, MatchResult& out) { emit_table(T, out); }
 
 // ================================================================================================ sharded (multi-GPU)
 // One process per GPU.  The path shards in two exchanges (ParallelMemHash.cpp:42-121 is the
@@ -2026,11 +2138,20 @@ pack_hits_kernel(MatchArgs a, const uint32_t* __restrict__ hid, const uint32_t* 
 		off = mem_off[i];
 		out_len[i] = l;
 	}
-	const uint32_t cnt = n_hits - i0 < 32u ? n_hits - i0 : 32u;
-	for (uint32_t k = 0; k < cnt; ++k) {
+	// (lanes past n_hits hold len = 0: their turns copy nothing)  Eight hits' first 32 members are in flight at a time —
+	// one hit per turn would leave the warp waiting for a single dependent load — the rare longer lists follow.
+#pragma unroll 8
+	for (uint32_t k = 0; k < 32; ++k) {
 		const uint32_t sk = __shfl_sync(0xffffffffu, s, k), lk = __shfl_sync(0xffffffffu, len, k);
 		const uint32_t ok = __shfl_sync(0xffffffffu, off, k);
-		for (uint32_t t = lane; t < lk; t += 32) out_mem[ok + t] = a.vals[sk + t] | (strand_of<KeyT>(a.keys, sk + t) << 31);
+		if (lane < lk) out_mem[ok + lane] = a.vals[sk + lane] | (strand_of<KeyT>(a.keys, sk + lane) << 31);
+	}
+	if (__any_sync(0xffffffffu, len > 32u)) {
+		for (uint32_t k = 0; k < 32; ++k) {
+			const uint32_t sk = __shfl_sync(0xffffffffu, s, k), lk = __shfl_sync(0xffffffffu, len, k);
+			const uint32_t ok = __shfl_sync(0xffffffffu, off, k);
+			for (uint32_t t = 32 + lane; t < lk; t += 32) out_mem[ok + t] = a.vals[sk + t] | (strand_of<KeyT>(a.keys, sk + t) << 31);
+		}
 	}
 }
 

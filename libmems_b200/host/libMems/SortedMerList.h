@@ -114,6 +114,16 @@ public:
 	uint64_t SMLLength() const { return info.sml_length; }
 	bool IsCircular() const { return false; }
 	mems_sml_t handle() const { return sml; }
+	// MemorySML::Clone / DNAMemorySML::Clone (MemorySML.cpp:36-38): a new object over the same device-resident list
+	virtual SortedMerList* Clone() const {
+		SortedMerList* c = make_empty();
+		if (sml) {
+			mems_sml_t h = nullptr;
+			Context::check(mems_sml_clone(sml, &h));
+			c->adopt(h);
+		}
+		return c;
+	}
 	void adopt(mems_sml_t h) {  // used by MatchList::CreateMemorySMLs (batch build)
 		Clear();
 		sml = h;
@@ -121,6 +131,7 @@ public:
 	}
 
 protected:
+	virtual SortedMerList* make_empty() const { return new SortedMerList(); }
 	uint64_t mer_at(uint64_t offset, bool dna) const {
 		uint64_t f = 0, d = 0;
 		Context::check(mems_sml_seed_mers(sml, &offset, 1, &f, &d));
@@ -218,6 +229,20 @@ public:
 		if (h.version != FormatVersion()) throw MemsException(MEMS_ERR_UNSUPPORTED, "FileSML: unsupported file format");
 		if (h.circular) throw MemsException(MEMS_ERR_UNSUPPORTED, "circular sequences are not supported");
 		if (h.alphabet_bits != 2) throw MemsException(MEMS_ERR_UNSUPPORTED, "FileSML: not a DNA list");
+		// nothing is sized from the header before the header is plausible and the file is as long as it says
+		if (h.length > 0xffffffffull) throw MemsException(MEMS_ERR_INVALID, "FileSML: corrupt header (sequence length)");
+		if (h.seed_length < 1 || h.seed_length > 31 || h.seed == 0 ||
+		    (uint32_t)mems_get_seed_length(h.seed) != h.seed_length || (uint32_t)mems_get_seed_weight(h.seed) != h.seed_weight)
+			throw MemsException(MEMS_ERR_INVALID, "FileSML: corrupt header (seed pattern)");
+		{
+			const uint64_t want_words = (h.length * 2 + 31) / 32 + 2;
+			const uint64_t want_pos = h.length >= h.seed_length ? h.length - h.seed_length + 1 : 0;
+			f.seekg(0, std::ios::end);
+			const uint64_t file_size = (uint64_t)f.tellg();
+			f.seekg((std::streamoff)sizeof h, std::ios::beg);
+			if (file_size < sizeof h + want_words * sizeof(uint32_t) + want_pos * sizeof(smlSeqI_t))
+				throw MemsException(MEMS_ERR_INVALID, "FileSML: premature end of file");
+		}
 		const uint64_t n_words = (h.length * 2 + 31) / 32 + 2;
 		std::vector<uint32_t> words(n_words);
 		f.read(reinterpret_cast<char*>(words.data()), (std::streamsize)(n_words * sizeof(uint32_t)));
@@ -250,6 +275,7 @@ public:
 	const std::string& FileName() const { return filename; }
 
 protected:
+	SortedMerList* make_empty() const override { return new DNAFileSML(filename); }
 	std::string filename;
 };
 
@@ -257,6 +283,9 @@ protected:
 class DNAMemorySML : public SortedMerList {
 public:
 	uint64_t GetSeedMer(uint64_t offset) const override { return mer_at(offset, true); }
+	DNAMemorySML* Clone() const override { return static_cast<DNAMemorySML*>(SortedMerList::Clone()); }
+protected:
+	SortedMerList* make_empty() const override { return new DNAMemorySML(); }
 };
 
 }  // namespace mems

@@ -310,6 +310,105 @@ int ref_write_list(int n_seqs, const char* const* seqs, const uint64_t* lens, ui
 	}
 }
 
+namespace {
+void flatten(MatchList& ml, int64_t** flat_out, uint64_t* n_flat_out, uint64_t* n_matches_out) {
+	std::vector<int64_t> flat;
+	for (size_t i = 0; i < ml.size(); ++i) {
+		flat.push_back((int64_t)ml[i]->SeqCount());
+		flat.push_back((int64_t)ml[i]->Length());
+		for (uint s = 0; s < ml[i]->SeqCount(); ++s) flat.push_back((int64_t)ml[i]->Start(s));
+	}
+	*n_matches_out = ml.size();
+	*n_flat_out = flat.size();
+	*flat_out = (int64_t*)malloc(sizeof(int64_t) * (flat.size() ? flat.size() : 1));
+	memcpy(*flat_out, flat.data(), sizeof(int64_t) * flat.size());
+}
+void build_list(MatchList& ml, int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed) {
+	for (int g = 0; g < n_seqs; ++g) {
+		ml.seq_table.push_back(new gnSequence(seqs[g], lens[g]));
+		ml.seq_filename.push_back("mem");
+		DNAMemorySML* sml = new DNAMemorySML();
+		sml->Create(*ml.seq_table[g], seed);
+		ml.sml_table.push_back(sml);
+	}
+}
+}
+
+// MemHash::FindMatchesFromPosition (MemHash.cpp:117-127) with LogProgress and SetMatchLog streams attached
+// (MatchFinder.cpp:298-309, MemHash.cpp:237-241); the two log texts are strdup'ed (ref_free).
+int ref_find_matches_from(int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed, const uint64_t* start_points,
+                          int64_t** flat_out, uint64_t* n_flat_out, uint64_t* n_matches_out, uint64_t* counts_out,
+                          char** progress_out, char** match_log_out) {
+	try {
+		MatchList ml;
+		build_list(ml, n_seqs, seqs, lens, seed);
+		MemHash mh;
+		std::ostringstream progress, matches;
+		mh.LogProgress(&progress);
+		mh.SetMatchLog(&matches);
+		std::vector<gnSeqI> sp(start_points, start_points + n_seqs);
+		mh.FindMatchesFromPosition(ml, sp);
+		if (counts_out) { counts_out[0] = mh.MemCount(); counts_out[1] = mh.MemCollisionCount(); }
+		flatten(ml, flat_out, n_flat_out, n_matches_out);
+		if (progress_out) *progress_out = strdup(progress.str().c_str());
+		if (match_log_out) *match_log_out = strdup(matches.str().c_str());
+		mh.Clear();
+		ml.Clear();
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	} catch (const char* s) {
+		g_err = s;
+		return 2;
+	}
+}
+
+// MemHash::WriteFile (MemHash.cpp:307-328) of the MemHash result: the .mems text
+int ref_mems_write_file(int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed, char** text_out) {
+	try {
+		MatchList ml;
+		build_list(ml, n_seqs, seqs, lens, seed);
+		MemHash mh;
+		mh.FindMatches(ml);
+		std::ostringstream os;
+		mh.WriteFile(os);
+		*text_out = strdup(os.str().c_str());
+		mh.Clear();
+		ml.Clear();
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	}
+}
+
+// MemHash::LoadFile (MemHash.cpp:266-305) into a MemHash that holds the sequences (AddHashEntry extends what it
+// inserts, so the sequences must be there) -> its match list and counters
+int ref_mems_load_file(int n_seqs, const char* const* seqs, const uint64_t* lens, uint64_t seed, const char* text,
+                       int64_t** flat_out, uint64_t* n_flat_out, uint64_t* n_matches_out, uint64_t* counts_out) {
+	try {
+		MatchList ml;
+		build_list(ml, n_seqs, seqs, lens, seed);
+		MemHash mh;
+		for (int g = 0; g < n_seqs; ++g) mh.AddSequence(ml.sml_table[g], ml.seq_table[g]);
+		std::istringstream is(text);
+		mh.LoadFile(is);
+		if (counts_out) { counts_out[0] = mh.MemCount(); counts_out[1] = mh.MemCollisionCount(); }
+		mh.GetMatchList(ml);
+		flatten(ml, flat_out, n_flat_out, n_matches_out);
+		mh.Clear();
+		ml.Clear();
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	} catch (const char* s) {
+		g_err = s;
+		return 2;
+	}
+}
+
 // mask for mode 3 (MaskedMemHash::SetMask, MaskedMemHash.h:32)
 void ref_set_seq_mask(uint64_t mask) { g_seq_mask = mask; }
 

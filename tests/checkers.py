@@ -243,6 +243,57 @@ class Reference(_Checker):
             raise RuntimeError(self.err())
         return text.value.decode()
 
+    def _seq_args(self, seqs):
+        bufs = [_as_bytes(s) for s in seqs]
+        arr = (ctypes.c_char_p * len(bufs))(*bufs)
+        lens = (u64 * len(bufs))(*[len(b) for b in bufs])
+        return bufs, arr, lens
+
+    def _take_flat(self, flat, nflat):
+        out = np.ctypeslib.as_array(flat, shape=(max(nflat.value, 1),))[:nflat.value].copy()
+        self.lib.ref_free(flat)
+        return flat_to_matches(out)
+
+    def _take_text(self, p):
+        text = ctypes.string_at(p).decode()
+        self.lib.ref_free(p)
+        return text
+
+    def find_matches_from(self, seqs, seed, start_points):
+        """MemHash::FindMatchesFromPosition with LogProgress / SetMatchLog attached: (matches, info)."""
+        bufs, arr, lens = self._seq_args(seqs)
+        sp = (u64 * len(bufs))(*[int(x) for x in start_points])
+        flat = ctypes.POINTER(ctypes.c_int64)()
+        nflat, nm = u64(), u64()
+        counts = (u64 * 2)()
+        prog, mlog = _vp(), _vp()
+        rc = self.lib.ref_find_matches_from(len(bufs), arr, lens, u64(seed), sp, ctypes.byref(flat), ctypes.byref(nflat),
+                                            ctypes.byref(nm), counts, ctypes.byref(prog), ctypes.byref(mlog))
+        if rc:
+            raise RuntimeError(self.err())
+        return self._take_flat(flat, nflat), {"mem_count": counts[0], "collisions": counts[1],
+                                              "progress": self._take_text(prog), "match_log": self._take_text(mlog)}
+
+    def mems_write_file(self, seqs, seed):
+        """MemHash::FindMatches + MemHash::WriteFile -> .mems text."""
+        bufs, arr, lens = self._seq_args(seqs)
+        text = _vp()
+        if self.lib.ref_mems_write_file(len(bufs), arr, lens, u64(seed), ctypes.byref(text)):
+            raise RuntimeError(self.err())
+        return self._take_text(text)
+
+    def mems_load_file(self, seqs, seed, text):
+        """MemHash::LoadFile of bare match lines into a MemHash holding the sequences -> (matches, counters)."""
+        bufs, arr, lens = self._seq_args(seqs)
+        flat = ctypes.POINTER(ctypes.c_int64)()
+        nflat, nm = u64(), u64()
+        counts = (u64 * 2)()
+        rc = self.lib.ref_mems_load_file(len(bufs), arr, lens, u64(seed), text.encode(), ctypes.byref(flat), ctypes.byref(nflat),
+                                         ctypes.byref(nm), counts)
+        if rc:
+            raise RuntimeError(self.err())
+        return self._take_flat(flat, nflat), {"mem_count": counts[0], "collisions": counts[1]}
+
     def seed_occurrence(self, seq, seed):
         s = _as_bytes(seq)
         out = np.zeros(len(s), np.float32)

@@ -6,6 +6,11 @@
 //        facade_demo writesml <seed_weight> <raw-sequence-file> <out.sml>   DNAFileSML::Create
 //        facade_demo loadsml <file.sml>       DNAFileSML::LoadFile, prints seed, lengths and the first entries
 //        facade_demo smllayout                sizeof / offsets of the façade's SMLHeader
+//        facade_demo frompos <seed_weight> <start0,start1,...> <raw-sequence-file>...   MemHash::FindMatchesFromPosition with
+//                             LogProgress and SetMatchLog attached: matches on stdout, then "#progress" + text, "#matchlog" + text
+//        facade_demo memsfile <seed_weight> <raw-sequence-file>...   MemHash::WriteFile of the search on stdout
+//        facade_demo loadmems <file with bare match lines>            MemHash::LoadFile, prints the table + counters
+//        facade_demo clone <seed_weight> <raw-sequence-file>          SortedMerList::Clone: the clone outlives the original
 #include <cstddef>
 #include <fstream>
 #include <iostream>
@@ -30,6 +35,67 @@ int main(int argc, char** argv) {
 	if (argc < 3) return 2;
 	const std::string mode = argv[1];
 	try {
+		if (mode == "frompos" || mode == "memsfile") {
+			const int first = mode == "frompos" ? 4 : 3;
+			if (argc <= first) return 2;
+			MatchList ml;
+			for (int i = first; i < argc; ++i) {
+				std::ifstream f(argv[i], std::ios::binary);
+				std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+				ml.seq_table.push_back(new genome::gnSequence(s));
+				ml.seq_filename.push_back(argv[i]);
+			}
+			ml.CreateMemorySMLs((unsigned)atoi(argv[2]), nullptr);
+			MemHash mh;
+			mh.SetOutputOrder(MEMS_ORDER_REFERENCE);
+			if (mode == "memsfile") {
+				mh.FindMatches(ml);
+				mh.WriteFile(std::cout);
+			} else {
+				std::vector<uint64_t> sp;
+				std::stringstream list(argv[3]);
+				std::string tok;
+				while (std::getline(list, tok, ',')) sp.push_back(std::stoull(tok));
+				std::ostringstream progress, matchlog, offsets;
+				mh.LogProgress(&progress);
+				mh.SetMatchLog(&matchlog);
+				mh.SetOffsetLog(&offsets);
+				mh.FindMatchesFromPosition(ml, sp);
+				for (Match* m : ml) std::cout << *m << "\n";
+				std::cout << "#counts " << mh.MemCount() << " " << mh.MemCollisionCount() << "\n";
+				std::cout << "#progress\n" << progress.str() << "#matchlog\n" << matchlog.str() << "#offsets\n" << offsets.str();
+			}
+			mh.Clear();
+			ml.Clear();
+			return 0;
+		}
+		if (mode == "loadmems") {
+			std::ifstream f(argv[2]);
+			MemHash mh;
+			mh.LoadFile(f);
+			MatchList ml;
+			mh.GetMatchList(ml);
+			for (Match* m : ml) std::cout << *m << "\n";
+			std::cout << "#counts " << mh.MemCount() << " " << mh.MemCollisionCount() << "\n";
+			for (Match* m : ml) m->Free();
+			return 0;
+		}
+		if (mode == "clone") {
+			if (argc < 4) return 2;
+			std::ifstream f(argv[3], std::ios::binary);
+			std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+			genome::gnSequence seq(s);
+			DNAMemorySML* a = new DNAMemorySML();
+			a->Create(seq, getSeed((unsigned)atoi(argv[2])));
+			const bmer first = (*a)[0];
+			DNAMemorySML* b = a->Clone();
+			delete a;  // the clone keeps the device-resident list alive
+			const bmer again = (*b)[0];
+			std::cout << (first.position == again.position && first.mer == again.mer && b->SMLLength() + b->SeedLength() - 1 == s.size())
+			          << " " << b->GetSeedMer(again.position) << " " << again.mer << "\n";
+			delete b;
+			return 0;
+		}
 		if (mode == "writesml") {
 			if (argc < 5) return 2;
 			std::ifstream f(argv[3], std::ios::binary);

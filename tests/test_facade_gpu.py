@@ -164,3 +164,103 @@ def test_load_smls_creates_then_reuses_the_files(tmp_path):
     got, log = run_demo(tmp_path, "smlmemhash", 13, gs)  # other weight: seed mismatch, lists are recreated
     assert got == Oracle().find_matches(0, gs, mems.get_seed(13))[0]
     assert log.count("Default seed mismatch") == 3
+
+
+# ---- façade members beyond FindMatches, against what the unmodified reference produced (tests/golden/facade.json) ----
+import json  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _facade_cases():
+    return json.load(open(os.path.join(GOLD, "facade.json")))
+
+
+def _write_seqs(tmp_path, seqs):
+    files = []
+    for i, s in enumerate(seqs):
+        p = tmp_path / ("seq%d.raw" % i)
+        p.write_text(s)
+        files.append(str(p))
+    return files
+
+
+def _demo(args):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(DEMO):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([DEMO] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def _parse_matches(text):
+    out = []
+    for line in text.splitlines():
+        v = [int(x) for x in line.split("\t")]
+        out.append((len(v) - 1, v[0]) + tuple(v[1:]))
+    return out
+
+
+def test_find_matches_from_position_c_abi():
+    """MemHash::FindMatchesFromPosition through mems_match_params_t.start_points."""
+    from gpu_util import gpu_context
+    ctx = gpu_context()
+    for case in _facade_cases():
+        seqs = [s.encode() for s in case["seqs"]]
+        smls = ctx.create_smls(seqs, case["seed"])
+        flat, info = ctx.find_matches(smls, order=mems.ORDER_REFERENCE, start_points=case["start_points"])
+        assert mems.flat_to_matches(flat) == [tuple(m) for m in case["matches"]], case["tag"]
+        assert info["mem_count"] == case["mem_count"] and info["collisions"] == case["collisions"], case["tag"]
+        flat, _ = ctx.find_matches(smls, order=mems.ORDER_CANONICAL, start_points=case["start_points"])
+        assert mems.flat_to_matches(flat) == sorted(set(tuple(m) for m in case["matches"])), case["tag"]
+    ctx.close()
+
+
+def test_from_position_logs_and_mems_files_facade(tmp_path):
+    for case in _facade_cases():
+        d = tmp_path / case["tag"]
+        d.mkdir()
+        files = _write_seqs(d, case["seqs"])
+        out = _demo(["frompos", str(case["weight"]), ",".join(str(x) for x in case["start_points"])] + files)
+        body, rest = out.split("#counts ", 1)
+        counts, rest = rest.split("\n#progress\n", 1)
+        progress, rest = rest.split("#matchlog\n", 1)
+        matchlog, offsets = rest.split("#offsets\n", 1)
+        assert _parse_matches(body) == [tuple(m) for m in case["matches"]], case["tag"]
+        assert counts.split() == [str(case["mem_count"]), str(case["collisions"])], case["tag"]
+        assert progress == case["progress"], case["tag"]  # LogProgress: the reference's text, replayed
+        # SetMatchLog: the same records (the reference logs in order of discovery, the façade in table order)
+        assert sorted(matchlog.splitlines()) == sorted(case["match_log"].splitlines()), case["tag"]
+        assert offsets == ""  # SetOffsetLog: written only when a search restarts, which neither does on these inputs
+        # MemHash::WriteFile: byte for byte the reference's .mems text
+        assert _demo(["memsfile", str(case["weight"])] + files) == case["mems_file"], case["tag"]
+        # MemHash::LoadFile
+        for name, load in case["loads"].items():
+            f = d / (name + ".mems")
+            f.write_text("\n".join(load["lines"]) + "\n")
+            out = _demo(["loadmems", str(f)])
+            body, counts = out.split("#counts ", 1)
+            assert _parse_matches(body) == [tuple(m) for m in load["matches"]], (case["tag"], name)
+            assert counts.split() == [str(load["mem_count"]), str(load["collisions"])], (case["tag"], name)
+
+
+def test_sorted_mer_list_clone(tmp_path):
+    g = synth.genome_family(1, 5000, seed=35)[0]
+    p = tmp_path / "seq.raw"
+    p.write_bytes(g.tobytes())
+    out = _demo(["clone", "13", str(p)]).split()
+    assert out[0] == "1" and out[1] == out[2]  # same first entry after the original is gone; GetSeedMer is the canonical mer
+    # and through the C-ABI
+    from gpu_util import gpu_context
+    ctx = gpu_context()
+    a = ctx.create_sml(g, mems.get_seed(13))
+    b = a.clone()
+    want = a.read()
+    a.close()
+    got = b.read()
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    ctx.close()

@@ -93,3 +93,23 @@ add(1, [synth.repeat_genome(12000, seed=28, families=6, copies=7, min_len=60, ma
     R.get_seed(11), "repeat_w12_drops")
 add(2, synth.genome_family(3, 3000, seed=29, n_indels=3, max_indel=20), R.get_seed(13), "pairwise_w13")
 dump("matchlists.json", ml)
+
+# --- façade members beyond FindMatches (tests/test_facade_gpu.py, tests/test_table_cpu.py) -------------------------
+# MemHash::FindMatchesFromPosition with LogProgress / SetMatchLog attached, MemHash::WriteFile, MemHash::LoadFile
+fac = []
+for tag, G, n, w, gseed, sp in [("three_w13", 3, 30000, 13, 5, [5000, 100, 20000]), ("pair_w11", 2, 25000, 11, 6, [0, 0]),
+                                ("four_w15", 4, 15000, 15, 7, [0, 14000, 3, 20000]), ("pair_w16_past_end", 2, 12000, 16, 9, [100, 50000])]:
+    sd = R.get_seed(w)
+    gs = synth.genome_family(G, n, seed=gseed, snp_rate=0.03)
+    matches, info = R.find_matches_from(gs, sd, sp)
+    text = R.mems_write_file(gs, sd)
+    lines = [ln for ln in text.split("\n")[2 + 2 * G + 1:] if ln]
+    variants = {"as_written": lines, "reversed": lines[::-1], "with_repeats": lines + lines[:10]}
+    loads = {}
+    for k, v in variants.items():
+        ml, il = R.mems_load_file(gs, sd, "\n".join(v) + "\n")
+        loads[k] = {"lines": v, "matches": [list(m) for m in ml], "mem_count": il["mem_count"], "collisions": il["collisions"]}
+    fac.append({"tag": tag, "weight": w, "seed": sd, "seqs": [s(x) for x in gs], "start_points": sp,
+                "matches": [list(m) for m in matches], "mem_count": info["mem_count"], "collisions": info["collisions"],
+                "progress": info["progress"], "match_log": info["match_log"], "mems_file": text, "loads": loads})
+dump("facade.json", fac)
