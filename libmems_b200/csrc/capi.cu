@@ -276,7 +276,8 @@ int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls, const 
 		try {
 			if (p.table && p.table->t.size == 0) p.table->t.size = p.table_size ? p.table_size : 40000u;
 			find_matches_on_batch(*b, p.mode, (p.mode == MEMS_MODE_REPEAT || p.table) ? MEMS_ORDER_REFERENCE : p.order,
-			                      p.table_size ? p.table_size : 40000u, p.seq_mask, m->r, p.table ? &p.table->t : nullptr);
+			                      p.table_size ? p.table_size : 40000u, p.seq_mask, m->r, p.table ? &p.table->t : nullptr,
+			                      p.start_points);
 		} catch (...) {
 			delete m;
 			throw;

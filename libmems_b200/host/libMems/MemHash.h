@@ -210,7 +210,9 @@ protected:
 			}
 		}
 		if (total_mers == 0) return;
-		std::stable_sort(events.begin(), events.end(), [](const Event& a, const Event& b) { return a.mer < b.mer || (a.mer == b.mer && a.sml < b.sml); });
+		// (lists that reach the same mer: the reference's merge list takes the one that arrived last first; with the common
+		// case — all lists end on the same largest mer — that is the higher list index)
+		std::stable_sort(events.begin(), events.end(), [](const Event& a, const Event& b) { return a.mer < b.mer || (a.mer == b.mer && a.sml > b.sml); });
 		float progress = -1;
 		for (const Event& e : events) {
 			mers_processed += (double)e.size;

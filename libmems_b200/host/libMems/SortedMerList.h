@@ -240,6 +240,8 @@ public:
 			f.seekg(0, std::ios::end);
 			const uint64_t file_size = (uint64_t)f.tellg();
 			f.seekg((std::streamoff)sizeof h, std::ios::beg);
+			if (file_size < sizeof h + want_words * sizeof(uint32_t))
+				throw MemsException(MEMS_ERR_INVALID, "FileSML: error reading sequence data");
 			if (file_size < sizeof h + want_words * sizeof(uint32_t) + want_pos * sizeof(smlSeqI_t))
 				throw MemsException(MEMS_ERR_INVALID, "FileSML: premature end of file");
 		}

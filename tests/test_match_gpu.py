@@ -125,10 +125,13 @@ def test_medium_size_vs_oracle(ctx, orc):
     assert info["n_hits"] == winfo["hits"]
 
 
-def test_long_walks_between_sparse_hits(ctx, orc):
+@pytest.mark.parametrize("w", [15, 19, 16])
+def test_long_walks_between_sparse_hits(ctx, orc, w):
     """Few hits, long matching diagonal: the extension walks exceed a warp's probe budget and are finished
-    by the CTA-wide walker, including the case where a long walk has to link two distant hit groups."""
-    seed = mems.get_seed(15)
+    by the CTA-wide walker, including the case where a long walk has to link two distant hit groups.  w19 runs the
+    64-bit-key instances of every kernel, w16 the even-weight rule (a mer equal to its own reverse complement never
+    matches across orientations)."""
+    seed = mems.get_seed(w)
     rng = np.random.default_rng(99)
     T = synth.random_genome(30_000, rng)
     M1, M2 = synth.random_genome(60, rng), synth.random_genome(60, rng)
@@ -223,12 +226,14 @@ def test_multi_seed_accumulation(ctx, orc, it):
     assert mems.flat_to_matches(flat) == orc.find_matches(0, gs, seeds[0])[0]
 
 
-def test_grid_wide_walks(orc):
-    """With the warp and CTA budgets shrunk to 2, the long diagonals of the sparse-hit inputs are finished by the
-    grid-cooperative walker (all CTAs on one walk, grid barrier per round), including the linking case."""
+@pytest.mark.parametrize("w", [15, 19])
+def test_grid_wide_walks(orc, w):
+    """With the warp and CTA budgets shrunk to 1, the long diagonals of the sparse-hit inputs are finished by the
+    grid-cooperative walker (all CTAs on one walk, grid barrier per round), including the linking case; w19 = the
+    64-bit-key instances (giant_walk_kernel<u64>, long_walk_*<u64>)."""
     c = gpu_context()
     c.set_test_hooks(walk_budget=1)
-    seed = mems.get_seed(15)
+    seed = mems.get_seed(w)
     rng = np.random.default_rng(98)
     T = synth.random_genome(40_000, rng)
     M1, M2 = synth.random_genome(60, rng), synth.random_genome(60, rng)
@@ -342,3 +347,29 @@ def test_contexts_are_independent_across_threads(orc):
         th.join()
     assert not errors, errors
     assert got == want
+
+
+def test_u64_medium_size_vs_oracle(ctx, orc):
+    """64-bit keys (w19, the seed of BASELINE configs 3 and 5) on several 300 kbp genomes with inversions: every kernel's
+    <u64> instance against the oracle, in the reference's order too."""
+    seed = mems.get_seed(19)
+    gs = synth.genome_family(5, 300_000, seed=321)
+    want, winfo = orc.find_matches(0, gs, seed)
+    got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
+    assert got == canonical(want)
+    assert info["n_hits"] == winfo["hits"]
+    got_ref, info_ref = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH, mems.ORDER_REFERENCE)
+    assert got_ref == want and info_ref["collisions"] == winfo["collisions"]
+
+
+def test_non_palindromic_patterns(ctx, orc):
+    """The two entries of the reference's seed table that are not palindromes (weight 19 rank 2, weight 21 rank 1,
+    SURVEY.md 0-7) and a hand-made asymmetric pattern: cared base i sits at another offset on the other strand, so
+    reverse members are compared offset by offset.  Inputs carry an inversion, i.e. reverse members."""
+    for seed in (mems.get_seed(19, 2), mems.get_seed(21, 1), 0b1101000111):
+        gs = synth.genome_family(4, 40_000, seed=77, snp_rate=0.02, n_indels=4, max_indel=20)
+        gs.append(synth.revcomp(gs[1]))
+        want, winfo = orc.find_matches(0, gs, seed)
+        got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
+        assert got == canonical(want), hex(seed)
+        assert info["n_hits"] == winfo["hits"]

@@ -113,16 +113,19 @@ def test_bad_seeds_rejected(ctx):
         ctx.create_sml(b"ACGT" * 20, (1 << 32) - 1)  # span 32: unsupported (reference UB)
 
 
-def test_large_sort_properties(ctx):
+@pytest.mark.parametrize("w", [15, 19])
+def test_large_sort_properties(ctx, w):
     """Full-size property checks where the oracle would be slow: sortedness, permutation, and that every
-    sorted entry's key is the key at its position."""
-    seed = mems.get_seed(15)
+    sorted entry's key is the key at its position — for 32-bit keys (w15) and for 64-bit keys (w19: the
+    onesweep_kernel<u64> / extract_kernel<u64> instances BASELINE configs 3 and 5 run on)."""
+    seed = mems.get_seed(w)
+    L = mems.get_seed_length(seed)
     gs = synth.genome_family(3, 3_000_000, seed=5)
     smls = ctx.create_smls(gs, seed)
     for g, sml in zip(gs, smls):
         pos, mers = sml.read()
         n = sml.sml_length()
-        assert n == len(g) - 23 + 1
+        assert n == len(g) - L + 1
         assert np.all(mers[1:] >= mers[:-1])
         assert np.array_equal(np.sort(pos), np.arange(n, dtype=np.uint32))
         eq = mers[1:] == mers[:-1]
@@ -142,3 +145,15 @@ def test_seed_occurrence(ctx, orc):
         assert np.array_equal(s.seed_occurrence(), orc.seed_occurrence(q, seed))
     single = ctx.create_sml(g, mems.get_seed(15))
     assert np.array_equal(single.seed_occurrence(), orc.seed_occurrence(g, mems.get_seed(15)))
+
+
+def test_more_than_256_sequences_rejected(ctx):
+    """A create call sorts the per-sequence lists with one 8-bit counting pass on the sequence tag: more than 256
+    sequences must be refused cleanly (MEMS_ERR_UNSUPPORTED), not overflow that pass."""
+    seqs = [synth.random_genome(60, np.random.default_rng(i)) for i in range(257)]
+    with pytest.raises(mems.MemsError) as e:
+        ctx.create_smls(seqs, mems.get_seed(7))
+    assert e.value.code == 4
+    smls = ctx.create_smls(seqs[:256], mems.get_seed(7))  # 256 is fine, accessors included
+    pos, mers = smls[255].read()
+    assert len(pos) == 60 - mems.get_seed_length(mems.get_seed(7)) + 1 and np.all(mers[1:] >= mers[:-1])
