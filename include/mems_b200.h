@@ -141,6 +141,15 @@ typedef struct {
  * -> distinct matches. */
 int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls,
                       const mems_match_params_t* params, mems_matches_t* out);
+/* Many independent small problems in ONE launch set: the gap re-anchoring callers run CreateMemorySMLs + FindMatches on
+ * thousands of short sequence sets (ProgressiveAligner::pairwiseAnchorSearch, ProgressiveAligner.cpp:589-678, under
+ * `omp parallel for` at :695; Aligner::SearchLCBGaps, Aligner.cpp:784-930), where a call costs launch latency, not
+ * work.  Problem p owns the next n_seqs[p] entries of seqs / lens (at most MEMS_MAX_SEQS each, 256 sequences in all);
+ * all problems share one seed pattern.  out receives n_problems match lists; out[p] is exactly what
+ * mems_sml_create_batch + mems_find_matches return for problem p alone.  MEMS_MODE_MEMHASH or MEMS_MODE_PAIRWISE,
+ * MEMS_ORDER_ANY or MEMS_ORDER_CANONICAL. */
+int mems_find_matches_many(mems_ctx_t ctx, int n_problems, const int* n_seqs, const char* const* seqs, const uint64_t* lens,
+                           uint64_t seed, const mems_match_params_t* params, mems_matches_t* out);
 /* MemHash's mem_table as a persistent object (MemHash::Clear empties it, MemHash.cpp:76-93; ClearSequences keeps it) */
 int mems_table_create(uint32_t table_size /* 0 = 40000 */, mems_table_t* out);
 void mems_table_clear(mems_table_t t);

@@ -53,7 +53,7 @@ EXPORTS = [
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_clone", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
+    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_find_matches_many", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_shard_exchange_plan", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
     "mems_test_hooks",
@@ -98,6 +98,8 @@ def load():
     lib.mems_sml_seed_occurrence.argtypes = [_vp, _vp]
     lib.mems_find_matches.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(MatchParams),
                                       ctypes.POINTER(_vp)]
+    lib.mems_find_matches_many.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_vp),
+                                           ctypes.POINTER(_u64), _u64, ctypes.POINTER(MatchParams), ctypes.POINTER(_vp)]
     lib.mems_table_create.argtypes = [ctypes.c_uint32, ctypes.POINTER(_vp)]
     lib.mems_table_clear.argtypes = [_vp]
     lib.mems_table_destroy.argtypes = [_vp]
@@ -288,6 +290,30 @@ class Context:
         flat = view.view(_OwnedArray)
         flat._keep = keep
         return flat, d
+
+    def find_matches_many(self, problems, seed, mode=MODE_MEMHASH, order=ORDER_ANY):
+        """Many independent small problems (each a list of sequences) in one launch set; returns one (flat, info) per
+        problem, equal to create_smls + find_matches on that problem alone."""
+        parts = [_host_ptr(s) for prob in problems for s in prob]
+        n = len(parts)
+        counts = (ctypes.c_int * len(problems))(*[len(prob) for prob in problems])
+        ptrs = (_vp * n)(*[p[0] for p in parts])
+        lens = (_u64 * n)(*[p[1] for p in parts])
+        params = MatchParams(mode, order, 0, 0, None, 0, None)
+        out = (_vp * len(problems))()
+        self._check(self.lib.mems_find_matches_many(self.h, len(problems), counts, ptrs, lens, seed, ctypes.byref(params), out))
+        res = []
+        for g in range(len(problems)):
+            h = _vp(out[g])
+            info = MatchesInfo()
+            self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
+            d = {k: (float if k == "host_replay_ms" else int)(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+            flat = np.zeros(0, np.int64)
+            if info.n_flat:
+                flat = np.ctypeslib.as_array(self.lib.mems_matches_data(h), shape=(int(info.n_flat),)).copy()
+            self.lib.mems_matches_destroy(h)
+            res.append((flat, d))
+        return res
 
     # -- sharded (one process per GPU) ----------------------------------------------------------------
     def create_comm(self, unique_id, rank, world):

@@ -21,7 +21,7 @@ int bits_for(uint64_t max_value) {  // bits needed to store values 0..max_value
 }
 
 static void layout_batch(Batch& b, const std::vector<uint64_t>& lens, uint32_t tag0 = 0, int force_pos_bits = 0,
-                         int force_seq_bits = 0) {
+                         int force_seq_bits = 0, const std::vector<int>* group_sizes = nullptr) {
 	// the per-sequence lists are one counting pass on the sequence tag (Batch::sorted_positions): 8 digit bits
 	if (lens.size() > 256)
 		throw Error(MEMS_ERR_UNSUPPORTED, "more than 256 sequences in one create call; build them in several batches");
@@ -39,7 +39,9 @@ static void layout_batch(Batch& b, const std::vector<uint64_t>& lens, uint32_t t
 		m.word_off = word_off;
 		m.seed_off = seed_off;
 		m.tag = tag0 + (uint32_t)g;
-		m.pad_ = 0;
+		m.group = 0;
+		m.group_first = tag0;
+		m.group_count = (uint32_t)lens.size();
 		byte_off += (lens[g] + 15) / 16 * 16;
 		word_off += seq_packed_words(lens[g]);  // keeps every sequence 16-byte aligned
 		seed_off += m.n_seeds;
@@ -57,7 +59,30 @@ static void layout_batch(Batch& b, const std::vector<uint64_t>& lens, uint32_t t
 		            "shard the sequences across devices");
 	if (b.n_total > radix_max_items())
 		throw Error(MEMS_ERR_UNSUPPORTED, "more than 2^30-1 seed positions in one device batch; shard across devices");
-	b.key64 = b.sd.key_bits > 32;
+	b.n_groups = 1;
+	b.max_group = b.n_seqs;
+	b.group_bits = 0;
+	if (group_sizes) {  // several independent problems in one batch
+		size_t at = 0;
+		b.max_group = 0;
+		for (size_t k = 0; k < group_sizes->size(); ++k) {
+			const int cnt = (*group_sizes)[k];
+			if (cnt < 1 || at + (size_t)cnt > lens.size()) throw Error(MEMS_ERR_INVALID, "bad problem sizes");
+			for (int j = 0; j < cnt; ++j) {
+				SeqMeta& m = b.meta[at + j];
+				m.group = (uint32_t)k;
+				m.group_first = (uint32_t)at;
+				m.group_count = (uint32_t)cnt;
+			}
+			at += (size_t)cnt;
+			b.max_group = std::max(b.max_group, cnt);
+		}
+		if (at != lens.size()) throw Error(MEMS_ERR_INVALID, "problem sizes do not add up to the sequence count");
+		b.n_groups = (int)group_sizes->size();
+		b.group_bits = b.n_groups > 1 ? bits_for((uint64_t)b.n_groups - 1) : 0;
+		if (b.sd.key_bits + b.group_bits > 64) throw Error(MEMS_ERR_UNSUPPORTED, "seed weight x problem count exceeds 64 key bits");
+	}
+	b.key64 = b.sd.key_bits + b.group_bits > 32;
 }
 
 // packed sequences are in place: extract keys, sort the union
@@ -65,7 +90,7 @@ static void extract_and_sort(Batch& b) {
 	Ctx* c = b.ctx.get();
 	const size_t key_bytes = b.key64 ? 8 : 4;
 	const uint64_t n = b.n_total;
-	SortPlan plan = make_sort_plan(b.sd.key_bits);
+	SortPlan plan = make_sort_plan(b.sort_bits());
 	// extraction output stays resident in position order: the window test of match extension reads it
 	DevBuf<uint8_t> keys_pos(c, n * key_bytes), keys_a(c, n * key_bytes), keys_b(c, n * key_bytes);
 	DevBuf<uint32_t> vals_a(c, n), vals_b(c, n);
@@ -88,13 +113,13 @@ static void extract_and_sort(Batch& b) {
 
 std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
                                                 const uint64_t* lens, uint64_t seed, uint32_t tag0, int pos_bits,
-                                                int seq_bits) {
+                                                int seq_bits, const std::vector<int>* group_sizes) {
 	auto b = std::make_shared<Batch>();
 	b->ctx = ctx;
 	b->sd = make_seed_desc(seed);
 	Ctx* c = ctx.get();
 	MEMS_CUDA(cudaSetDevice(c->device));
-	layout_batch(*b, std::vector<uint64_t>(lens, lens + n_seqs), tag0, pos_bits, seq_bits);
+	layout_batch(*b, std::vector<uint64_t>(lens, lens + n_seqs), tag0, pos_bits, seq_bits, group_sizes);
 	if (n_seqs == 0) return b;
 	const SeqMeta& last = b->meta.back();
 	const uint64_t total_bytes = last.byte_off + ((uint64_t)last.n_bases + 15) / 16 * 16;
@@ -152,9 +177,9 @@ Batch::~Batch() {
 }
 
 std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
-                                              const uint64_t* lens, uint64_t seed) {
+                                              const uint64_t* lens, uint64_t seed, const std::vector<int>* group_sizes) {
 	if (n_seqs < 1) throw Error(MEMS_ERR_INVALID, "need at least one sequence");
-	auto b = prepare_batch_from_ascii(ctx, n_seqs, seqs, lens, seed, 0, 0, 0);
+	auto b = prepare_batch_from_ascii(ctx, n_seqs, seqs, lens, seed, 0, 0, 0, group_sizes);
 	extract_and_sort(*b);  // queued behind the pack; the GPU works on it while the host looks at the gap flag
 	b->check_gap();
 	return b;

@@ -286,6 +286,36 @@ int mems_find_matches(mems_ctx_t ctx, int n_smls, const mems_sml_t* smls, const 
 	});
 }
 
+int mems_find_matches_many(mems_ctx_t ctx, int n_problems, const int* n_seqs, const char* const* seqs, const uint64_t* lens,
+                           uint64_t seed, const mems_match_params_t* params, mems_matches_t* out) {
+	if (!ctx) return fail(nullptr, MEMS_ERR_INVALID, "null context");
+	Ctx* c = ctx->c.get();
+	if (!n_seqs || !seqs || !lens || !out || n_problems < 1) return fail(c, MEMS_ERR_INVALID, "bad arguments");
+	return guarded(c, [&] {
+		MEMS_CUDA(cudaSetDevice(c->device));
+		mems_match_params_t p;
+		memset(&p, 0, sizeof p);
+		if (params) p = *params;
+		if (p.table || p.seq_mask || p.start_points) throw Error(MEMS_ERR_INVALID, "table, seq_mask and start_points do not apply to mems_find_matches_many");
+		std::vector<int> groups(n_seqs, n_seqs + n_problems);
+		int total = 0;
+		for (int g : groups) {
+			if (g < 1 || g > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "1..MEMS_MAX_SEQS sequences per problem");
+			total += g;
+		}
+		for (int i = 0; i < total; ++i)
+			if (lens[i] && !seqs[i]) throw Error(MEMS_ERR_INVALID, "null sequence pointer");
+		auto b = build_batch_from_ascii(ctx->c, total, seqs, lens, seed, &groups);
+		std::vector<MatchResult> results;
+		find_matches_many(*b, p.mode, p.order, results);
+		for (int g = 0; g < n_problems; ++g) {
+			auto* m = new mems_matches();
+			m->r = std::move(results[g]);
+			out[g] = m;
+		}
+	});
+}
+
 int mems_table_create(uint32_t table_size, mems_table_t* out) {
 	if (!out) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
 	return guarded(nullptr, [&] {

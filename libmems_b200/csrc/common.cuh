@@ -49,7 +49,11 @@ struct SeqMeta {
 	uint32_t n_bases;
 	uint32_t n_seeds;   // SMLLength: n_bases - L + 1, or 0
 	uint32_t tag;       // sequence id written into the values (index in the batch; global id when sharded)
-	uint32_t pad_;
+	// A batch may hold several independent PROBLEMS (mems_find_matches_many): the sequences of one problem are a group.
+	// The group number sits above the key's 2w+1 bits, so no equal-seed run spans two problems.
+	uint32_t group;        // 0 for ordinary batches
+	uint32_t group_first;  // tag of the group's first sequence
+	uint32_t group_count;  // sequences in the group (= SeqCount of its matches)
 };
 
 struct Error : std::runtime_error {
@@ -166,7 +170,7 @@ void launch_pack(Ctx* c, const uint8_t* d_ascii, uint32_t* d_packed, const SeqMe
 // digit histograms of all radix passes (n_passes x 256 counters, zeroed by the caller).
 void launch_extract(Ctx* c, const uint32_t* d_packed, const SeqMeta* d_meta, const SeqMeta* h_meta, int n_seqs,
                     const SeedDesc& sd, int pos_bits, bool key64, void* d_keys, uint32_t* d_vals, uint32_t* d_hist,
-                    int n_passes, const int* pass_shift, const int* pass_bits);
+                    int n_passes, const int* pass_shift, const int* pass_bits);  // keys carry SeqMeta::group above sd.key_bits
 // Bit planes of a packed buffer: planes[i] = {high bits, low bits} of the 2-bit codes of bases 32i .. 32i+31
 // (bit j of a word <-> base 32i + j); n_words (a multiple of 2) packed words -> n_words / 2 entries.
 void launch_planes(Ctx* c, const uint32_t* d_packed, uint2* d_planes, uint64_t n_words);
@@ -219,7 +223,10 @@ struct Batch {
 	int n_seqs = 0;
 	int pos_bits = 0;  // value = (seq << pos_bits) | position
 	int seq_bits = 0;
+	int group_bits = 0;  // key = (group << sd.key_bits) | compact key; 0 unless the batch holds several problems
+	int n_groups = 1, max_group = 0;  // problems in the batch, sequences in the largest
 	bool key64 = false;
+	int sort_bits() const { return sd.key_bits + group_bits; }
 	uint64_t n_total = 0;  // seeds in the union
 	std::vector<SeqMeta> meta;
 	DevBuf<SeqMeta> d_meta;
@@ -243,12 +250,12 @@ struct Batch {
 	const uint32_t* sorted_positions();  // builds the per-sequence lists on first use
 };
 std::shared_ptr<Batch> build_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
-                                              const uint64_t* lens, uint64_t seed);
+                                              const uint64_t* lens, uint64_t seed, const std::vector<int>* group_sizes = nullptr);
 // layout + H2D + pack only (no keys yet).  tag0 = id of the first sequence; pos_bits/seq_bits > 0 override the
 // batch-local choice (sharded runs use the global ones).
 std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_seqs, const char* const* seqs,
                                                 const uint64_t* lens, uint64_t seed, uint32_t tag0, int pos_bits,
-                                                int seq_bits);
+                                                int seq_bits, const std::vector<int>* group_sizes = nullptr);
 int bits_for(uint64_t max_value);
 struct SeqRef {
 	const Batch* batch;
@@ -334,6 +341,8 @@ void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, u
 bool table_add_entry(HashTable& T, uint32_t seq_count, int64_t length, const int64_t* starts, int64_t mersize);
 // the table's content in output order (buckets in order, front to back)
 void table_list(const HashTable& T, MatchResult& out);
+// every group of the batch as its own problem (MEMS_MODE_MEMHASH / PAIRWISE, ORDER_ANY / CANONICAL): out[g] = group g's matches
+void find_matches_many(Batch& b, int mode, int order, std::vector<MatchResult>& out);
 void find_matches_sharded(std::shared_ptr<Ctx> ctx, Comm* comm, int n_seqs, const char* const* seqs, const uint64_t* lens,
                           uint64_t seed, int mode, int order, MatchResult& out);
 

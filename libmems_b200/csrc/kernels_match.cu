@@ -56,7 +56,8 @@ struct MatchArgs {
 	uint32_t n;
 	int pos_bits;
 	uint32_t pos_mask;
-	int n_seqs;
+	int n_seqs;            // sequences in the batch (all problems together)
+	int max_group;         // sequences in its largest problem (= n_seqs unless the batch holds several, SeqMeta::group)
 	int mode;
 	uint64_t seq_set;  // MaskedMemHash filter: required member set, bit g = sequence g (0 = no filter)
 	int test_hash_bits;  // 0 = use the full diagonal hash; n > 0 keeps only n bits (tests force bucket collisions with it)
@@ -99,11 +100,13 @@ __device__ __forceinline__ uint16_t serial_run(const MatchArgs& a, uint32_t i, u
 	bool ok = true;
 	if (a.mode == MEMS_MODE_MEMHASH) {
 		// at most one occurrence per sequence (repeat_tolerance 0), >= 2 sequences
-		uint64_t seen = 1ull << (a.vals[i] >> a.pos_bits);
+		// (sequence numbers relative to the run's problem: a problem has at most MEMS_MAX_SEQS sequences, a batch of many more)
+		const uint32_t g0 = a.n_seqs > 64 ? a.meta[a.vals[i] >> a.pos_bits].group_first : 0u;
+		uint64_t seen = 1ull << ((a.vals[i] >> a.pos_bits) - g0);
 		uint32_t j = i + 1;
 		while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
 			if (ok) {
-				uint64_t bit = 1ull << (a.vals[j] >> a.pos_bits);
+				uint64_t bit = 1ull << ((a.vals[j] >> a.pos_bits) - g0);
 				if (seen & bit) ok = false;
 				seen |= bit;
 			}
@@ -1091,13 +1094,22 @@ giant_walk_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, c
 }
 
 // ------------------------------------------------------------------------------------------------ 6. emit
-__global__ void emit_size_kernel(const uint32_t* __restrict__ comp_rep, const uint32_t* __restrict__ hid,
-                                 const uint16_t* __restrict__ hit_len, uint32_t n_comp, int mode, int n_seqs,
-                                 uint32_t* __restrict__ rec_size) {
+__global__ void emit_size_kernel(MatchArgs a, const uint32_t* __restrict__ comp_rep, const uint32_t* __restrict__ hid,
+                                 const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_comp,
+                                 uint32_t* __restrict__ rec_size, uint32_t* __restrict__ rec_group) {
 	const uint32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
 	if (comp >= n_comp) return;
-	const uint32_t len = hit_len[hid[comp_rep[comp]]] & ~kFirstStrandBit;
-	rec_size[comp] = 2u + (mode == MEMS_MODE_REPEAT ? len : (uint32_t)n_seqs);
+	const uint32_t h = hid[comp_rep[comp]];
+	const uint32_t len = hit_len[h] & ~kFirstStrandBit;
+	uint32_t count = (uint32_t)a.n_seqs;
+	if (a.max_group != a.n_seqs) {  // several problems in the batch: SeqCount is the problem's
+		const SeqMeta m = a.meta[a.vals[hit_start[h]] >> a.pos_bits];
+		count = m.group_count;
+		if (rec_group) rec_group[comp] = m.group;
+	} else if (rec_group) {
+		rec_group[comp] = 0;
+	}
+	rec_size[comp] = 2u + (a.mode == MEMS_MODE_REPEAT ? len : count);
 }
 
 template <class KeyT>
@@ -1116,7 +1128,12 @@ __global__ void emit_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hke
 	const int64_t x0 = (int64_t)(hkey[hi] & a.pos_mask);
 	const int64_t kl = (int64_t)comp_left[comp] - x0, kr = (int64_t)comp_right[comp] - x0;
 	int64_t* rec = flat + rec_off[comp];
-	const uint32_t seqcount = a.mode == MEMS_MODE_REPEAT ? len : (uint32_t)a.n_seqs;
+	uint32_t seqcount = a.mode == MEMS_MODE_REPEAT ? len : (uint32_t)a.n_seqs, first_seq = 0;
+	if (a.max_group != a.n_seqs) {  // several problems in the batch: sequence numbers relative to the problem's first
+		const SeqMeta m = a.meta[a.vals[s] >> a.pos_bits];
+		seqcount = m.group_count;
+		first_seq = m.group_first;
+	}
 	rec[0] = seqcount;
 	rec[1] = kr - kl + L;
 	if (a.mode != MEMS_MODE_REPEAT)
@@ -1128,7 +1145,7 @@ __global__ void emit_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hke
 		const int64_t p = val & a.pos_mask;
 		// forward member: first covered base p+kl (1-based start p+kl+1); reverse member: covers p-kr .. p-kl+L-1
 		const int64_t start = o ? -(p - kr + 1) : (p + kl + 1);
-		const uint32_t slot = a.mode == MEMS_MODE_REPEAT ? idx : (val >> a.pos_bits);
+		const uint32_t slot = a.mode == MEMS_MODE_REPEAT ? idx : (val >> a.pos_bits) - first_seq;
 		rec[2 + slot] = start;
 		++idx;
 	}
@@ -1296,7 +1313,7 @@ static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	const uint32_t n = a.n;
 	// overlap of the warps' windows = the longest run that must close inside one (up to 16 sequences' worth)
 	ScanShape sh;
-	sh.own = 32u - (uint32_t)std::min(std::max(a.n_seqs, 2), 16);
+	sh.own = 32u - (uint32_t)std::min(std::max(a.max_group, 2), 16);
 	if (a.mode != MEMS_MODE_MEMHASH) sh.own = 24;  // repeat policy: copies per family, not sequences, set the run length
 	const uint64_t n_chunks = ((uint64_t)n + scan_chunk_entries(sh) - 1) / scan_chunk_entries(sh);
 	sh.chunks_per_cta = (uint32_t)std::max<uint64_t>(1, n_chunks / ((uint64_t)c->sm_count * 16));
@@ -1336,8 +1353,9 @@ __device__ uint64_t unique_sequences(const MatchArgs& a, uint32_t i, uint32_t* r
 	const uint64_t mk = masked_of<KeyT>(a.keys, i);
 	uint64_t once = 0, more = 0;
 	uint32_t j = i;
+	const uint32_t g0 = a.n_seqs > 64 ? a.meta[a.vals[i] >> a.pos_bits].group_first : 0u;  // bits relative to the run's problem
 	while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && j - i <= kRunCap) {
-		const uint64_t bit = 1ull << (a.vals[j] >> a.pos_bits);
+		const uint64_t bit = 1ull << ((a.vals[j] >> a.pos_bits) - g0);
 		more |= once & bit;
 		once |= bit;
 		++j;
@@ -1373,13 +1391,14 @@ pair_emit_kernel(MatchArgs a, const uint32_t* __restrict__ pair_count, const uin
 	uint32_t run;
 	const uint64_t uniq = unique_sequences<KeyT>(a, i, &run);
 	uint32_t at = 2 * pair_off[i];
+	const uint32_t g0 = a.n_seqs > 64 ? a.meta[a.vals[i] >> a.pos_bits].group_first : 0u;
 	// sequences in ascending order; a sequence's (single) entry is found by scanning the run
 	for (uint64_t ra = uniq; ra; ra &= ra - 1) {
-		const uint32_t ga = __ffsll((long long)ra) - 1;
+		const uint32_t ga = g0 + __ffsll((long long)ra) - 1;
 		uint32_t ja = i;
 		while ((a.vals[ja] >> a.pos_bits) != ga) ++ja;
 		for (uint64_t rb = ra & (ra - 1); rb; rb &= rb - 1) {
-			const uint32_t gb = __ffsll((long long)rb) - 1;
+			const uint32_t gb = g0 + __ffsll((long long)rb) - 1;
 			uint32_t jb = i;
 			while ((a.vals[jb] >> a.pos_bits) != gb) ++jb;
 			const uint32_t lo = ja < jb ? ja : jb, hi = ja < jb ? jb : ja;  // union order: strand 0 first, then (seq,pos)
@@ -1432,10 +1451,17 @@ static void find_pair_hits(Ctx* c, const MatchArgs& a, HitSet& hits, DevBuf<uint
 	}
 }
 
+// several problems in one batch: per record (in device order) its problem, and which records are duplicates to drop
+struct ManyOut {
+	std::vector<uint32_t> group;
+	std::vector<char> drop;
+};
+
 // ---- stage B: hits (members readable through a.keys / a.vals) -> extended, distinct matches
 template <class KeyT>
 static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const SeedDesc& sd, HitSet& hits, int order,
-                        uint32_t table_size, MatchResult& out, HashTable* persistent = nullptr, uint64_t* given_hkey = nullptr) {
+                        uint32_t table_size, MatchResult& out, HashTable* persistent = nullptr, uint64_t* given_hkey = nullptr,
+                        ManyOut* many = nullptr) {
 	Ctx* c = ctx.get();
 	const int L = sd.L;
 	const int mode = a.mode;
@@ -1573,6 +1599,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	const uint32_t n_comp = h_tail[0];
 	const bool collision_seen = h_tail[1] != 0;
 	DevBuf<uint32_t> comp_rep(c, n_comp), comp_left(c, n_comp), comp_right(c, n_comp), rec_size(c, n_comp), rec_off(c, n_comp);
+	DevBuf<uint32_t> rec_group(c, many ? n_comp : 1);
 	DevBuf<uint8_t> comp_suspect(c, n_comp);
 	if (collision_seen) MEMS_CUDA(cudaMemsetAsync(comp_suspect.p, 0, n_comp, c->stream));
 	{
@@ -1594,7 +1621,8 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	const uint32_t comp_blocks = (n_comp + 255) / 256;
 	{
 		KernelScope ks(c, "emit_size");
-		emit_size_kernel<<<comp_blocks, 256, 0, c->stream>>>(comp_rep.p, hid, hit_len.p, n_comp, mode, a.n_seqs, rec_size.p);
+		emit_size_kernel<<<comp_blocks, 256, 0, c->stream>>>(a, comp_rep.p, hid, hit_start.p, hit_len.p, n_comp, rec_size.p,
+		                                                     many ? rec_group.p : nullptr);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, rec_size.p, rec_off.p, n_comp, scalars.p + 5);
@@ -1609,7 +1637,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		MEMS_CUDA(cudaGetLastError());
 		MEMS_CUDA(cudaMemcpyAsync(&h_sus_count, sus_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	}
-	if (mode != MEMS_MODE_REPEAT && (uint64_t)n_comp * (uint64_t)(a.n_seqs + 2) > 0xffffffffull)
+	if (mode != MEMS_MODE_REPEAT && (uint64_t)n_comp * (uint64_t)(a.max_group + 2) > 0xffffffffull)
 		throw Error(MEMS_ERR_UNSUPPORTED, "match list larger than 2^32 values; search fewer sequences per call");
 	const uint32_t n_flat = d2h_u32(c, scalars.p + 5);
 	DevBuf<int64_t> d_flat(c, n_flat);
@@ -1665,6 +1693,14 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 					drop[sus[k].second] = 1;
 					++n_drop;
 				}
+		}
+		if (many) {  // the caller splits the records by problem (find_matches_many)
+			many->group.resize(n_comp);
+			MEMS_CUDA(cudaMemcpyAsync(many->group.data(), rec_group.p, (size_t)n_comp * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+			MEMS_CUDA(cudaStreamSynchronize(c->stream));
+			many->drop = std::move(drop);
+			out.n_matches = n_comp - n_drop;
+			return;
 		}
 		if (order == MEMS_ORDER_CANONICAL) {
 			std::vector<Rec> recs = split_records(raw, n_flat);
@@ -1935,7 +1971,7 @@ __global__ void start_compact_kernel(const KeyT* __restrict__ keys, const uint32
 
 template <class KeyT>
 static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
-                               HashTable* persistent, const uint64_t* start_points) {
+                               HashTable* persistent, const uint64_t* start_points, ManyOut* many = nullptr) {
 	Ctx* c = b.ctx.get();
 	out.seq_count = (uint32_t)b.n_seqs;
 	out.seed_length = (uint32_t)b.sd.L;
@@ -1950,6 +1986,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.pos_bits = b.pos_bits;
 	a.pos_mask = b.pos_mask();
 	a.n_seqs = b.n_seqs;
+	a.max_group = b.max_group;
 	a.mode = mode;
 	// the reference's "match number" puts sequence 0 in the most significant of n_seqs bits; here bit g = sequence g
 	a.test_hash_bits = c->test_hash_bits;
@@ -2012,7 +2049,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 		if (persistent) emit_table(*persistent, out);  // nothing new: the result is still the whole table
 		return;
 	}
-	extend_hits<KeyT>(b.ctx, a, b.sd, hits, order, table_size, out, persistent);
+	extend_hits<KeyT>(b.ctx, a, b.sd, hits, order, table_size, out, persistent, nullptr, many);
 }
 
 void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, uint64_t seq_mask, MatchResult& out,
@@ -2020,10 +2057,56 @@ void find_matches_on_batch(Batch& b, int mode, int order, uint32_t table_size, u
 	if (persistent && order != MEMS_ORDER_REFERENCE) throw Error(MEMS_ERR_INVALID, "a persistent table needs MEMS_ORDER_REFERENCE");
 	if (seq_mask && mode != MEMS_MODE_MEMHASH) throw Error(MEMS_ERR_INVALID, "seq_mask applies to MEMS_MODE_MEMHASH only");
 	if (b.n_seqs > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one match-finding call");
+	if (b.n_groups > 1) throw Error(MEMS_ERR_INVALID, "a batch of several problems is searched with mems_find_matches_many");
 	if (b.key64)
 		find_matches_typed<uint64_t>(b, mode, order, table_size, seq_mask, out, persistent, start_points);
 	else
 		find_matches_typed<uint32_t>(b, mode, order, table_size, seq_mask, out, persistent, start_points);
+}
+
+// ---- many small problems in one launch set (the gap re-anchoring callers, ProgressiveAligner.cpp:589-678 under
+// `omp parallel for` at :695): the batch holds the sequences of all problems, the problem number sits above the key
+// bits, so one sort, one run scan and one extension serve them all; the records are split by problem on the host.
+void find_matches_many(Batch& b, int mode, int order, std::vector<MatchResult>& out) {
+	if (mode != MEMS_MODE_MEMHASH && mode != MEMS_MODE_PAIRWISE)
+		throw Error(MEMS_ERR_UNSUPPORTED, "mems_find_matches_many: MEMS_MODE_MEMHASH or MEMS_MODE_PAIRWISE");
+	if (order == MEMS_ORDER_REFERENCE)
+		throw Error(MEMS_ERR_UNSUPPORTED, "mems_find_matches_many: MEMS_ORDER_ANY or MEMS_ORDER_CANONICAL (the reference's table order needs one table per problem)");
+	if (b.max_group > MEMS_MAX_SEQS) throw Error(MEMS_ERR_UNSUPPORTED, "more than MEMS_MAX_SEQS sequences in one problem");
+	out.clear();
+	out.resize(b.n_groups);
+	for (int g = 0; g < b.n_groups; ++g) out[g].seed_length = (uint32_t)b.sd.L;
+	for (int i = 0; i < b.n_seqs; ++i) out[b.meta[i].group].seq_count = b.meta[i].group_count;
+	MatchResult all;
+	ManyOut many;
+	if (b.key64)
+		find_matches_typed<uint64_t>(b, mode, MEMS_ORDER_ANY, 40000u, 0, all, nullptr, nullptr, &many);
+	else
+		find_matches_typed<uint32_t>(b, mode, MEMS_ORDER_ANY, 40000u, 0, all, nullptr, nullptr, &many);
+	const int64_t* raw = all.flat.data();
+	const size_t n_flat = all.flat.size();
+	size_t at = 0;
+	for (size_t k = 0; at < n_flat; ++k) {
+		const size_t sz = (size_t)raw[at] + 2;
+		if (many.drop.empty() || !many.drop[k]) {
+			MatchResult& r = out[many.group[k]];
+			r.flat.vec.insert(r.flat.vec.end(), raw + at, raw + at + sz);
+			++r.n_matches;
+		}
+		at += sz;
+	}
+	for (MatchResult& r : out) {
+		if (order == MEMS_ORDER_CANONICAL && r.n_matches > 1) {
+			std::vector<Rec> recs = split_records(r.flat.vec.data(), r.flat.vec.size());
+			std::sort(recs.begin(), recs.end(), rec_less);
+			std::vector<int64_t> sorted;
+			sorted.reserve(r.flat.vec.size());
+			for (const Rec& x : recs) sorted.insert(sorted.end(), x.p, x.p + x.size());
+			r.flat.vec.swap(sorted);
+		}
+		r.mem_count = r.n_matches;
+		r.max_run = all.max_run;  // (of the whole batch)
+	}
 }
 
 bool table_add_entry(HashTable& T, uint32_t seq_count, int64_t length, const int64_t* starts, int64_t mersize) {
@@ -2250,6 +2333,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		m.seed_off = seed_off;
 		m.word_off = word_off;
 		m.tag = (uint32_t)g;
+		m.group_count = (uint32_t)n_seqs;
 		seed_off += m.n_seeds;
 		word_off += seq_packed_words(lens[g]);
 		max_seeds = std::max(max_seeds, m.n_seeds);
@@ -2467,6 +2551,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.pos_bits = pos_bits;
 	a1.pos_mask = pos_bits >= 32 ? 0xffffffffu : ((1u << pos_bits) - 1u);
 	a1.n_seqs = n_seqs;
+	a1.max_group = n_seqs;
 	a1.mode = mode;
 	a1.seq_set = 0;
 	a1.test_hash_bits = c->test_hash_bits;

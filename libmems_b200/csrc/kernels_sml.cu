@@ -145,6 +145,7 @@ extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ 
 	for (int i = threadIdx.x; i < pd.n_passes * 256; i += kExtractThreads) s_hist[i] = 0;
 	__syncthreads();
 	const uint32_t seq_tag = m.tag << pos_bits;
+	const KeyT group_key = m.group ? (KeyT)((KeyT)m.group << sd.key_bits) : (KeyT)0;  // problem number above the key bits
 	const uint32_t* src = packed + m.word_off;
 	// a CTA walks tiles_per_cta consecutive tiles and flushes its histograms once: one flush per tile would be
 	// ~1000 same-address global atomics per 2048 seeds, which bounds the kernel at the L2 atomic units
@@ -188,7 +189,7 @@ extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ 
 				}
 			}
 #pragma unroll
-			for (int k = 0; k < kExtractItems; ++k) key[k] = (KeyT)canonical_key((uint64_t)f[k], sd.w);
+			for (int k = 0; k < kExtractItems; ++k) key[k] = (KeyT)canonical_key((uint64_t)f[k], sd.w) | group_key;
 		} else {
 			uint64_t f[kExtractItems];
 #pragma unroll
@@ -202,7 +203,7 @@ extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ 
 				for (int k = 0; k < kExtractItems; ++k) f[k] |= ((((uint64_t)hi[k] << 32) | lo[k]) >> net) & mask;
 			}
 #pragma unroll
-			for (int k = 0; k < kExtractItems; ++k) key[k] = (KeyT)canonical_key(f[k], sd.w);
+			for (int k = 0; k < kExtractItems; ++k) key[k] = (KeyT)canonical_key(f[k], sd.w) | group_key;
 		}
 		const uint64_t slot = m.seed_off + (uint64_t)p0;  // a multiple of 4
 		store8<KeyT>(keys + slot, key);
@@ -223,7 +224,7 @@ extract_kernel(const uint32_t* __restrict__ packed, const SeqMeta* __restrict__ 
 		for (int k = 0; k < kExtractItems; ++k) {
 			const int64_t p = p0 + k;
 			if (p < 0 || p >= (int64_t)m.n_seeds) continue;
-			const uint64_t ck = canonical_key(extract_fwd(window64(src, (uint32_t)p), sd), sd.w);
+			const uint64_t ck = canonical_key(extract_fwd(window64(src, (uint32_t)p), sd), sd.w) | (uint64_t)group_key;
 			keys[m.seed_off + p] = (KeyT)ck;
 			vals[m.seed_off + p] = seq_tag | (uint32_t)p;
 #pragma unroll

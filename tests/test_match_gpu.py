@@ -373,3 +373,31 @@ def test_non_palindromic_patterns(ctx, orc):
         got, info = gpu_matches(ctx, gs, seed, mems.MODE_MEMHASH)
         assert got == canonical(want), hex(seed)
         assert info["n_hits"] == winfo["hits"]
+
+
+def test_many_small_problems_in_one_call(ctx, orc):
+    """mems_find_matches_many: dozens of independent gap-sized problems (pairs and small sets, ragged, some empty of
+    matches) in one launch set; every problem's list must equal the oracle's for that problem alone."""
+    rng = np.random.default_rng(17)
+    for seed, mode in ((mems.get_seed(9), mems.MODE_MEMHASH), (mems.get_seed(11), mems.MODE_MEMHASH), (mems.get_seed(9), mems.MODE_PAIRWISE)):
+        problems = []
+        for k in range(70):
+            G = int(rng.integers(2, 5)) if k % 7 else 2
+            n = int(rng.integers(30, 12000))
+            gs = synth.genome_family(G, n, seed=1000 + k, snp_rate=0.03, n_indels=int(rng.integers(0, 4)), max_indel=15)
+            if k % 11 == 0:
+                gs[1] = synth.random_genome(n, rng)  # unrelated: no matches
+            if k % 13 == 0:
+                gs[-1] = gs[-1][:10]  # shorter than the seed
+            problems.append(gs)
+        res = ctx.find_matches_many(problems, seed, mode=mode, order=mems.ORDER_CANONICAL)
+        assert len(res) == len(problems)
+        for k, (gs, (flat, info)) in enumerate(zip(problems, res)):
+            want, _ = orc.find_matches(2 if mode == mems.MODE_PAIRWISE else 0, gs, seed)
+            assert mems.flat_to_matches(flat) == canonical(want), k
+            assert info["seq_count"] == len(gs) and info["n_matches"] == len(canonical(want))
+    # limits: more than MEMS_MAX_SEQS sequences in one problem, more than 256 in all
+    with pytest.raises(mems.MemsError):
+        ctx.find_matches_many([[b"ACGT" * 20] * 65], mems.get_seed(7))
+    with pytest.raises(mems.MemsError):
+        ctx.find_matches_many([[b"ACGT" * 20] * 2] * 129, mems.get_seed(7))
