@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <ostream>
+#include <stdexcept>
 #include <vector>
 
 namespace mems {
@@ -40,6 +41,28 @@ public:
 	}
 	void Invert() {
 		for (int64_t& s : m_start) s = -s;
+	}
+	// HybridAbstractMatch::MoveStart / MoveEnd (HybridAbstractMatch.h:271-290): the alignment's first column sits at the
+	// left end of forward members and at the right end of reverse ones, so moving the start touches forward starts only
+	// and moving the end grows the magnitude of reverse starts
+	void MoveStart(int64_t amount) {
+		for (int64_t& s : m_start)
+			if (s > 0) s += amount;
+	}
+	void MoveEnd(int64_t amount) {
+		for (int64_t& s : m_start)
+			if (s < 0) s -= amount;
+	}
+	// UngappedLocalAlignment::CropStart / CropEnd (UngappedLocalAlignment.h:138-152)
+	void CropStart(uint64_t crop_amount) {
+		if (crop_amount > m_length) throw std::out_of_range("SeqIndexOutOfBounds");
+		m_length -= crop_amount;
+		MoveStart((int64_t)crop_amount);
+	}
+	void CropEnd(uint64_t crop_amount) {
+		if (crop_amount > m_length) throw std::out_of_range("SeqIndexOutOfBounds");
+		m_length -= crop_amount;
+		MoveEnd((int64_t)crop_amount);
 	}
 	bool operator==(const Match& o) const { return m_length == o.m_length && m_start == o.m_start; }
 

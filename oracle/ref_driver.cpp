@@ -23,6 +23,12 @@
 
 using namespace mems;
 using namespace genome;
+using namespace std;
+
+// the reference's EliminateOverlaps, unmodified (cut out of Aligner.cpp by oracle/Makefile)
+namespace mems {
+#include "eliminate_overlaps.inc"
+}
 
 namespace {
 double now_s() {
@@ -399,6 +405,32 @@ int ref_mems_load_file(int n_seqs, const char* const* seqs, const uint64_t* lens
 		flatten(ml, flat_out, n_flat_out, n_matches_out);
 		mh.Clear();
 		ml.Clear();
+		return 0;
+	} catch (gnException& e) {
+		g_err = e.code.name + ": " + e.msg;
+		return 1;
+	} catch (const char* s) {
+		g_err = s;
+		return 2;
+	}
+}
+
+// EliminateOverlaps (Aligner.cpp:62-180) on a match list given as flat records -> the list it leaves behind, in its order
+int ref_eliminate_overlaps(const int64_t* flat_in, uint64_t n_flat_in, int64_t** flat_out, uint64_t* n_flat_out, uint64_t* n_matches_out) {
+	try {
+		MatchList ml;
+		for (uint64_t i = 0; i < n_flat_in;) {
+			const uint k = (uint)flat_in[i];
+			Match m(k);
+			Match* mm = m.Copy();
+			mm->SetLength((gnSeqI)flat_in[i + 1]);
+			for (uint s = 0; s < k; ++s) mm->SetStart(s, flat_in[i + 2 + s]);
+			ml.push_back(mm);
+			i += 2 + k;
+		}
+		EliminateOverlaps(ml);
+		flatten(ml, flat_out, n_flat_out, n_matches_out);
+		for (size_t i = 0; i < ml.size(); ++i) ml[i]->Free();
 		return 0;
 	} catch (gnException& e) {
 		g_err = e.code.name + ": " + e.msg;

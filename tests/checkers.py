@@ -294,6 +294,15 @@ class Reference(_Checker):
             raise RuntimeError(self.err())
         return self._take_flat(flat, nflat), {"mem_count": counts[0], "collisions": counts[1]}
 
+    def eliminate_overlaps(self, matches):
+        """The reference's EliminateOverlaps (Aligner.cpp:62-180) on a list of (SeqCount, Length, starts...) tuples."""
+        flat_in = np.array([x for m in matches for x in m], dtype=np.int64)
+        flat = ctypes.POINTER(ctypes.c_int64)()
+        nflat, nm = u64(), u64()
+        if self.lib.ref_eliminate_overlaps(_ptr(flat_in), u64(len(flat_in)), ctypes.byref(flat), ctypes.byref(nflat), ctypes.byref(nm)):
+            raise RuntimeError(self.err())
+        return self._take_flat(flat, nflat)
+
     def seed_occurrence(self, seq, seed):
         s = _as_bytes(seq)
         out = np.zeros(len(s), np.float32)

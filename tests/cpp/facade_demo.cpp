@@ -11,6 +11,7 @@
 //        facade_demo memsfile <seed_weight> <raw-sequence-file>...   MemHash::WriteFile of the search on stdout
 //        facade_demo loadmems <file with bare match lines>            MemHash::LoadFile, prints the table + counters
 //        facade_demo clone <seed_weight> <raw-sequence-file>          SortedMerList::Clone: the clone outlives the original
+//        facade_demo overlaps <file with bare match lines>            EliminateOverlaps (Aligner.cpp:62-180), prints the list it leaves
 #include <cstddef>
 #include <fstream>
 #include <iostream>
@@ -18,6 +19,7 @@
 #include <sstream>
 #include <string>
 
+#include "libMems/Aligner.h"
 #include "libMems/MemHash.h"
 
 using namespace mems;
@@ -67,6 +69,26 @@ int main(int argc, char** argv) {
 			}
 			mh.Clear();
 			ml.Clear();
+			return 0;
+		}
+		if (mode == "overlaps") {  // host code only: runs without a GPU
+			std::ifstream f(argv[2]);
+			MatchList ml;
+			std::string line;
+			while (std::getline(f, line)) {
+				std::stringstream ls(line);
+				std::vector<int64_t> v;
+				int64_t x;
+				while (ls >> x) v.push_back(x);
+				if (v.size() < 2) continue;
+				Match* m = new Match((unsigned)v.size() - 1);
+				m->SetLength((uint64_t)v[0]);
+				for (size_t i = 1; i < v.size(); ++i) m->SetStart((unsigned)i - 1, v[i]);
+				ml.push_back(m);
+			}
+			EliminateOverlaps(ml);
+			for (Match* m : ml) std::cout << *m << "\n";
+			for (Match* m : ml) m->Free();
 			return 0;
 		}
 		if (mode == "loadmems") {

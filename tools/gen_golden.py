@@ -113,3 +113,12 @@ for tag, G, n, w, gseed, sp in [("three_w13", 3, 30000, 13, 5, [5000, 100, 20000
                 "matches": [list(m) for m in matches], "mem_count": info["mem_count"], "collisions": info["collisions"],
                 "progress": info["progress"], "match_log": info["match_log"], "mems_file": text, "loads": loads})
 dump("facade.json", fac)
+
+# --- EliminateOverlaps (Aligner.cpp:62-180) on MemHash results, in the order MemHash returns them -------------------
+ov = []
+for tag, G, n, w, gseed in [("four_w11", 4, 20000, 11, 7), ("three_w13_inverted", 3, 30000, 13, 5), ("six_w9", 6, 8000, 9, 12), ("pair_w15", 2, 40000, 15, 3)]:
+    sd = R.get_seed(w)
+    gs = synth.genome_family(G, n, seed=gseed, snp_rate=0.03)
+    matches, _ = R.find_matches(0, gs, sd)
+    ov.append({"tag": tag, "input": [list(m) for m in matches], "output": [list(m) for m in R.eliminate_overlaps(matches)]})
+dump("overlaps.json", ov)
