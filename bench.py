@@ -263,6 +263,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # run this rank on the CPUs next to its GPU: the page-locked buffers of the copies are then allocated on the GPU's
+    # NUMA node (eight ranks whose buffers sit behind the other socket share one inter-socket link)
+    numa = "unchanged"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip().isdigit()]
+        phys = int(vis[local_rank]) if local_rank < len(vis) else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        numa = "bound to the GPU's CPU set (%d CPUs)" % len(os.sched_getaffinity(0))
+    except Exception as e:  # noqa: BLE001
+        numa = "unchanged (%s)" % type(e).__name__
     n_genomes, length, weight, mode, desc = WORKLOADS[name]
     seed = mems.get_seed(weight)
     match_mode = mems.MODE_REPEAT if mode == "repeat" else mems.MODE_MEMHASH
@@ -445,6 +457,7 @@ def main():
             "config": {"workload": desc, "genomes": n_genomes, "genome_length": length, "seed_weight": weight,
                        "seed_pattern": hex(seed), "multi_gpu": ("sharded: genome blocks per rank, seed-range all-to-all + diagonal all-to-all "
                                      "(peer-to-peer over NVLink); weak scaling by genome length") if world > 1 else "n/a",
+                       "host_affinity": numa,
                        "l2": "per-step working set (%.0f MB of seed records per GPU) exceeds the 126 MB L2" %
                              (mbp_total / world * (8 if 2 * weight + 1 <= 32 else 12))},
             "e2e": {"value": mbp_total * args.steps / (ms_e2e / 1e3), "unit": "Mbp/s",
