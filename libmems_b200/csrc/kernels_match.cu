@@ -60,6 +60,7 @@ struct MatchArgs {
 	int max_group;         // sequences in its largest problem (= n_seqs unless the batch holds several, SeqMeta::group)
 	int mode;
 	uint64_t seq_set;  // MaskedMemHash filter: required member set, bit g = sequence g (0 = no filter)
+	int hit_key_bits;      // hit sort key = top (hit_key_bits - pos_bits) bits of the diagonal hash, then the first member's position
 	int test_hash_bits;  // 0 = use the full diagonal hash; n > 0 keeps only n bits (tests force bucket collisions with it)
 	int warp_budget;     // probes one warp spends on a walk before a CTA takes over (kWarpProbeBudget; tests shrink it)
 	int cta_budget;      // rounds one CTA spends before the whole grid takes over (kCtaRoundBudget; tests shrink it)
@@ -341,7 +342,9 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 			hash = mix64(hash, (uint64_t)diag);
 		}
 		if (a.test_hash_bits) hash = (hash & ((1ull << a.test_hash_bits) - 1ull)) << (64 - a.test_hash_bits);
-		const uint64_t key = ((hash >> a.pos_bits) << a.pos_bits) | (uint64_t)x0;
+		// 56 key bits = seven sort passes: 56 - pos_bits hash bits are plenty (two diagonals that share them only cost
+		// extra window tests and the de-dup of the components marked below)
+		const uint64_t key = ((hash >> (64 - a.hit_key_bits + a.pos_bits)) << a.pos_bits) | (uint64_t)x0;
 		hkey[h] = key;
 		hid[h] = h;
 		hit_len[h] = (uint16_t)(len | (sf ? kFirstStrandBit : 0));
@@ -748,7 +751,9 @@ struct SegView {
 template <class KeyT>
 __global__ void __launch_bounds__(kExtendWarps * 32)
 walk_right_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, uint32_t* __restrict__ seg_link,
-                  uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
+                  uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count,
+                  uint32_t* __restrict__ seg_left, uint8_t* __restrict__ seg_left_state, uint2* __restrict__ defer_left,
+                  uint32_t* __restrict__ defer_left_count) {
 	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
 	__shared__ SeedShape s_shape;
 	load_seed_shape(&s_shape, sd);
@@ -785,6 +790,21 @@ walk_right_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, u
 		seg_link[seg] = link;
 		seg_reach[seg] = (uint32_t)(x0 + c);
 	}
+	// The first segment of a DIAGONAL certainly starts a component (nothing on its diagonal can link to it), and its
+	// members are already staged: walk left right away instead of setting all of this up again in walk_left_kernel.
+	if (!(v.flags[hi] & kFlagSameDiag)) {
+		bool l2, ex2;
+		const int32_t cl = -w.walk(0, -1, -1, &l2, a.warp_budget, &ex2);
+		if (w.lane == 0) {
+			if (ex2) {
+				defer_left[atomicAdd(defer_left_count, 1u)] = make_uint2(seg, (uint32_t)cl);
+				seg_left_state[seg] = 2;  // handed to the CTA-wide walker
+			} else {
+				seg_left[seg] = (uint32_t)(x0 + cl);
+				seg_left_state[seg] = 1;
+			}
+		}
+	}
 }
 
 // a segment starts a component unless its predecessor linked to it
@@ -800,7 +820,8 @@ walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, co
                  const uint32_t* __restrict__ seg_reach, const uint32_t* __restrict__ first,
                  const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
                  uint32_t* __restrict__ comp_right, uint8_t* __restrict__ comp_suspect, uint2* __restrict__ defer,
-                 uint32_t* __restrict__ defer_count) {
+                 uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ seg_left,
+                 const uint8_t* __restrict__ seg_left_state) {
 	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
 	__shared__ SeedShape s_shape;
 	load_seed_shape(&s_shape, sd);
@@ -816,6 +837,14 @@ walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, co
 		if (v.suspect[e0] | v.suspect[e1]) comp_suspect[comp] = 1;  // only ever set: racing writers agree
 	}
 	if (!is_first) return;
+	const uint8_t done = seg_left_state[seg];  // walk_right_kernel already walked left from a diagonal's first segment
+	if (done) {
+		if (lane == 0) {
+			comp_rep[comp] = v.seg_head[seg];
+			if (done == 1) comp_left[comp] = seg_left[seg];
+		}
+		return;
+	}
 	const uint32_t hi = v.seg_head[seg];
 	const uint32_t h = v.hid[hi];
 	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
@@ -1474,7 +1503,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	// ---- 2. describe + 3. sort by (diagonal hash, first-member position)
 	// (given_hkey: the hits arrive described — sharded path, where the key travelled with the hit through the
 	// diagonal exchange; only the identity permutation and the digit histograms are made here)
-	SortPlan plan = make_sort_plan(64);
+	SortPlan plan = make_sort_plan(a.hit_key_bits);
 	DevBuf<uint64_t> hk_a(c, given_hkey ? 0 : n_hits), hk_b(c, n_hits);
 	DevBuf<uint32_t> hid_a(c, n_hits), hid_b(c, n_hits), hist(c, (size_t)plan.n_passes * 256);
 	MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)plan.n_passes * 256 * sizeof(uint32_t), c->stream));
@@ -1533,7 +1562,10 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	SegView v{hkey, hid, hit_start.p, hit_len.p, flags.p, seg_head.p, n_hits, n_seg, seg_order, suspect.p};
 	DevBuf<uint32_t> seg_link(c, n_seg), seg_reach(c, n_seg), first(c, n_seg), first_excl(c, n_seg);
 	const SegView& v_for_giant = v;
-	DevBuf<uint2> defer(c, n_seg);
+	DevBuf<uint2> defer(c, n_seg), defer_left(c, n_seg);
+	DevBuf<uint32_t> seg_left(c, n_seg);
+	DevBuf<uint8_t> seg_left_state(c, n_seg);
+	MEMS_CUDA(cudaMemsetAsync(seg_left_state.p, 0, n_seg, c->stream));
 	uint32_t* defer_count = scalars.p + 6;  // [6] right walks, [7] left walks handed to whole CTAs
 	const uint32_t long_grid = 2u * (uint32_t)c->sm_count;
 	DevBuf<uint32_t> queue_heads(c, 4);  // [0],[1] work-queue heads; [2],[3] giant-walk counts (right, left)
@@ -1566,7 +1598,8 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	{
 		KernelScope ks(c, "walk_right");
 		walk_right_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(a, sd, v, seg_link.p, seg_reach.p,
-		                                                                          defer.p, defer_count);
+		                                                                          defer.p, defer_count, seg_left.p, seg_left_state.p,
+		                                                                          defer_left.p, defer_count + 1);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
@@ -1606,12 +1639,12 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		KernelScope ks(c, "walk_left");
 		walk_left_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(
 		    a, sd, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, comp_suspect.p,
-		    defer.p, defer_count + 1);
+		    defer_left.p, defer_count + 1, seg_left.p, seg_left_state.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
 		KernelScope ks(c, "long_walk_left");
-		long_walk_left_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, sd, v, defer.p, defer_count + 1,
+		long_walk_left_kernel<KeyT><<<long_grid, kLongWarps * 32, 0, c->stream>>>(a, sd, v, defer_left.p, defer_count + 1,
 		                                                                          queue_heads.p + 1, first_excl.p, comp_left.p, giant.p, queue_heads.p + 3);
 		MEMS_CUDA(cudaGetLastError());
 	}
@@ -1989,6 +2022,7 @@ static void find_matches_typed(Batch& b, int mode, int order, uint32_t table_siz
 	a.max_group = b.max_group;
 	a.mode = mode;
 	// the reference's "match number" puts sequence 0 in the most significant of n_seqs bits; here bit g = sequence g
+	a.hit_key_bits = b.pos_bits <= 26 ? 56 : 64;
 	a.test_hash_bits = c->test_hash_bits;
 	a.warp_budget = c->test_walk_budget ? c->test_walk_budget : kWarpProbeBudget;
 	a.cta_budget = c->test_walk_budget ? c->test_walk_budget : kCtaRoundBudget;
@@ -2247,8 +2281,9 @@ __global__ void sorted_len_kernel(const uint32_t* __restrict__ hid, const uint16
 // What this rank sends to every rank d: hits [bound[d], bound[d+1]) of the hit keys grouped by their top 8 hash bits
 // (rank d owns the buckets [ceil(256 d / world), ceil(256 (d+1) / world))) and the members of those hits.
 // counts[d] = hits, counts[world + d] = members.
-__global__ void hit_send_counts_kernel(const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ mem_off, uint32_t n_hits,
-                                       const uint32_t* __restrict__ last_len, int world, uint64_t* __restrict__ counts) {
+__global__ void hit_send_counts_kernel(const uint64_t* __restrict__ hkey, int top_shift, const uint32_t* __restrict__ mem_off,
+                                       uint32_t n_hits, const uint32_t* __restrict__ last_len, int world,
+                                       uint64_t* __restrict__ counts) {
 	__shared__ uint32_t s_bound[257], s_mbound[257];
 	const int d = threadIdx.x;
 	if (d <= world) {
@@ -2259,7 +2294,7 @@ __global__ void hit_send_counts_kernel(const uint64_t* __restrict__ hkey, const 
 			lo = 0;
 			while (lo < hi) {
 				const uint32_t mid = (lo + hi) / 2;
-				if ((hkey[mid] >> 56) < t) lo = mid + 1;
+				if ((hkey[mid] >> top_shift) < t) lo = mid + 1;
 				else hi = mid;
 			}
 		}
@@ -2554,6 +2589,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	a1.max_group = n_seqs;
 	a1.mode = mode;
 	a1.seq_set = 0;
+	a1.hit_key_bits = pos_bits <= 26 ? 56 : 64;
 	a1.test_hash_bits = c->test_hash_bits;
 	a1.warp_budget = c->test_walk_budget ? c->test_walk_budget : kWarpProbeBudget;
 	a1.cta_budget = c->test_walk_budget ? c->test_walk_budget : kCtaRoundBudget;
@@ -2570,7 +2606,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	const uint32_t n1 = hits1.n;
 	SortPlan hplan;
 	hplan.n_passes = 1;
-	hplan.shift[0] = 56;
+	hplan.shift[0] = a1.hit_key_bits - 8;
 	hplan.bits[0] = 8;
 	DevBuf<uint64_t> hk_a(c, n1), hk_b(c, n1), d_counts(c, (size_t)2 * W * (W + 1));
 	DevBuf<uint32_t> hid_a(c, n1), hid_b(c, n1), slen(c, n1), moff(c, n1), scal(c, 2);
@@ -2603,7 +2639,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		KernelScope ks(c, "shard_hit_counts");
 		last_len_kernel<<<1, 32, 0, c->stream>>>(slen.p, n1, scal.p + 1);
 		MEMS_CUDA(cudaGetLastError());
-		hit_send_counts_kernel<<<1, 32 * ((W + 32) / 32), 0, c->stream>>>(hkey, moff.p, n1, scal.p + 1, W, d_counts.p);
+		hit_send_counts_kernel<<<1, 32 * ((W + 32) / 32), 0, c->stream>>>(hkey, a1.hit_key_bits - 8, moff.p, n1, scal.p + 1, W, d_counts.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	comm_all_gather_u64(comm, d_counts.p, d_counts.p + 2 * W, (size_t)2 * W);
