@@ -267,6 +267,8 @@ def main():
     # NUMA node (eight ranks whose buffers sit behind the other socket share one inter-socket link)
     numa = "unchanged"
     try:
+        if world == 1 and not os.environ.get("MEMS_BENCH_BIND"):
+            raise RuntimeError("single GPU: not bound")
         import pynvml
         pynvml.nvmlInit()
         vis = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip().isdigit()]

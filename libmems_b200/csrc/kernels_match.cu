@@ -813,38 +813,42 @@ __global__ void chain_first_kernel(const uint32_t* __restrict__ seg_link, uint32
 	if (seg < n_seg) first[seg] = (seg == 0 || !seg_link[seg - 1]) ? 1u : 0u;
 }
 
-// Left walk of every component's first segment, and scatter of both component ends.
+// Both ends of every component into the component arrays, one thread per segment; the first segments that still need
+// their left walk (walk_right_kernel did it for the first segment of every diagonal) go on a list.
+__global__ void finish_segments_kernel(SegView v, const uint32_t* __restrict__ seg_link, const uint32_t* __restrict__ seg_reach,
+                                       const uint32_t* __restrict__ first, const uint32_t* __restrict__ first_excl,
+                                       const uint32_t* __restrict__ seg_left, const uint8_t* __restrict__ seg_left_state,
+                                       uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
+                                       uint32_t* __restrict__ comp_right, uint8_t* __restrict__ comp_suspect,
+                                       uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count) {
+	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg >= v.n_seg) return;
+	const bool is_first = first[seg] != 0;
+	const uint32_t comp = first_excl[seg] - (is_first ? 0u : 1u);
+	if (!seg_link[seg]) comp_right[comp] = seg_reach[seg];
+	const uint32_t e0 = v.seg_head[seg], e1 = (seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits) - 1;
+	if (v.suspect[e0] | v.suspect[e1]) comp_suspect[comp] = 1;  // only ever set: racing writers agree
+	if (!is_first) return;
+	comp_rep[comp] = e0;
+	const uint8_t done = seg_left_state[seg];
+	if (done == 1) comp_left[comp] = seg_left[seg];
+	else if (done == 0) todo[atomicAdd(todo_count, 1u)] = seg;  // (2: already with the CTA-wide walker)
+}
+
+// Left walk of the listed first segments.
 template <class KeyT>
 __global__ void __launch_bounds__(kExtendWarps * 32)
-walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint32_t* __restrict__ seg_link,
-                 const uint32_t* __restrict__ seg_reach, const uint32_t* __restrict__ first,
-                 const uint32_t* __restrict__ first_excl, uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
-                 uint32_t* __restrict__ comp_right, uint8_t* __restrict__ comp_suspect, uint2* __restrict__ defer,
-                 uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ seg_left,
-                 const uint8_t* __restrict__ seg_left_state) {
+walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint32_t* __restrict__ todo,
+                 const uint32_t* __restrict__ todo_count, const uint32_t* __restrict__ first_excl,
+                 uint32_t* __restrict__ comp_left, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
 	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
 	__shared__ SeedShape s_shape;
 	load_seed_shape(&s_shape, sd);
 	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
-	if (slot >= v.n_seg) return;
-	const uint32_t seg = v.order[slot];
+	if (slot >= *todo_count) return;
+	const uint32_t seg = todo[slot];
 	const int lane = threadIdx.x & 31;
-	const bool is_first = first[seg] != 0;
-	const uint32_t comp = first_excl[seg] - (is_first ? 0u : 1u);
-	if (!seg_link[seg] && lane == 0) comp_right[comp] = seg_reach[seg];
-	if (lane == 0) {
-		const uint32_t e0 = v.seg_head[seg], e1 = (seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits) - 1;
-		if (v.suspect[e0] | v.suspect[e1]) comp_suspect[comp] = 1;  // only ever set: racing writers agree
-	}
-	if (!is_first) return;
-	const uint8_t done = seg_left_state[seg];  // walk_right_kernel already walked left from a diagonal's first segment
-	if (done) {
-		if (lane == 0) {
-			comp_rep[comp] = v.seg_head[seg];
-			if (done == 1) comp_left[comp] = seg_left[seg];
-		}
-		return;
-	}
+	const uint32_t comp = first_excl[seg];
 	const uint32_t hi = v.seg_head[seg];
 	const uint32_t h = v.hid[hi];
 	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
@@ -852,7 +856,6 @@ walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, co
 	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
 	bool linked, exhausted;
 	const int32_t c = -w.walk(0, -1, -1, &linked, a.warp_budget, &exhausted);
-	if (lane == 0) comp_rep[comp] = hi;
 	if (exhausted) {
 		if (lane == 0) {
 			const uint32_t at = atomicAdd(defer_count, 1u);
@@ -860,9 +863,7 @@ walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, co
 		}
 		return;
 	}
-	if (lane == 0) {
-		comp_left[comp] = (uint32_t)(x0 + c);
-	}
+	if (lane == 0) comp_left[comp] = (uint32_t)(x0 + c);
 }
 
 // ---- long walks -------------------------------------------------------------------------------------
@@ -1635,11 +1636,19 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	DevBuf<uint32_t> rec_group(c, many ? n_comp : 1);
 	DevBuf<uint8_t> comp_suspect(c, n_comp);
 	if (collision_seen) MEMS_CUDA(cudaMemsetAsync(comp_suspect.p, 0, n_comp, c->stream));
+	DevBuf<uint32_t> left_todo(c, n_comp), left_todo_count(c, 1);
+	MEMS_CUDA(cudaMemsetAsync(left_todo_count.p, 0, sizeof(uint32_t), c->stream));
 	{
-		KernelScope ks(c, "walk_left");
-		walk_left_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(
-		    a, sd, v, seg_link.p, seg_reach.p, first.p, first_excl.p, comp_rep.p, comp_left.p, comp_right.p, comp_suspect.p,
-		    defer_left.p, defer_count + 1, seg_left.p, seg_left_state.p);
+		KernelScope ks(c, "finish_segments");
+		finish_segments_kernel<<<seg_blocks, 256, 0, c->stream>>>(v, seg_link.p, seg_reach.p, first.p, first_excl.p, seg_left.p,
+		                                                          seg_left_state.p, comp_rep.p, comp_left.p, comp_right.p,
+		                                                          comp_suspect.p, left_todo.p, left_todo_count.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
+	{
+		KernelScope ks(c, "walk_left");  // at most one listed segment per component: warps past the list's end leave at once
+		walk_left_kernel<KeyT><<<(n_comp + kExtendWarps - 1) / kExtendWarps, kExtendWarps * 32, 0, c->stream>>>(
+		    a, sd, v, left_todo.p, left_todo_count.p, first_excl.p, comp_left.p, defer_left.p, defer_count + 1);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
