@@ -410,6 +410,46 @@ __device__ bool same_diagonal(const MatchArgs& a, uint32_t sa, uint32_t la, uint
 constexpr uint8_t kFlagHead = 1;      // starts a new segment
 constexpr uint8_t kFlagSameDiag = 2;  // same diagonal as the previous entry in sorted order
 
+// A hit of at most 8 members as registers: its members in merged (sequence, position) order relative to the first.
+// Two hits lie on one diagonal iff their signatures are equal.  A thread builds the signature of its own hit once and
+// takes its predecessor's from the neighbouring lane, so every member list is gathered from the union once, not twice
+// (the gathers are what this kernel costs: the lists of hits that are neighbours here sit at random places there).
+struct HitSig {
+	uint32_t len;      // members; kSigLong = more than 8: compared through memory (same_diagonal)
+	uint32_t so[4];    // (sequence << 1 | orientation) of members 0..7, 16 bits each
+	uint32_t diag[7];  // members 1..7: position minus / plus the first member's, by orientation
+};
+constexpr uint32_t kSigLong = 0xffffffffu;
+
+template <class KeyT>
+__device__ __forceinline__ HitSig load_sig(const MatchArgs& a, uint32_t s, uint32_t len) {
+	HitSig g;
+	g.len = len;
+#pragma unroll
+	for (int t = 0; t < 4; ++t) g.so[t] = 0;
+#pragma unroll
+	for (int t = 0; t < 7; ++t) g.diag[t] = 0;
+	if (len > 8) {
+		g.len = kSigLong;
+		return g;
+	}
+	MemberIter<KeyT> it(a, s, len);
+	uint32_t val, st;
+	it.next(val, st);
+	const uint32_t sf = st, x0 = val & a.pos_mask;
+	g.so[0] = (val >> a.pos_bits) << 1;
+#pragma unroll
+	for (int t = 1; t < 8; ++t) {
+		if ((uint32_t)t < len) {
+			it.next(val, st);
+			const uint32_t o = st ^ sf, p = val & a.pos_mask;
+			g.so[t >> 1] |= (((val >> a.pos_bits) << 1) | o) << (16 * (t & 1));
+			g.diag[t - 1] = o ? p + x0 : p - x0;  // (32-bit wrap is one-to-one here: |p - x0| < 2^30, p + x0 < 2^31)
+		}
+	}
+	return g;
+}
+
 template <class KeyT>
 __global__ void __launch_bounds__(256)
 segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
@@ -417,14 +457,51 @@ segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const
                     uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head, uint32_t* __restrict__ collision_seen,
                     uint8_t* __restrict__ suspect) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_hits) return;
+	const bool valid = i < n_hits;
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t s_mine = 0, l_mine = 0;
+	HitSig mine;
+	mine.len = 0;
+#pragma unroll
+	for (int t = 0; t < 4; ++t) mine.so[t] = 0;
+#pragma unroll
+	for (int t = 0; t < 7; ++t) mine.diag[t] = 0;
+	if (valid) {
+		const uint32_t h = hid[i];
+		s_mine = hit_start[h];
+		l_mine = hit_len[h] & ~kFirstStrandBit;
+		mine = load_sig<KeyT>(a, s_mine, l_mine);
+	}
+	// the predecessor's hit: from the lane below, or (first lane of a warp) gathered like the own one
+	HitSig prev;
+	prev.len = __shfl_up_sync(0xffffffffu, mine.len, 1);
+#pragma unroll
+	for (int t = 0; t < 4; ++t) prev.so[t] = __shfl_up_sync(0xffffffffu, mine.so[t], 1);
+#pragma unroll
+	for (int t = 0; t < 7; ++t) prev.diag[t] = __shfl_up_sync(0xffffffffu, mine.diag[t], 1);
+	uint32_t s_prev = __shfl_up_sync(0xffffffffu, s_mine, 1), l_prev = __shfl_up_sync(0xffffffffu, l_mine, 1);
+	if (!valid) return;
 	uint8_t f = kFlagHead;
 	if (i > 0) {
 		const uint64_t k = hkey[i], kp = hkey[i - 1];
 		if ((k >> a.pos_bits) == (kp >> a.pos_bits)) {
-			const uint32_t ha = hid[i], hb = hid[i - 1];
-			if (same_diagonal<KeyT>(a, hit_start[ha], hit_len[ha] & ~kFirstStrandBit, hit_start[hb],
-			                        hit_len[hb] & ~kFirstStrandBit)) {
+			if (lane == 0) {
+				const uint32_t hb = hid[i - 1];
+				s_prev = hit_start[hb];
+				l_prev = hit_len[hb] & ~kFirstStrandBit;
+				prev = load_sig<KeyT>(a, s_prev, l_prev);
+			}
+			bool same;
+			if (mine.len == kSigLong || prev.len == kSigLong) {
+				same = same_diagonal<KeyT>(a, s_mine, l_mine, s_prev, l_prev);
+			} else {
+				same = mine.len == prev.len;
+#pragma unroll
+				for (int t = 0; t < 4; ++t) same = same && mine.so[t] == prev.so[t];
+#pragma unroll
+				for (int t = 0; t < 7; ++t) same = same && mine.diag[t] == prev.diag[t];
+			}
+			if (same) {
 				f = kFlagSameDiag;
 				const uint64_t gap = (k & a.pos_mask) - (kp & a.pos_mask);
 				if (gap > (uint64_t)L) f |= kFlagHead;
