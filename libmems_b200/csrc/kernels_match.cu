@@ -306,6 +306,36 @@ struct MemberIter {
 	}
 };
 
+// The members of a hit of at most 8 entries in ascending (sequence, position) order, as registers: all loads are issued
+// at once (MemberIter's merge is a chain of dependent loads) and a 19-step sorting network orders them.  Unused slots hold
+// 0xffffffff and sort to the end.
+__device__ __forceinline__ void order2(uint32_t& va, uint32_t& sa, uint32_t& vb, uint32_t& sb) {
+	const bool swap = vb < va;
+	const uint32_t v0 = swap ? vb : va, v1 = swap ? va : vb, s0 = swap ? sb : sa, s1 = swap ? sa : sb;
+	va = v0;
+	vb = v1;
+	sa = s0;
+	sb = s1;
+}
+template <class KeyT>
+__device__ __forceinline__ void sorted_members8(const MatchArgs& a, uint32_t s, uint32_t len, uint32_t (&v)[8], uint32_t (&st)[8]) {
+#pragma unroll
+	for (int t = 0; t < 8; ++t) {
+		const bool in = (uint32_t)t < len;
+		v[t] = in ? a.vals[s + t] : 0xffffffffu;
+		st[t] = in ? strand_of<KeyT>(a.keys, s + t) : 0u;
+	}
+#define MEMS_CE(i, j) order2(v[i], st[i], v[j], st[j])
+	MEMS_CE(0, 1); MEMS_CE(2, 3); MEMS_CE(4, 5); MEMS_CE(6, 7);
+	MEMS_CE(0, 2); MEMS_CE(1, 3); MEMS_CE(4, 6); MEMS_CE(5, 7);
+	MEMS_CE(1, 2); MEMS_CE(5, 6); MEMS_CE(0, 4); MEMS_CE(3, 7);
+	MEMS_CE(1, 5); MEMS_CE(2, 6);
+	MEMS_CE(1, 4); MEMS_CE(3, 6);
+	MEMS_CE(2, 4); MEMS_CE(3, 5);
+	MEMS_CE(3, 4);
+#undef MEMS_CE
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
 	h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
 	h *= 0xBF58476D1CE4E5B9ull;
@@ -328,18 +358,39 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += gridDim.x * blockDim.x) {
 		const uint32_t s = hit_start[h];
 		const uint32_t len = hit_len[h];
-		MemberIter<KeyT> it(a, s, len);
-		uint32_t val, st;
-		it.next(val, st);
-		const uint32_t sf = st;
-		const int64_t x0 = val & a.pos_mask;
-		uint64_t hash = mix64(0x1234567ull + len, val >> a.pos_bits);
-		while (it.next(val, st)) {
-			const uint32_t o = st ^ sf;
-			const int64_t p = val & a.pos_mask;
-			const int64_t diag = o ? p + x0 : p - x0;
-			hash = mix64(hash, ((uint64_t)(val >> a.pos_bits) << 1) | o);
-			hash = mix64(hash, (uint64_t)diag);
+		uint32_t sf;
+		int64_t x0;
+		uint64_t hash;
+		if (len <= 8) {  // the usual case: members as registers, no dependent loads
+			uint32_t v[8], st8[8];
+			sorted_members8<KeyT>(a, s, len, v, st8);
+			sf = st8[0];
+			x0 = v[0] & a.pos_mask;
+			hash = mix64(0x1234567ull + len, v[0] >> a.pos_bits);
+#pragma unroll
+			for (int t = 1; t < 8; ++t) {
+				if ((uint32_t)t < len) {
+					const uint32_t o = st8[t] ^ sf;
+					const int64_t p = v[t] & a.pos_mask;
+					const int64_t diag = o ? p + x0 : p - x0;
+					hash = mix64(hash, ((uint64_t)(v[t] >> a.pos_bits) << 1) | o);
+					hash = mix64(hash, (uint64_t)diag);
+				}
+			}
+		} else {
+			MemberIter<KeyT> it(a, s, len);
+			uint32_t val, st;
+			it.next(val, st);
+			sf = st;
+			x0 = val & a.pos_mask;
+			hash = mix64(0x1234567ull + len, val >> a.pos_bits);
+			while (it.next(val, st)) {
+				const uint32_t o = st ^ sf;
+				const int64_t p = val & a.pos_mask;
+				const int64_t diag = o ? p + x0 : p - x0;
+				hash = mix64(hash, ((uint64_t)(val >> a.pos_bits) << 1) | o);
+				hash = mix64(hash, (uint64_t)diag);
+			}
 		}
 		if (a.test_hash_bits) hash = (hash & ((1ull << a.test_hash_bits) - 1ull)) << (64 - a.test_hash_bits);
 		// 56 key bits = seven sort passes: 56 - pos_bits hash bits are plenty (two diagonals that share them only cost
@@ -433,17 +484,15 @@ __device__ __forceinline__ HitSig load_sig(const MatchArgs& a, uint32_t s, uint3
 		g.len = kSigLong;
 		return g;
 	}
-	MemberIter<KeyT> it(a, s, len);
-	uint32_t val, st;
-	it.next(val, st);
-	const uint32_t sf = st, x0 = val & a.pos_mask;
-	g.so[0] = (val >> a.pos_bits) << 1;
+	uint32_t v[8], st[8];
+	sorted_members8<KeyT>(a, s, len, v, st);
+	const uint32_t sf = st[0], x0 = v[0] & a.pos_mask;
+	g.so[0] = (v[0] >> a.pos_bits) << 1;
 #pragma unroll
 	for (int t = 1; t < 8; ++t) {
 		if ((uint32_t)t < len) {
-			it.next(val, st);
-			const uint32_t o = st ^ sf, p = val & a.pos_mask;
-			g.so[t >> 1] |= (((val >> a.pos_bits) << 1) | o) << (16 * (t & 1));
+			const uint32_t o = st[t] ^ sf, p = v[t] & a.pos_mask;
+			g.so[t >> 1] |= (((v[t] >> a.pos_bits) << 1) | o) << (16 * (t & 1));
 			g.diag[t - 1] = o ? p + x0 : p - x0;  // (32-bit wrap is one-to-one here: |p - x0| < 2^30, p + x0 < 2^31)
 		}
 	}
