@@ -1927,17 +1927,31 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		                                                               mem_val.p, mem_strand.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	std::vector<uint32_t> h_rec(n_hits), h_off(n_hits), h_val(n_mem);
-	std::vector<uint8_t> h_strand(n_mem);
-	MEMS_CUDA(cudaMemcpyAsync(h_rec.data(), rec_of_hit.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaMemcpyAsync(h_off.data(), mem_off.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaMemcpyAsync(h_val.data(), mem_val.p, (size_t)n_mem * 4, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaMemcpyAsync(h_strand.data(), mem_strand.p, (size_t)n_mem, cudaMemcpyDeviceToHost, c->stream));
+	// (page-locked staging from the context's pool: pageable targets would make these copies several times slower)
+	struct Staging {
+		Ctx* c;
+		void* p = nullptr;
+		size_t cap = 0;
+		~Staging() {
+			if (p) c->pinned_put(p, cap);
+		}
+	} staging{c};
+	const size_t stage_words = (size_t)n_hits * 2 + (size_t)n_mem + ((size_t)n_mem + 3) / 4;
+	staging.p = c->pinned_get(stage_words * 4 + 64, &staging.cap);
+	uint32_t* const h_rec = static_cast<uint32_t*>(staging.p);
+	uint32_t* const h_off = h_rec + n_hits;
+	uint32_t* const h_val = h_off + n_hits;
+	uint8_t* const h_strand = reinterpret_cast<uint8_t*>(h_val + n_mem);
+	MEMS_CUDA(cudaMemcpyAsync(h_rec, rec_of_hit.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaMemcpyAsync(h_off, mem_off.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaMemcpyAsync(h_val, mem_val.p, (size_t)n_mem * 4, cudaMemcpyDeviceToHost, c->stream));
+	MEMS_CUDA(cudaMemcpyAsync(h_strand, mem_strand.p, (size_t)n_mem, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 
 	mark("members to host");
 	// emitted records in component order: record r starts at raw[rec_start[r]]
 	std::vector<size_t> rec_start;
+	rec_start.reserve(n_comp);
 	for (size_t i = 0; i < n_flat; i += (size_t)raw[i] + 2) rec_start.push_back(i);
 
 	// the table of this call, or the caller's persistent one (several FindMatches calls into one MemHash table)
@@ -2023,10 +2037,13 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		if (range[t] < range[t - 1]) range[t] = range[t - 1];
 	}
 	std::vector<std::vector<std::unique_ptr<Entry>>> stored_by(n_threads);
-	std::vector<uint64_t> collisions_by(n_threads, 0);
+	// a table that lives for this call only keeps no copies: its entries point at the records the device emitted
+	std::vector<std::vector<Entry>> arena_by(n_threads);
+	std::vector<uint64_t> collisions_by(n_threads, 0), words_by(n_threads, 0), count_by(n_threads, 0);
 	run_parallel([&](unsigned t) {
 		Entry probe;
 		std::vector<int64_t> probe_start;
+		if (!persistent) arena_by[t].reserve(bucket_first[range[t + 1]] - bucket_first[range[t]]);  // pointers stay valid
 		for (uint32_t bkt = range[t]; bkt < range[t + 1]; ++bkt) {
 			std::vector<Entry*>& bucket = table[bkt];
 			for (uint32_t k = bucket_first[bkt]; k < bucket_first[bkt + 1]; ++k) {
@@ -2039,27 +2056,67 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 				}
 				// "ExtendMatch": the extended form of this hit is the component the device computed for it
 				const int64_t* rec = raw + rec_start[h_rec[h]];
-				auto e = std::make_unique<Entry>();
+				Entry* e;
+				if (persistent) {
+					stored_by[t].push_back(std::make_unique<Entry>());
+					e = stored_by[t].back().get();
+					e->own.assign(rec + 2, rec + 2 + rec[0]);
+					e->start = e->own.data();
+				} else {
+					arena_by[t].emplace_back();
+					e = &arena_by[t].back();
+					e->start = rec + 2;
+				}
 				e->seqcount = (uint32_t)rec[0];
 				e->len = rec[1];
 				e->mersize = 0;  // stored copies lose m_mersize (MatchHashEntry.cpp:118-126)
-				e->own.assign(rec + 2, rec + 2 + rec[0]);
-				e->start = e->own.data();
 				e_calc_offset(*e);
 				at = bucket_lower_bound(bucket, *e);
-				bucket.insert(bucket.begin() + at, e.get());
-				stored_by[t].push_back(std::move(e));
+				bucket.insert(bucket.begin() + at, e);
+				words_by[t] += (uint64_t)e->seqcount + 2;
+				++count_by[t];
 			}
 		}
 	});
 	for (unsigned t = 0; t < n_threads; ++t) {
 		T.collisions += collisions_by[t];
-		T.mem_count += stored_by[t].size();
+		T.mem_count += count_by[t];
 		for (auto& e : stored_by[t]) stored.push_back(std::move(e));
 	}
 	out.mem_count = T.mem_count;
 	out.collisions = T.collisions;
 	mark("table replay");
+	if (!persistent) {
+		// MemHash::GetMatchList (MemHash.h:183-203): buckets in order, front to back — every thread writes the records of
+		// its own bucket range into a page-locked buffer of the pool (no copies of copies, no fresh pages to fault in)
+		uint64_t total = 0, n_out = 0;
+		std::vector<uint64_t> word_at(n_threads, 0);
+		for (unsigned t = 0; t < n_threads; ++t) {
+			word_at[t] = total;
+			total += words_by[t];
+			n_out += count_by[t];
+		}
+		size_t out_cap = 0;
+		int64_t* dst = (int64_t*)c->pinned_get((size_t)total * sizeof(int64_t) + 64, &out_cap);
+		run_parallel([&](unsigned t) {
+			int64_t* w = dst + word_at[t];
+			for (uint32_t bkt = range[t]; bkt < range[t + 1]; ++bkt)
+				for (const Entry* e : table[bkt]) {
+					*w++ = e->seqcount;
+					*w++ = e->len;
+					memcpy(w, e->start, sizeof(int64_t) * e->seqcount);
+					w += e->seqcount;
+				}
+		});
+		out.flat.release();  // the device's records (raw) are no longer needed
+		out.flat.pinned = dst;
+		out.flat.pinned_cap = out_cap;
+		out.flat.pinned_n = (size_t)total;
+		out.n_matches = n_out;
+		mark("output list");
+		out.host_replay_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_replay).count();
+		return;
+	}
 	// MemHash::GetMatchList (MemHash.h:183-203): buckets in order, front to back
 	{
 		size_t total = 0;
