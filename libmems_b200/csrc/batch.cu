@@ -127,7 +127,10 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 	b->d_meta = DevBuf<SeqMeta>(c, b->n_seqs);
 	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
 	b->packed = DevBuf<uint32_t>(c, b->total_words);
-	MEMS_CUDA(cudaMemsetAsync(b->packed.p, 0, b->total_words * sizeof(uint32_t), c->stream));  // pads and alignment gaps
+	{
+		CopyScope zs(c, "copy_zero_packed", (double)b->total_words * 4);
+		MEMS_CUDA(cudaMemsetAsync(b->packed.p, 0, b->total_words * sizeof(uint32_t), c->stream));  // pads and alignment gaps
+	}
 	DevBuf<uint8_t> ascii(c, total_bytes + 16);
 	DevBuf<uint32_t> gap_flag(c, 1);
 	MEMS_CUDA(cudaMemsetAsync(gap_flag.p, 0, sizeof(uint32_t), c->stream));

@@ -316,7 +316,10 @@ int radix_sort_pairs(Ctx* c, bool key64, void* d_keys[2], uint32_t* d_vals[2], u
 	DevBuf<uint32_t> bin_base(c, (size_t)P * kRadix);
 	const size_t status_words = (size_t)n_tiles * kRadix;
 	DevBuf<uint32_t> status(c, status_words * P + P);  // + one ticket per pass
-	MEMS_CUDA(cudaMemsetAsync(status.p, 0, (status_words * P + P) * sizeof(uint32_t), c->stream));
+	{
+		CopyScope zs(c, "copy_zero_sort_state", (double)(status_words * P + P) * 4);
+		MEMS_CUDA(cudaMemsetAsync(status.p, 0, (status_words * P + P) * sizeof(uint32_t), c->stream));
+	}
 	{
 		KernelScope ks(c, "scan_bins");
 		scan_bins_kernel<<<P, kRadix, 0, c->stream>>>(d_hist, bin_base.p);

@@ -3,16 +3,19 @@ sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 import libmems_b200 as mems
 from libmems_b200 import synth
-gs = synth.baseline_genomes('c2')
+name = sys.argv[1] if len(sys.argv) > 1 else 'c2'
+gs = synth.baseline_genomes(name)
+W = synth.BASELINE_WORKLOADS[name]
 dev = [torch.from_numpy(g).cuda() for g in gs]
 stream = torch.cuda.Stream()
 ctx = mems.Context(0, stream=stream.cuda_stream)
-seed = mems.get_seed(15)
+seed = mems.get_seed(W[2])
+mode = mems.MODE_REPEAT if W[3] == 'repeat' else mems.MODE_MEMHASH
 bufs = [(d.data_ptr(), d.numel()) for d in dev]
 def ev():
     e = torch.cuda.Event(enable_timing=True); e.record(stream); return e
 for _ in range(3):
-    s = ctx.create_smls(bufs, seed); f, i = ctx.find_matches(s)
+    s = ctx.create_smls(bufs, seed); f, i = ctx.find_matches(s, mode=mode)
     for x in s: x.close()
 K = 10
 tc = tf = 0.0
@@ -23,7 +26,7 @@ for _ in range(K):
     t1 = time.perf_counter(); b = ev()
     torch.cuda.synchronize(); t1s = time.perf_counter()
     c = ev(); t2 = time.perf_counter()
-    f, i = ctx.find_matches(s)
+    f, i = ctx.find_matches(s, mode=mode)
     t3 = time.perf_counter(); d = ev()
     torch.cuda.synchronize()
     tc += a.elapsed_time(b); tf += c.elapsed_time(d)
