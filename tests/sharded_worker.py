@@ -56,6 +56,25 @@ def main():
             assert hits == sinfo["n_hits"]
             print("sharded ok: call=%d world=%d genomes=%d x %d matches=%d hits=%d per-rank matches=%s" %
                   (call, world, n_genomes, n_len, len(union), hits, [len(p) for p, _ in gathered]))
+    # a failure local to ONE rank (a '-' in its block) must come back as the same error on EVERY rank instead of
+    # leaving the others in the next collective; a fresh communicator afterwards works as before
+    gs = synth.genome_family(n_genomes, 20_000, seed=14)
+    first, count = mems.shard_sequence_range(n_genomes, world - 1, world)
+    bad = bytearray(gs[first].tobytes())
+    bad[len(bad) // 2] = ord("-")
+    gs[first] = np.frombuffer(bytes(bad), dtype=np.uint8)
+    first, count = mems.shard_sequence_range(n_genomes, rank, world)
+    seqs = [g if first <= i < first + count else None for i, g in enumerate(gs)]
+    try:
+        ctx.find_matches_sharded(comm, seqs, [len(g) for g in gs], seed)
+        code = 0
+    except mems.MemsError as e:
+        code = e.code
+    codes = [None] * world
+    dist.all_gather_object(codes, code)
+    assert codes == [2] * world, "every rank must report MEMS_ERR_GAP, got %s" % codes
+    if rank == 0:
+        print("sharded ok: gap on the last rank's block reported by all %d ranks" % world)
     dist.barrier()
     comm.close()
     ctx.close()
