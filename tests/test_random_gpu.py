@@ -18,7 +18,7 @@ def random_case(rng):
     G = int(rng.integers(2, 10))
     n = int(rng.choice([int(rng.integers(1, 80)), int(rng.integers(80, 2000)), int(rng.integers(2000, 30000))]))
     gs = synth.genome_family(G, n, seed=int(rng.integers(1, 1 << 30)), snp_rate=float(rng.choice([0.0, 0.005, 0.02, 0.08])),
-                             n_indels=int(rng.integers(0, 6)), max_indel=int(rng.integers(1, 40)))
+                             n_indels=int(rng.integers(0, 6)) if n >= 300 else 0, max_indel=int(rng.integers(1, 40)))
     if rng.random() < 0.3:
         gs[int(rng.integers(0, G))] = synth.revcomp(gs[int(rng.integers(0, G))])
     if rng.random() < 0.3:
