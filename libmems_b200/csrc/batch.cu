@@ -91,7 +91,7 @@ static void extract_and_sort(Batch& b) {
 	const size_t key_bytes = b.key64 ? 8 : 4;
 	const uint64_t n = b.n_total;
 	SortPlan plan = make_sort_plan(b.sort_bits());
-	// extraction output stays resident in position order: the window test of match extension reads it
+	// extraction output (position order) is the input of the first pass and stays resident for SeedOccurrenceList / start points
 	DevBuf<uint8_t> keys_pos(c, n * key_bytes), keys_a(c, n * key_bytes), keys_b(c, n * key_bytes);
 	DevBuf<uint32_t> vals_a(c, n), vals_b(c, n);
 	DevBuf<uint32_t> hist(c, (size_t)plan.n_passes * 256);
@@ -125,22 +125,39 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 	const uint64_t total_bytes = last.byte_off + ((uint64_t)last.n_bases + 15) / 16 * 16;
 
 	b->d_meta = DevBuf<SeqMeta>(c, b->n_seqs);
-	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
 	b->packed = DevBuf<uint32_t>(c, b->total_words);
 	{
 		CopyScope zs(c, "copy_zero_packed", (double)b->total_words * 4);
 		MEMS_CUDA(cudaMemsetAsync(b->packed.p, 0, b->total_words * sizeof(uint32_t), c->stream));  // pads and alignment gaps
 	}
-	DevBuf<uint8_t> ascii(c, total_bytes + 16);
+	// Sequences in host memory (pageable or page-locked) are staged in one device buffer; a sequence that already lives
+	// in this device's memory, 16-byte aligned, is packed where it lies.
+	std::vector<char> in_place(n_seqs, 0);
+	uint64_t staged_bytes = 0;
+	for (int g = 0; g < n_seqs; ++g) {
+		if (!lens[g]) continue;
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, seqs[g]) == cudaSuccess && attr.type == cudaMemoryTypeDevice && attr.device == c->device &&
+		    (reinterpret_cast<uintptr_t>(seqs[g]) & 15u) == 0)
+			in_place[g] = 1;
+		else
+			staged_bytes += (lens[g] + 15) / 16 * 16;
+		cudaGetLastError();  // (an unregistered host pointer makes older runtimes report an error here)
+	}
+	DevBuf<uint8_t> ascii(c, (staged_bytes ? total_bytes : 0) + 16);
 	DevBuf<uint32_t> gap_flag(c, 1);
 	MEMS_CUDA(cudaMemsetAsync(gap_flag.p, 0, sizeof(uint32_t), c->stream));
 	{
-		CopyScope cs(c, "copy_in_sequences", (double)total_bytes);
-		for (int g = 0; g < n_seqs; ++g)
-			if (lens[g])
-				// cudaMemcpyDefault: seqs[g] may be pageable or pinned host memory, or already a device pointer
+		CopyScope cs(c, "copy_in_sequences", (double)staged_bytes);
+		for (int g = 0; g < n_seqs; ++g) {
+			if (!lens[g]) continue;
+			if (in_place[g])
+				b->meta[g].byte_off = reinterpret_cast<uint64_t>(seqs[g]) - reinterpret_cast<uint64_t>(ascii.p);  // see pack_kernel
+			else
 				MEMS_CUDA(cudaMemcpyAsync(ascii.p + b->meta[g].byte_off, seqs[g], lens[g], cudaMemcpyDefault, c->stream));
+		}
 	}
+	MEMS_CUDA(cudaMemcpyAsync(b->d_meta.p, b->meta.data(), sizeof(SeqMeta) * b->n_seqs, cudaMemcpyHostToDevice, c->stream));
 	launch_pack(c, ascii.p, b->packed.p, b->d_meta.p, b->meta.data(), n_seqs, gap_flag.p);
 	b->planes = DevBuf<uint2>(c, b->total_words / 2);
 	launch_planes(c, b->packed.p, b->planes.p, b->total_words);

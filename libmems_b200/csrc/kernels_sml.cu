@@ -38,10 +38,17 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t* __restrict__ packed, co
 	uint32_t out = 0;
 	uint64_t base0 = wi * 16;
 	if (base0 < m.n_bases) {
-		const uint8_t* src = ascii + m.byte_off + base0;  // byte_off is 16-byte aligned, base0 a multiple of 16
-		uint4 raw = *reinterpret_cast<const uint4*>(src);  // staging buffer is padded to 16 bytes per sequence
-		uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+		// byte_off is relative to the staging buffer; a sequence that already lives in device memory is read where it
+		// lies (its byte_off then is the distance from the staging buffer to it).  16-byte aligned either way.
+		const uint8_t* src = reinterpret_cast<const uint8_t*>(reinterpret_cast<uint64_t>(ascii) + m.byte_off) + base0;
 		uint32_t n_here = m.n_bases - base0 < 16 ? (uint32_t)(m.n_bases - base0) : 16u;
+		uint32_t r[4] = {0, 0, 0, 0};
+		if (n_here == 16u) {
+			const uint4 raw = *reinterpret_cast<const uint4*>(src);
+			r[0] = raw.x; r[1] = raw.y; r[2] = raw.z; r[3] = raw.w;
+		} else {  // the sequence's last bases: never read past its end (it may be the end of a caller's allocation)
+			for (uint32_t k = 0; k < n_here; ++k) r[k >> 2] |= (uint32_t)src[k] << ((k & 3) * 8);
+		}
 		bool gap = false;
 #pragma unroll
 		for (int k = 0; k < 16; ++k) {
