@@ -29,7 +29,6 @@ import hashlib
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -59,12 +58,15 @@ def make_genomes(name, n_genomes, length, seed):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons while the timed regions run (B200_PROFILING.md's clocks line), sampled
-    in-process through NVML every 20 ms: an `nvidia-smi -lms` child takes the driver lock while it starts up and
-    stalled the first timed region by milliseconds."""
+    """SM clock and throttle reasons while the timed regions run (B200_PROFILING.md's clocks line), read through NVML by
+    the thread that drives the GPU, between the SML build call (which returns while the GPU is still sorting) and the
+    match-finding call: the GPU is under load, and no CUDA call of ours is in flight.  A polling thread (or an
+    `nvidia-smi -lms` child) contends with the CUDA calls of the steps for the driver's locks: at a 20 ms period it
+    stalled single steps by up to a second."""
 
     def __init__(self, device):
-        self.device, self.rows, self.stop_flag, self.t, self.nvml = device, [], threading.Event(), None, None
+        self.device, self.rows, self.nvml, self.last = device, [], None, 0.0
+        self.period = float(os.environ.get("MEMS_BENCH_CLOCK_PERIOD", "0.02"))
 
     def start(self):
         try:
@@ -74,8 +76,6 @@ class ClockSampler:
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self._sample()  # first query outside the timed region
-            self.t = threading.Thread(target=self._loop, daemon=True)
-            self.t.start()
         except Exception as e:  # noqa: BLE001 - NVML missing or refused: report it instead of failing the bench
             self.nvml, self.err = None, str(e)
 
@@ -92,19 +92,22 @@ class ClockSampler:
         self.rows.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)),
                           int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
 
-    def _loop(self):
-        while not self.stop_flag.wait(0.02):
+    def tick(self):
+        """Called by the step function while the GPU works: one sample if the last one is older than the period."""
+        if self.nvml is None:
+            return
+        now = time.perf_counter()
+        if now - self.last >= self.period:
+            self.last = now
             try:
                 self._sample()
             except Exception:  # noqa: BLE001
-                return
+                self.nvml = None
 
     def stop(self):
-        if not self.nvml:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
-        self.stop_flag.set()
-        self.t.join(timeout=2)
-        n = self.nvml
+        n = self.nvml or __import__("pynvml")
         names = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
         reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
@@ -114,7 +117,8 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
-                "samples": len(sm), "source": "NVML, 20 ms period, warm-up and all timed regions of the headline workload"}
+                "samples": len(sm), "source": "NVML, read by the driving thread while the GPU works on a step (at most every %g ms), "
+                                              "warm-up and all timed regions of the headline workload" % (1e3 * self.period)}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -263,6 +267,19 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # The host thread drives ~60 launches and a handful of waits per step.  MEMS_BENCH_PRIO=nice / fifo ask the scheduler
+    # to favour this process (an experiment: it made no difference on the pool's boxes); the default leaves it alone.
+    prio = os.environ.get("MEMS_BENCH_PRIO", "none")
+    host_priority = "unchanged"
+    try:
+        if prio == "fifo":
+            os.sched_setscheduler(0, os.SCHED_FIFO, os.sched_param(10))
+            host_priority = "SCHED_FIFO 10"
+        elif prio == "nice":
+            os.setpriority(os.PRIO_PROCESS, 0, -20)
+            host_priority = "nice -20"
+    except (OSError, AttributeError) as e:
+        host_priority = "unchanged (%s)" % type(e).__name__
     # run this rank on the CPUs next to its GPU: the page-locked buffers of the copies are then allocated on the GPU's
     # NUMA node (eight ranks whose buffers sit behind the other socket share one inter-socket link)
     numa = "unchanged"
@@ -313,9 +330,12 @@ def main():
             ms = float(t.item())
         return ms, flat, info
 
+    sampler = ClockSampler(local_rank)
+
     def single_step(m, sd):
         def step(bufs):
             smls = ctx.create_smls([(b.data_ptr(), b.numel()) for b in bufs], sd)
+            sampler.tick()  # the GPU is sorting; no CUDA call of this process is in flight
             flat, info = ctx.find_matches(smls, mode=m)
             for s in smls:
                 s.close()
@@ -343,7 +363,9 @@ def main():
 
         def step(bufs):
             seqs = [(b.data_ptr(), b.numel()) if b is not None else None for b in bufs]
-            return ctx.find_matches_sharded(comm, seqs, lens, seed, mode=match_mode)
+            res = ctx.find_matches_sharded(comm, seqs, lens, seed, mode=match_mode)
+            sampler.tick()  # (one collective call per step: the sample falls between two steps)
+            return res
 
         # ---- parity of the sharded MatchList, before anything is timed: the union of the ranks' shares against a
         # single-GPU run of the same input on rank 0 (both as canonically sorted record lists)
@@ -368,8 +390,7 @@ def main():
         dist.barrier()
         del gs
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:  # one poller per node: concurrent pollers contend for the driver and stall the ranks
+    if rank == 0:  # one reader per node
         sampler.start()  # before the warm-up: NVML's start-up cost must not land in a timed region
     # warm-up with the same buffer lifetime pattern as the timed regions (one MatchList alive outside, one per step):
     # the first cudaHostAlloc of a result buffer costs milliseconds
@@ -459,7 +480,7 @@ def main():
             "config": {"workload": desc, "genomes": n_genomes, "genome_length": length, "seed_weight": weight,
                        "seed_pattern": hex(seed), "multi_gpu": ("sharded: genome blocks per rank, seed-range all-to-all + diagonal all-to-all "
                                      "(peer-to-peer over NVLink); weak scaling by genome length") if world > 1 else "n/a",
-                       "host_affinity": numa,
+                       "host_affinity": numa, "host_priority": host_priority,
                        "l2": "per-step working set (%.0f MB of seed records per GPU) exceeds the 126 MB L2" %
                              (mbp_total / world * (8 if 2 * weight + 1 <= 32 else 12))},
             "e2e": {"value": mbp_total * args.steps / (ms_e2e / 1e3), "unit": "Mbp/s",

@@ -66,6 +66,7 @@ int mems_ctx_create(int device, void* stream, mems_ctx_t* out) {
 			                               "' is not sm_100 class; this library ships sm_100a code only");
 		auto c = std::make_shared<Ctx>();
 		c->device = device;
+		if (const char* e = getenv("MEMS_TRACE_SLOW")) c->trace_slow_ms = atof(e);
 		c->sm_count = prop.multiProcessorCount;
 		if (stream) {
 			c->stream = (cudaStream_t)stream;
@@ -73,10 +74,6 @@ int mems_ctx_create(int device, void* stream, mems_ctx_t* out) {
 			MEMS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 			c->own_stream = true;
 		}
-		// keep freed blocks in the pool: repeated builds reuse them instead of going back to the driver
-		MEMS_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
-		uint64_t threshold = UINT64_MAX;
-		MEMS_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
 		*out = new mems_ctx{c};
 	});
 }

@@ -2,9 +2,13 @@
 // Nothing here is part of the public ABI (see include/mems_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
 #include <stdint.h>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -80,7 +84,6 @@ struct Ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
-	cudaMemPool_t pool = nullptr;
 	int sm_count = 148;
 	bool profiling = false;
 	uint64_t launch_count = 0;
@@ -90,9 +93,19 @@ struct Ctx {
 	// test hooks (mems_test_hooks): 0 = production behaviour
 	int test_hash_bits = 0;    // keep only this many bits of the diagonal hash (forces bucket collisions)
 	int test_walk_budget = 0;  // probes / rounds before a walk moves on to the next larger walker
+	double trace_slow_ms = 0;  // MEMS_TRACE_SLOW
 
-	void* alloc(size_t bytes);  // stream-ordered
+	void* alloc(size_t bytes);  // stream-ordered on `stream`: arena of cudaMalloc'ed slabs, no driver call once warm
 	void free(void* p);
+	std::mutex arena_mutex;
+	std::vector<std::pair<char*, size_t>> arena_slabs;
+	std::map<char*, size_t> arena_free;             // free blocks by address (merged with their neighbours on free)
+	std::multimap<size_t, char*> arena_by_size;     // the same blocks by size (best fit)
+	std::unordered_map<char*, size_t> arena_used;
+	size_t arena_reserved = 0;
+	void arena_insert_free(char* p, size_t bytes);
+	void arena_erase_free(std::map<char*, size_t>::iterator it);
+	void arena_release_idle_slabs();
 	// page-locked host staging buffers for results (D2H at full PCIe rate), recycled across calls
 	std::vector<std::pair<void*, size_t>> pinned_free;
 	void* pinned_get(size_t bytes, size_t* capacity);
@@ -139,12 +152,18 @@ struct DevBuf {
 struct KernelScope {
 	Ctx* c;
 	const char* name;
+	std::chrono::steady_clock::time_point t0;
 	KernelScope(Ctx* ctx, const char* nm, double bytes = 0) : c(ctx), name(nm) {
 		c->launch_count++;
 		if (c->profiling) c->prof_begin(nm, bytes);
+		if (c->trace_slow_ms > 0) t0 = std::chrono::steady_clock::now();
 	}
 	~KernelScope() {
 		if (c->profiling) c->prof_end(name);
+		if (c->trace_slow_ms > 0) {  // MEMS_TRACE_SLOW: a launch call that blocks the host (diagnosis of step-time outliers)
+			const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+			if (ms >= c->trace_slow_ms) fprintf(stderr, "[mems slow] launch of %s took %.3f ms on the host\n", name, ms);
+		}
 	}
 };
 

@@ -1,4 +1,8 @@
-// context.cu — per-thread execution context: stream, stream-ordered memory pool, launch profiler.
+// context.cu — per-thread execution context: stream, stream-ordered device-memory arena, launch profiler.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -6,14 +10,122 @@
 
 namespace mems {
 
+namespace {
+// MEMS_TRACE_SLOW=<ms>: report host-side calls of the allocator that take longer (diagnosis of step-time outliers)
+double slow_ms() {
+	static const double v = getenv("MEMS_TRACE_SLOW") ? atof(getenv("MEMS_TRACE_SLOW")) : 0.0;
+	return v;
+}
+struct SlowCall {
+	const char* what;
+	size_t bytes;
+	std::chrono::steady_clock::time_point t0;
+	SlowCall(const char* w, size_t b) : what(w), bytes(b) {
+		if (slow_ms() > 0) t0 = std::chrono::steady_clock::now();
+	}
+	~SlowCall() {
+		if (slow_ms() > 0) {
+			const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+			if (ms >= slow_ms()) fprintf(stderr, "[mems slow] %s(%zu bytes) took %.3f ms\n", what, bytes, ms);
+		}
+	}
+};
+}  // namespace
+
+// Device memory: an arena owned by the context.  Every buffer of a call lives and dies in stream order on the context's
+// one stream, so a host-side best-fit allocator over a few cudaMalloc'ed slabs is exact (a block freed here is reused only
+// by work enqueued later on the same stream) and a repeated workload makes no driver call at all in the steady state.
+// cudaMallocAsync's pool went back to the driver for the large blocks of every step on the pool's boxes — milliseconds each,
+// and hundreds of milliseconds whenever another tenant of the node held the kernel driver's lock.
+static constexpr size_t kArenaAlign = 512, kSlabMin = 32u << 20, kSlabRound = 2u << 20;
+
+void Ctx::arena_insert_free(char* p, size_t bytes) {
+	arena_free[p] = bytes;
+	arena_by_size.insert({bytes, p});
+}
+
+void Ctx::arena_erase_free(std::map<char*, size_t>::iterator it) {
+	auto range = arena_by_size.equal_range(it->second);
+	for (auto j = range.first; j != range.second; ++j)
+		if (j->second == it->first) {
+			arena_by_size.erase(j);
+			break;
+		}
+	arena_free.erase(it);
+}
+
+void Ctx::arena_release_idle_slabs() {
+	for (size_t i = 0; i < arena_slabs.size();) {
+		auto it = arena_free.find(arena_slabs[i].first);
+		if (it != arena_free.end() && it->second == arena_slabs[i].second) {
+			arena_erase_free(it);
+			cudaFree(arena_slabs[i].first);
+			arena_reserved -= arena_slabs[i].second;
+			arena_slabs.erase(arena_slabs.begin() + i);
+		} else {
+			++i;
+		}
+	}
+}
+
 void* Ctx::alloc(size_t bytes) {
-	void* p = nullptr;
-	MEMS_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, stream));
+	bytes = (std::max<size_t>(bytes, 1) + kArenaAlign - 1) & ~(kArenaAlign - 1);
+	std::lock_guard<std::mutex> lock(arena_mutex);
+	auto fit = arena_by_size.lower_bound(bytes);
+	if (fit == arena_by_size.end()) {  // grow: one more slab (cudaMalloc synchronises the device; warm-up only)
+		const size_t slab = std::max(kSlabMin, (bytes + kSlabRound - 1) & ~(kSlabRound - 1));
+		void* p = nullptr;
+		SlowCall sc("cudaMalloc", slab);
+		cudaError_t e = cudaMalloc(&p, slab);
+		if (e == cudaErrorMemoryAllocation) {  // give idle slabs back (their last users may still run: wait for them) and retry
+			cudaGetLastError();
+			MEMS_CUDA(cudaStreamSynchronize(stream));
+			arena_release_idle_slabs();
+			e = cudaMalloc(&p, slab);
+		}
+		MEMS_CUDA(e);
+		arena_slabs.push_back({(char*)p, slab});
+		arena_reserved += slab;
+		arena_insert_free((char*)p, slab);
+		fit = arena_by_size.lower_bound(bytes);
+	}
+	char* p = fit->second;
+	const size_t have = fit->first;
+	arena_by_size.erase(fit);
+	arena_free.erase(p);
+	if (have > bytes) arena_insert_free(p + bytes, have - bytes);
+	arena_used[p] = bytes;
 	return p;
 }
 
-void Ctx::free(void* p) {
-	if (p) cudaFreeAsync(p, stream);
+void Ctx::free(void* ptr) {
+	if (!ptr) return;
+	std::lock_guard<std::mutex> lock(arena_mutex);
+	auto u = arena_used.find((char*)ptr);
+	if (u == arena_used.end()) return;  // not ours
+	char* p = u->first;
+	size_t bytes = u->second;
+	arena_used.erase(u);
+	// merge with free neighbours of the same slab
+	size_t si = 0;
+	while (si < arena_slabs.size() && !(p >= arena_slabs[si].first && p < arena_slabs[si].first + arena_slabs[si].second)) ++si;
+	char* lo = arena_slabs[si].first;
+	char* hi = lo + arena_slabs[si].second;
+	auto next = arena_free.lower_bound(p);
+	if (next != arena_free.end() && next->first == p + bytes && next->first < hi) {
+		bytes += next->second;
+		arena_erase_free(next);
+	}
+	auto prev = arena_free.lower_bound(p);
+	if (prev != arena_free.begin()) {
+		--prev;
+		if (prev->first >= lo && prev->first + prev->second == p) {
+			p = prev->first;
+			bytes += prev->second;
+			arena_erase_free(prev);
+		}
+	}
+	arena_insert_free(p, bytes);
 }
 
 void* Ctx::pinned_get(size_t bytes, size_t* capacity) {
@@ -29,6 +141,7 @@ void* Ctx::pinned_get(size_t bytes, size_t* capacity) {
 	}
 	size_t cap = (bytes + (1u << 20)) & ~(size_t)((1u << 20) - 1);  // round up to 1 MiB
 	void* p = nullptr;
+	SlowCall sc("cudaHostAlloc", cap);
 	MEMS_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
 	*capacity = cap;
 	return p;
@@ -111,6 +224,7 @@ Ctx::~Ctx() {
 	for (auto e : free_events) cudaEventDestroy(e);
 	for (auto& pb : pinned_free) cudaFreeHost(pb.first);
 	for (uint32_t* p : host_words_free) cudaFreeHost(p);
+	for (auto& sl : arena_slabs) cudaFree(sl.first);
 	if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
