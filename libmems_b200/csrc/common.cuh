@@ -106,6 +106,10 @@ struct Ctx {
 	void arena_insert_free(char* p, size_t bytes);
 	void arena_erase_free(std::map<char*, size_t>::iterator it);
 	void arena_release_idle_slabs();
+	// tile states of the chained scans (exclusive_scan_u32): [0] ticket counter, [1..] one word per tile, stamped by epoch
+	uint64_t* scan_state = nullptr;
+	size_t scan_cap = 0;
+	uint32_t scan_epoch = 0, scan_ticket_base = 0;
 	// page-locked host staging buffers for results (D2H at full PCIe rate), recycled across calls
 	std::vector<std::pair<void*, size_t>> pinned_free;
 	void* pinned_get(size_t bytes, size_t* capacity);

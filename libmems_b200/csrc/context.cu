@@ -225,6 +225,7 @@ Ctx::~Ctx() {
 	for (auto& pb : pinned_free) cudaFreeHost(pb.first);
 	for (uint32_t* p : host_words_free) cudaFreeHost(p);
 	for (auto& sl : arena_slabs) cudaFree(sl.first);
+	if (scan_state) cudaFree(scan_state);
 	if (own_stream && stream) cudaStreamDestroy(stream);
 }
 

@@ -603,6 +603,19 @@ constexpr int kExtendWarps = 4;
 constexpr int kMemberTile = 64;  // members staged in shared memory per warp (MEMS_MAX_SEQS fits at once)
 constexpr int kProbeWindows = 1024;  // windows one warp tests per probe
 constexpr int kWarpProbeBudget = 6;  // probes a single warp spends on one walk before deferring it to a whole CTA
+// Nine walks in ten end within a few hundred windows (config 2: 88 % of the segments need ONE 1024-window probe), so
+// the walk kernels start every segment on a GROUP of kGroupLanes lanes — 32 windows per lane as before, several
+// segments per warp — and only the walks that outlast kGroupProbeBudget group probes continue on the whole warp.
+#ifndef MEMS_GROUP_LANES
+#define MEMS_GROUP_LANES 8
+#endif
+#ifndef MEMS_GROUP_BUDGET
+#define MEMS_GROUP_BUDGET 2
+#endif
+constexpr int kGroupLanes = MEMS_GROUP_LANES;
+constexpr int kGroupsPerWarp = 32 / kGroupLanes;
+constexpr int kGroupMembers = 16;  // members staged per segment (segment_stage_kernel); hits with more go to the whole warp
+constexpr int kGroupProbeBudget = MEMS_GROUP_BUDGET;
 
 struct SeedShape {  // what the window test needs of the pattern (SeedDesc::off / mirror), in shared memory
 	uint8_t off[32], mirror[32];
@@ -647,36 +660,72 @@ __device__ __forceinline__ Chunk reverse_chunk(const Chunk& c) {
 	return r;
 }
 
+// What a walk needs of one member of a hit (union entry j; sf = strand of the hit's first member): the base index of
+// its window 0 in the batch's base array (.x low 32 bits, .y high bits; bit 31 of .y = opposite orientation to the first
+// member) and the window offsets [lo, hi] at which the member still lies inside its sequence.
 template <class KeyT>
-struct WarpHit {
+__device__ __forceinline__ uint2 walk_member_entry(const MatchArgs& a, uint32_t j, uint32_t sf, int32_t& lo, int32_t& hi) {
+	const uint32_t val = a.vals[j];
+	const uint32_t o = strand_of<KeyT>(a.keys, j) ^ sf;
+	const SeqMeta m = a.meta[val >> a.pos_bits];
+	const int32_t p = (int32_t)(val & a.pos_mask), last = (int32_t)m.n_seeds - 1;
+	lo = o ? p - last : -p;
+	hi = o ? p : last - p;
+	const uint64_t base = m.word_off * 16ull + (uint64_t)p;
+	return make_uint2((uint32_t)base, (uint32_t)(base >> 32) | (o ? 0x80000000u : 0u));
+}
+
+// GW lanes (a whole warp, or an aligned group of 4/8/16 lanes) walk one hit: every sync primitive below is scoped to the
+// group's lanes, so the groups of a warp run their own control flow.
+template <class KeyT, int GW = 32>
+struct WalkHit {
+	static constexpr int kWindows = 32 * GW;                             // windows per probe
+	static constexpr int kTile = kMemberTile;  // members staged at once (groups only ever see hits of <= kGroupMembers)
 	const MatchArgs& a;
 	const SeedShape& shape;
-	uint2* s_mem;  // this warp's kMemberTile slots: base index of the member's window 0 in the batch's base array
+	uint2* s_mem;  // this group's kTile slots: base index of the member's window 0 in the batch's base array
 	               // (.x low 32 bits, .y high bits), bit 31 of .y = opposite orientation to the first member
 	uint32_t s, len, sf;
 	int32_t kmin, kmax;  // valid window offsets (all |k| < 2^31: positions are < 2^30)
 	bool any_reverse;
-	int lane;
+	int lane;  // within the group
+	uint32_t gmask = 0xffffffffu;  // the group's lanes in the warp
+	int gshift = 0;                // its first lane
 #ifdef MEMS_WALK_STATS
 	uint32_t n_probes = 0;
 #endif
 
-	__device__ uint2 member_entry(uint32_t j, int32_t& lo, int32_t& hi) const {
-		const uint32_t val = a.vals[j];
-		const uint32_t o = strand_of<KeyT>(a.keys, j) ^ sf;
-		const SeqMeta m = a.meta[val >> a.pos_bits];
-		const int32_t p = (int32_t)(val & a.pos_mask), last = (int32_t)m.n_seeds - 1;
-		lo = o ? p - last : -p;
-		hi = o ? p : last - p;
-		const uint64_t base = m.word_off * 16ull + (uint64_t)p;
-		return make_uint2((uint32_t)base, (uint32_t)(base >> 32) | (o ? 0x80000000u : 0u));
+	__device__ __forceinline__ uint32_t ballot(bool p) const {
+		return GW == 32 ? __ballot_sync(0xffffffffu, p) : (__ballot_sync(gmask, p) & gmask) >> gshift;
 	}
+	__device__ __forceinline__ uint32_t shfl(uint32_t x, int src) const { return __shfl_sync(gmask, x, src, GW); }
+	__device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+	__device__ __forceinline__ int32_t group_max(int32_t x) const {
+		if constexpr (GW == 32) {
+			return __reduce_max_sync(0xffffffffu, x);
+		} else {
+#pragma unroll
+			for (int o = GW / 2; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(gmask, x, o, GW));
+			return x;
+		}
+	}
+	__device__ __forceinline__ int32_t group_min(int32_t x) const {
+		if constexpr (GW == 32) {
+			return __reduce_min_sync(0xffffffffu, x);
+		} else {
+#pragma unroll
+			for (int o = GW / 2; o > 0; o >>= 1) x = min(x, __shfl_xor_sync(gmask, x, o, GW));
+			return x;
+		}
+	}
+
+	__device__ uint2 member_entry(uint32_t j, int32_t& lo, int32_t& hi) const { return walk_member_entry<KeyT>(a, j, sf, lo, hi); }
 	__device__ void load_tile(uint32_t first) {
-		for (uint32_t t = lane; t < kMemberTile && first + t < len; t += 32) {
+		for (uint32_t t = lane; t < kTile && first + t < len; t += GW) {
 			int32_t lo, hi;
 			s_mem[t] = member_entry(s + first + t, lo, hi);
 		}
-		__syncwarp();
+		sync();
 	}
 	__device__ void init(uint32_t hit_s, uint32_t hit_len, uint32_t first_strand) {
 		s = hit_s;
@@ -684,20 +733,34 @@ struct WarpHit {
 		sf = first_strand;
 		int32_t lo = INT32_MIN, hi = INT32_MAX;
 		bool rev = false;
-		for (uint32_t t = lane; t < len; t += 32) {  // one pass: valid range and the first member tile together
+		for (uint32_t t = lane; t < len; t += GW) {  // one pass: valid range and the first member tile together
 			int32_t l2, h2;
 			const uint2 e = member_entry(s + t, l2, h2);
-			if (t < kMemberTile) s_mem[t] = e;
+			if (t < kTile) s_mem[t] = e;
 			rev |= (e.y >> 31) != 0u;
 			lo = max(lo, l2);
 			hi = min(hi, h2);
 		}
-		kmin = __reduce_max_sync(0xffffffffu, lo);
-		kmax = __reduce_min_sync(0xffffffffu, hi);
-		any_reverse = __any_sync(0xffffffffu, rev);
-		__syncwarp();
+		kmin = group_max(lo);
+		kmax = group_min(hi);
+		any_reverse = ballot(rev) != 0u;
+		sync();
 	}
-	// Probe the kProbeWindows windows at distances 1.. from k0 in direction dir (+1/-1): this lane's 32 windows are
+	// A segment staged by segment_stage_kernel: members, valid range and orientations are already known.
+	__device__ void adopt(const uint2* __restrict__ staged, uint32_t hit_s, uint32_t hit_len, uint32_t first_strand, int32_t lo,
+	                      int32_t hi, bool rev, bool members_in_place) {
+		s = hit_s;
+		len = hit_len;
+		sf = first_strand;
+		kmin = lo;
+		kmax = hi;
+		any_reverse = rev;
+		if (!members_in_place) {
+			for (uint32_t t = lane; t < len; t += GW) s_mem[t] = staged[t];
+			sync();
+		}
+	}
+	// Probe the kWindows windows at distances 1.. from k0 in direction dir (+1/-1): this lane's 32 windows are
 	// the distances 32*lane + 1 .. 32*lane + 32, bit j of the result = distance 32*lane + j + 1 matches.
 	__device__ uint32_t probe(int32_t k0, int dir) {
 #ifdef MEMS_WALK_STATS
@@ -712,7 +775,7 @@ struct WarpHit {
 			if (j0 <= j1) m = (0xffffffffu >> (31 - j1)) & (0xffffffffu << j0);
 		}
 		const bool live = m != 0u;  // lanes without a valid window load nothing (their addresses may lie outside the buffer)
-		if (!__any_sync(0xffffffffu, live)) return 0u;
+		if (!ballot(live)) return 0u;
 		// Every member is read in the orientation of the hit's first member: members of the other orientation load the
 		// mirrored chunk and reverse it (the complement is folded into the XOR).  The reference the others are compared
 		// with is simply the first union entry, whichever orientation it has; cared base i of a window sits at offset
@@ -727,9 +790,9 @@ struct WarpHit {
 			ref = ref_rev ? reverse_chunk(load_chunk(a.planes, base0 - klo + (L - 1) - 63)) : load_chunk(a.planes, base0 + klo);
 		}
 		uint32_t d0 = 0, d1 = 0;  // disagreement per base of the chunk, all members
-		for (uint32_t first = 0; first < len; first += kMemberTile) {
+		for (uint32_t first = 0; first < len; first += kTile) {
 			if (first) load_tile(first);
-			const uint32_t cnt = len - first < kMemberTile ? len - first : kMemberTile;
+			const uint32_t cnt = len - first < kTile ? len - first : kTile;
 			for (uint32_t t = first ? 0u : 1u; t < cnt; ++t) {
 				const uint2 e = s_mem[t];
 				const int64_t base = (int64_t)(((uint64_t)(e.y & 0x7fffffffu) << 32) | e.x);
@@ -753,9 +816,9 @@ struct WarpHit {
 					}
 				}
 			}
-			if (len > kMemberTile) __syncwarp();
+			if (len > kTile) sync();
 		}
-		if (len > kMemberTile) load_tile(0);
+		if (len > kTile) load_tile(0);
 		const uint32_t ok0 = ~d0, ok1 = ~d1;
 		for (int i = 0; i < w; ++i) m &= __funnelshift_r(ok0, ok1, ref_off[i]);
 		if (any_reverse && !(w & 1)) {
@@ -773,22 +836,22 @@ struct WarpHit {
 	}
 	// distance (1-based) of the highest / lowest set bit over the warp's words, 0 if none
 	__device__ int highest_set(uint32_t m) const {
-		const uint32_t b = __ballot_sync(0xffffffffu, m != 0u);
+		const uint32_t b = ballot(m != 0u);
 		if (!b) return 0;
 		const int z = 31 - __clz((int)b);
-		return 32 * z + 32 - __clz((int)__shfl_sync(0xffffffffu, m, z));
+		return 32 * z + 32 - __clz((int)shfl(m, z));
 	}
 	__device__ int lowest_set(uint32_t m) const {
-		const uint32_t b = __ballot_sync(0xffffffffu, m != 0u);
+		const uint32_t b = ballot(m != 0u);
 		if (!b) return 0;
 		const int z = __ffs((int)b) - 1;
-		return 32 * z + __ffs((int)__shfl_sync(0xffffffffu, m, z));
+		return 32 * z + __ffs((int)shfl(m, z));
 	}
 	// Where a chain of matches at most L apart breaks inside one probe.  The chain starts at distance `from`
 	// (0 = the window the walk stands on, else a set bit of m); matches before `from` are ignored.  A distance d is
 	// "open" when none of the L windows before it (d-L .. d-1) matches; the chain's last match x is followed by L
 	// mismatches, so the first open distance after `from` is x + L + 1 (whether or not that window itself matches).
-	// Returns it (<= kProbeWindows: the gap then lies completely inside the probed windows), or 0 when the chain runs
+	// Returns it (<= kWindows: the gap then lies completely inside the probed windows), or 0 when the chain runs
 	// on to the end of the probe.  Lane-parallel: a lane smears its word and its predecessor's by 1..L bits.
 	__device__ int chain_break(uint32_t m, int from) const {
 		const int L = shape.L;
@@ -799,7 +862,7 @@ struct WarpHit {
 			if (lane < fl) cur = 0u;
 			else if (lane == fl) cur &= 0xffffffffu << fb;
 		}
-		uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
+		uint32_t prev = __shfl_up_sync(gmask, cur, 1, GW);
 		if (lane == 0) prev = from == 0 ? 0x80000000u : 0u;
 		// reach = bits of OR_{s = 1..L} ((cur:prev) << s) that fall into cur's word: shift by one, double, one more step
 		uint32_t hi = __funnelshift_l(prev, cur, 1), lo = prev << 1;
@@ -838,7 +901,7 @@ struct WarpHit {
 				return walked;
 			}
 			uint32_t m = probe(k0 + dir * walked, dir);
-			if (stop_dist >= 0 && stop_dist - walked <= kProbeWindows) {
+			if (stop_dist >= 0 && stop_dist - walked <= kWindows) {
 				// the next segment's first hit is a matching window of this diagonal: nothing beyond it matters
 				const int t = stop_dist - walked - 1, tl = t >> 5, tb = t & 31;
 				if (lane > tl) m = 0u;
@@ -854,9 +917,11 @@ struct WarpHit {
 		}
 	}
 };
+template <class KeyT>
+using WarpHit = WalkHit<KeyT, 32>;
 
 #ifdef MEMS_WALK_STATS
-__device__ unsigned long long g_walk_stats[16];  // [0] probes total, [1] max per walk, [2+i] walks with 2^i probes
+__device__ unsigned long long g_walk_stats[48];  // [0] probes total, [1] max per walk, [2+i] walks with 2^i probes
 #endif
 
 struct SegView {
@@ -874,62 +939,205 @@ struct SegView {
 // Right walk of every segment: from its last hit, follow matching windows until either the next segment of
 // the same diagonal is within reach (link = 1: the two are connected, its own walk continues from there) or
 // no window within L matches (link = 0: reach = last matching window, the component's right end).
+// A warp takes kGroupsPerWarp consecutive segments of the walk order: first every group of kGroupLanes lanes walks its
+// own segment (kGroupProbeBudget probes of 32 x kGroupLanes windows), then the whole warp finishes, one after the other,
+// the walks that are still going (and the hits with more members than a group stages).
+struct __align__(16) SegDesc {  // one segment as the walk kernels see it, staged in walk order by segment_stage_kernel
+	uint32_t seg, x0;    // x0: first-member position of the segment's first hit
+	uint32_t hit_start;  // union index of the first hit's members
+	uint32_t info;       // member count | kSeg* flags
+	int32_t c, next_at;  // last hit / first hit of the diagonal's next segment, as distances from x0
+	int32_t kmin, kmax;  // valid window offsets (staged segments)
+};
+constexpr uint32_t kSegLenMask = 0xffffu, kSegStrand = 1u << 16, kSegHasNext = 1u << 17, kSegFirstOfDiagonal = 1u << 18,
+                   kSegAnyReverse = 1u << 19, kSegStaged = 1u << 20;
+
+// Everything a walk needs of its segment sits at the end of a chain of dependent loads (walk order -> segment -> hit ->
+// union entries -> sequence table).  Followed by the walking warps themselves that chain is most of a short walk's
+// time; here 8 threads per segment follow it once, with the whole grid's parallelism to hide it, and leave a 32-byte
+// descriptor and the member entries (hits of <= kGroupMembers members) at the segment's slot of the walk order.
 template <class KeyT>
-__global__ void __launch_bounds__(kExtendWarps * 32)
-walk_right_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, uint32_t* __restrict__ seg_link,
-                  uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count,
-                  uint32_t* __restrict__ seg_left, uint8_t* __restrict__ seg_left_state, uint2* __restrict__ defer_left,
-                  uint32_t* __restrict__ defer_left_count) {
-	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
-	__shared__ SeedShape s_shape;
-	load_seed_shape(&s_shape, sd);
-	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
-	if (slot >= v.n_seg) return;
+__global__ void __launch_bounds__(256)
+segment_stage_kernel(MatchArgs a, SegView v, SegDesc* __restrict__ desc, uint2* __restrict__ members, uint32_t* __restrict__ slot_of_seg) {
+	const int sub = threadIdx.x & 7;
+	const uint32_t slot = (blockIdx.x * 256u + threadIdx.x) >> 3;
+	if (slot >= v.n_seg) return;  // whole groups leave
+	const uint32_t gmask = 0xffu << ((threadIdx.x & 31) & ~7);
 	const uint32_t seg = v.order[slot];  // segments are visited in order of genome position (L2 locality)
 	const uint32_t hi = v.seg_head[seg];
 	const uint32_t end = seg + 1 < v.n_seg ? v.seg_head[seg + 1] : v.n_hits;
 	const uint32_t h = v.hid[hi];
 	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-	WarpHit<KeyT> w{a, s_shape, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, false, (int)(threadIdx.x & 31)};
-	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
-	int32_t c = (int32_t)((int64_t)(v.hkey[end - 1] & a.pos_mask) - x0);
-	const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
-	const int32_t next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
-	bool linked, exhausted;
-	c += w.walk(c, +1, has_next ? next_at - c : -1, &linked, a.warp_budget, &exhausted);
-	if (exhausted) {  // hand the rest of this walk to a whole CTA (long_walk_kernel)
-		if (w.lane == 0) {
-			const uint32_t at = atomicAdd(defer_count, 1u);
-			defer[at] = make_uint2(seg, (uint32_t)(int32_t)c);
+	const uint32_t hit_start = v.hit_start[h], hl = v.hit_len[h];
+	const uint32_t len = hl & ~kFirstStrandBit, strand = (hl & kFirstStrandBit) ? 1u : 0u;
+	int32_t lo = INT32_MIN, hi_k = INT32_MAX;
+	bool rev = false;
+	const bool staged = len <= (uint32_t)kGroupMembers;
+	if (staged) {
+		for (uint32_t t = sub; t < len; t += 8) {
+			int32_t l2, h2;
+			const uint2 e = walk_member_entry<KeyT>(a, hit_start + t, strand, l2, h2);
+			members[(size_t)slot * kGroupMembers + t] = e;
+			rev |= (e.y >> 31) != 0u;
+			lo = max(lo, l2);
+			hi_k = min(hi_k, h2);
 		}
-		return;
+#pragma unroll
+		for (int o = 4; o > 0; o >>= 1) {
+			lo = max(lo, __shfl_xor_sync(gmask, lo, o, 8));
+			hi_k = min(hi_k, __shfl_xor_sync(gmask, hi_k, o, 8));
+		}
+		rev = (__ballot_sync(gmask, rev) & gmask) != 0u;
 	}
-	const uint32_t link = linked ? 1u : 0u;
+	if (sub == 0) {
+		const bool has_next = seg + 1 < v.n_seg && (v.flags[end] & kFlagSameDiag);
+		SegDesc d;
+		d.seg = seg;
+		d.x0 = (uint32_t)x0;
+		d.hit_start = hit_start;
+		d.info = len | (strand ? kSegStrand : 0u) | (has_next ? kSegHasNext : 0u) | ((v.flags[hi] & kFlagSameDiag) ? 0u : kSegFirstOfDiagonal) |
+		         (rev ? kSegAnyReverse : 0u) | (staged ? kSegStaged : 0u);
+		d.c = (int32_t)((int64_t)(v.hkey[end - 1] & a.pos_mask) - x0);
+		d.next_at = has_next ? (int32_t)((int64_t)(v.hkey[end] & a.pos_mask) - x0) : 0;
+		d.kmin = lo;
+		d.kmax = hi_k;
+		desc[slot] = d;
+		slot_of_seg[seg] = slot;
+	}
+}
+
+__device__ __forceinline__ SegDesc load_seg_desc(const SegDesc* __restrict__ p) {
+	const uint4 q0 = reinterpret_cast<const uint4*>(p)[0], q1 = reinterpret_cast<const uint4*>(p)[1];
+	SegDesc d;
+	d.seg = q0.x; d.x0 = q0.y; d.hit_start = q0.z; d.info = q0.w;
+	d.c = (int32_t)q1.x; d.next_at = (int32_t)q1.y; d.kmin = (int32_t)q1.z; d.kmax = (int32_t)q1.w;
+	return d;
+}
+__device__ __forceinline__ SegDesc broadcast_seg_desc(const SegDesc& w, int src) {
+	SegDesc r;
+	r.seg = __shfl_sync(0xffffffffu, w.seg, src);
+	r.x0 = __shfl_sync(0xffffffffu, w.x0, src);
+	r.hit_start = __shfl_sync(0xffffffffu, w.hit_start, src);
+	r.info = __shfl_sync(0xffffffffu, w.info, src);
+	r.c = __shfl_sync(0xffffffffu, w.c, src);
+	r.next_at = __shfl_sync(0xffffffffu, w.next_at, src);
+	r.kmin = __shfl_sync(0xffffffffu, w.kmin, src);
+	r.kmax = __shfl_sync(0xffffffffu, w.kmax, src);
+	return r;
+}
+// the whole warp takes over a segment one of its groups staged in shared memory (or sets a long hit up from scratch)
+template <class KeyT>
+__device__ __forceinline__ void warp_adopt(WarpHit<KeyT>& w, const SegDesc& d, uint2* group_mem, uint2* wide_mem) {
+	const uint32_t len = d.info & kSegLenMask;
+	if (d.info & kSegStaged) {
+		w.s_mem = group_mem;
+		w.adopt(nullptr, d.hit_start, len, (d.info & kSegStrand) ? 1u : 0u, d.kmin, d.kmax, (d.info & kSegAnyReverse) != 0u, true);
+	} else {
+		w.s_mem = wide_mem;
+		w.init(d.hit_start, len, (d.info & kSegStrand) ? 1u : 0u);
+	}
+}
+constexpr uint32_t kNeedRight = 1u, kNeedLeft = 2u;
+
+template <class KeyT>
+__global__ void __launch_bounds__(kExtendWarps * 32)
+walk_right_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const SegDesc* __restrict__ desc,
+                  const uint2* __restrict__ members, uint32_t* __restrict__ seg_link,
+                  uint32_t* __restrict__ seg_reach, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count,
+                  uint32_t* __restrict__ seg_left, uint8_t* __restrict__ seg_left_state, uint2* __restrict__ defer_left,
+                  uint32_t* __restrict__ defer_left_count) {
+	__shared__ uint2 s_mem[kExtendWarps][kGroupsPerWarp * kGroupMembers], s_wide[kExtendWarps][kMemberTile];
+	__shared__ SeedShape s_shape;
+	load_seed_shape(&s_shape, sd);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / kGroupLanes, gl = lane % kGroupLanes;
+	const uint32_t slot = (blockIdx.x * kExtendWarps + warp) * kGroupsPerWarp + grp;
+	if (slot - grp >= v.n_seg) return;  // warp-uniform
+	SegDesc d{};
+	uint32_t need = 0;
+	int32_t cl = 0;  // left walk so far
+	if (slot < v.n_seg) {
+		d = load_seg_desc(desc + slot);
+		need = kNeedRight | ((d.info & kSegFirstOfDiagonal) ? kNeedLeft : 0u);
+		if (d.info & kSegStaged) {
+			WalkHit<KeyT, kGroupLanes> g{a, s_shape, s_mem[warp] + grp * kGroupMembers, 0, 0, 0, 0, 0, false, gl,
+			                             kGroupLanes == 32 ? 0xffffffffu : ((1u << kGroupLanes) - 1u) << (grp * kGroupLanes), grp * kGroupLanes};
+			g.adopt(members + (size_t)slot * kGroupMembers, d.hit_start, d.info & kSegLenMask, (d.info & kSegStrand) ? 1u : 0u, d.kmin,
+			        d.kmax, (d.info & kSegAnyReverse) != 0u, false);
+			bool linked, exhausted;
 #ifdef MEMS_WALK_STATS
-	if (w.lane == 0) {
-		atomicAdd(&g_walk_stats[0], (unsigned long long)w.n_probes);
-		atomicMax(&g_walk_stats[1], (unsigned long long)w.n_probes);
-		atomicAdd(&g_walk_stats[2 + min(31 - __clz(w.n_probes | 1), 13)], 1ull);
-	}
+			const int32_t c_start = d.c;
 #endif
-	if (w.lane == 0) {
-		seg_link[seg] = link;
-		seg_reach[seg] = (uint32_t)(x0 + c);
+			d.c += g.walk(d.c, +1, (d.info & kSegHasNext) ? d.next_at - d.c : -1, &linked, kGroupProbeBudget, &exhausted);
+#ifdef MEMS_WALK_STATS
+			if (gl == 0 && !exhausted) atomicAdd(&g_walk_stats[16 + (linked ? 0 : 16) + min(31 - __clz((d.c - c_start) | 1), 15)], 1ull);
+#endif
+			if (!exhausted) {
+				need &= ~kNeedRight;
+				if (gl == 0) {
+					seg_link[d.seg] = linked ? 1u : 0u;
+					seg_reach[d.seg] = d.x0 + (uint32_t)d.c;
+				}
+			}
+			// The first segment of a DIAGONAL certainly starts a component (nothing on its diagonal can link to it), and its
+			// members are already staged: walk left right away instead of setting all of this up again in walk_left_kernel.
+			if (need & kNeedLeft) {
+				bool l2, ex2;
+				cl = -g.walk(0, -1, -1, &l2, kGroupProbeBudget, &ex2);
+				if (!ex2) {
+					need &= ~kNeedLeft;
+					if (gl == 0) {
+						seg_left[d.seg] = d.x0 + (uint32_t)cl;
+						seg_left_state[d.seg] = 1;
+					}
+				}
+			}
+#ifdef MEMS_WALK_STATS
+			if (gl == 0) {
+				atomicAdd(&g_walk_stats[0], (unsigned long long)g.n_probes);
+				atomicAdd(&g_walk_stats[2 + min(31 - __clz(g.n_probes | 1), 5)], 1ull);
+				if (need & kNeedRight) atomicAdd(&g_walk_stats[8], 1ull);
+				if (need & kNeedLeft) atomicAdd(&g_walk_stats[9], 1ull);
+			}
+#endif
+		}
 	}
-	// The first segment of a DIAGONAL certainly starts a component (nothing on its diagonal can link to it), and its
-	// members are already staged: walk left right away instead of setting all of this up again in walk_left_kernel.
-	if (!(v.flags[hi] & kFlagSameDiag)) {
-		bool l2, ex2;
-		const int32_t cl = -w.walk(0, -1, -1, &l2, a.warp_budget, &ex2);
-		if (w.lane == 0) {
-			if (ex2) {
-				defer_left[atomicAdd(defer_left_count, 1u)] = make_uint2(seg, (uint32_t)cl);
-				seg_left_state[seg] = 2;  // handed to the CTA-wide walker
-			} else {
-				seg_left[seg] = (uint32_t)(x0 + cl);
-				seg_left_state[seg] = 1;
+	__syncwarp();
+	// ---- the walks that go on: the whole warp, one segment at a time
+	uint32_t todo = __ballot_sync(0xffffffffu, need != 0u && gl == 0);
+	while (todo) {
+		const int src = __ffs((int)todo) - 1;
+		todo &= todo - 1u;
+		SegDesc b = broadcast_seg_desc(d, src);
+		const uint32_t b_need = __shfl_sync(0xffffffffu, need, src);
+		int32_t b_cl = __shfl_sync(0xffffffffu, cl, src);
+		WarpHit<KeyT> w{a, s_shape, nullptr, 0, 0, 0, 0, 0, false, lane};
+		warp_adopt<KeyT>(w, b, s_mem[warp] + (src / kGroupLanes) * kGroupMembers, s_wide[warp]);
+		if (b_need & kNeedRight) {
+			bool linked, exhausted;
+			b.c += w.walk(b.c, +1, (b.info & kSegHasNext) ? b.next_at - b.c : -1, &linked, a.warp_budget, &exhausted);
+			if (lane == 0) {
+				if (exhausted) {  // hand the rest of this walk to a whole CTA (long_walk_kernel)
+					defer[atomicAdd(defer_count, 1u)] = make_uint2(b.seg, (uint32_t)b.c);
+				} else {
+					seg_link[b.seg] = linked ? 1u : 0u;
+					seg_reach[b.seg] = b.x0 + (uint32_t)b.c;
+				}
 			}
 		}
+		if (b_need & kNeedLeft) {
+			bool l2, ex2;
+			b_cl -= w.walk(b_cl, -1, -1, &l2, a.warp_budget, &ex2);
+			if (lane == 0) {
+				if (ex2) {
+					defer_left[atomicAdd(defer_left_count, 1u)] = make_uint2(b.seg, (uint32_t)b_cl);
+					seg_left_state[b.seg] = 2;  // handed to the CTA-wide walker
+				} else {
+					seg_left[b.seg] = b.x0 + (uint32_t)b_cl;
+					seg_left_state[b.seg] = 1;
+				}
+			}
+		}
+		__syncwarp();  // s_wide is rewritten by the next segment
 	}
 }
 
@@ -946,7 +1154,8 @@ __global__ void finish_segments_kernel(SegView v, const uint32_t* __restrict__ s
                                        const uint32_t* __restrict__ seg_left, const uint8_t* __restrict__ seg_left_state,
                                        uint32_t* __restrict__ comp_rep, uint32_t* __restrict__ comp_left,
                                        uint32_t* __restrict__ comp_right, uint8_t* __restrict__ comp_suspect,
-                                       uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count) {
+                                       const uint32_t* __restrict__ slot_of_seg, uint32_t* __restrict__ todo,
+                                       uint32_t* __restrict__ todo_count) {
 	const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
 	if (seg >= v.n_seg) return;
 	const bool is_first = first[seg] != 0;
@@ -958,38 +1167,61 @@ __global__ void finish_segments_kernel(SegView v, const uint32_t* __restrict__ s
 	comp_rep[comp] = e0;
 	const uint8_t done = seg_left_state[seg];
 	if (done == 1) comp_left[comp] = seg_left[seg];
-	else if (done == 0) todo[atomicAdd(todo_count, 1u)] = seg;  // (2: already with the CTA-wide walker)
+	else if (done == 0) todo[atomicAdd(todo_count, 1u)] = slot_of_seg[seg];  // (2: already with the CTA-wide walker)
 }
 
-// Left walk of the listed first segments.
+// Left walk of the listed first segments (slots of the walk order; groups first, then the whole warp, as in
+// walk_right_kernel).
 template <class KeyT>
 __global__ void __launch_bounds__(kExtendWarps * 32)
-walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, SegView v, const uint32_t* __restrict__ todo,
+walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, const SegDesc* __restrict__ desc,
+                 const uint2* __restrict__ members, const uint32_t* __restrict__ todo_list,
                  const uint32_t* __restrict__ todo_count, const uint32_t* __restrict__ first_excl,
                  uint32_t* __restrict__ comp_left, uint2* __restrict__ defer, uint32_t* __restrict__ defer_count) {
-	__shared__ uint2 s_mem[kExtendWarps][kMemberTile];
+	__shared__ uint2 s_mem[kExtendWarps][kGroupsPerWarp * kGroupMembers], s_wide[kExtendWarps][kMemberTile];
 	__shared__ SeedShape s_shape;
 	load_seed_shape(&s_shape, sd);
-	const uint32_t slot = blockIdx.x * kExtendWarps + (threadIdx.x >> 5);
-	if (slot >= *todo_count) return;
-	const uint32_t seg = todo[slot];
-	const int lane = threadIdx.x & 31;
-	const uint32_t comp = first_excl[seg];
-	const uint32_t hi = v.seg_head[seg];
-	const uint32_t h = v.hid[hi];
-	const int64_t x0 = (int64_t)(v.hkey[hi] & a.pos_mask);
-	WarpHit<KeyT> w{a, s_shape, s_mem[threadIdx.x >> 5], 0, 0, 0, 0, 0, false, lane};
-	w.init(v.hit_start[h], v.hit_len[h] & ~kFirstStrandBit, (v.hit_len[h] & kFirstStrandBit) ? 1u : 0u);
-	bool linked, exhausted;
-	const int32_t c = -w.walk(0, -1, -1, &linked, a.warp_budget, &exhausted);
-	if (exhausted) {
-		if (lane == 0) {
-			const uint32_t at = atomicAdd(defer_count, 1u);
-			defer[at] = make_uint2(seg, (uint32_t)(int32_t)c);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / kGroupLanes, gl = lane % kGroupLanes;
+	const uint32_t item = (blockIdx.x * kExtendWarps + warp) * kGroupsPerWarp + grp;
+	const uint32_t n_todo = *todo_count;
+	if (item - grp >= n_todo) return;  // warp-uniform
+	SegDesc d{};
+	uint32_t need = 0;
+	int32_t cl = 0;
+	if (item < n_todo) {
+		const uint32_t slot = todo_list[item];
+		d = load_seg_desc(desc + slot);
+		need = 1;
+		if (d.info & kSegStaged) {
+			WalkHit<KeyT, kGroupLanes> g{a, s_shape, s_mem[warp] + grp * kGroupMembers, 0, 0, 0, 0, 0, false, gl,
+			                             kGroupLanes == 32 ? 0xffffffffu : ((1u << kGroupLanes) - 1u) << (grp * kGroupLanes), grp * kGroupLanes};
+			g.adopt(members + (size_t)slot * kGroupMembers, d.hit_start, d.info & kSegLenMask, (d.info & kSegStrand) ? 1u : 0u, d.kmin,
+			        d.kmax, (d.info & kSegAnyReverse) != 0u, false);
+			bool linked, exhausted;
+			cl = -g.walk(0, -1, -1, &linked, kGroupProbeBudget, &exhausted);
+			if (!exhausted) {
+				need = 0;
+				if (gl == 0) comp_left[first_excl[d.seg]] = d.x0 + (uint32_t)cl;
+			}
 		}
-		return;
 	}
-	if (lane == 0) comp_left[comp] = (uint32_t)(x0 + c);
+	__syncwarp();
+	uint32_t todo = __ballot_sync(0xffffffffu, need != 0u && gl == 0);
+	while (todo) {
+		const int src = __ffs((int)todo) - 1;
+		todo &= todo - 1u;
+		const SegDesc b = broadcast_seg_desc(d, src);
+		int32_t b_cl = __shfl_sync(0xffffffffu, cl, src);
+		WarpHit<KeyT> w{a, s_shape, nullptr, 0, 0, 0, 0, 0, false, lane};
+		warp_adopt<KeyT>(w, b, s_mem[warp] + (src / kGroupLanes) * kGroupMembers, s_wide[warp]);
+		bool linked, exhausted;
+		b_cl -= w.walk(b_cl, -1, -1, &linked, a.warp_budget, &exhausted);
+		if (lane == 0) {
+			if (exhausted) defer[atomicAdd(defer_count, 1u)] = make_uint2(b.seg, (uint32_t)b_cl);
+			else comp_left[first_excl[b.seg]] = b.x0 + (uint32_t)b_cl;
+		}
+		__syncwarp();
+	}
 }
 
 // ---- long walks -------------------------------------------------------------------------------------
@@ -1721,10 +1953,19 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		MEMS_CUDA(cudaLaunchCooperativeKernel((void*)giant_walk_kernel<KeyT>, dim3(giant_grid), dim3(kLongWarps * 32), args, 0,
 		                                      c->stream));
 	};
-	const uint32_t walk_blocks = (n_seg + kExtendWarps - 1) / kExtendWarps, seg_blocks = (n_seg + 255) / 256;
+	constexpr uint32_t kSegsPerWalkBlock = kExtendWarps * kGroupsPerWarp;
+	const uint32_t walk_blocks = (n_seg + kSegsPerWalkBlock - 1) / kSegsPerWalkBlock, seg_blocks = (n_seg + 255) / 256;
+	DevBuf<SegDesc> seg_desc(c, n_seg);
+	DevBuf<uint2> seg_members(c, (size_t)n_seg * kGroupMembers);
+	DevBuf<uint32_t> slot_of_seg(c, n_seg);
+	{
+		KernelScope ks(c, "segment_stage");
+		segment_stage_kernel<KeyT><<<(n_seg + 31) / 32, 256, 0, c->stream>>>(a, v, seg_desc.p, seg_members.p, slot_of_seg.p);
+		MEMS_CUDA(cudaGetLastError());
+	}
 	{
 		KernelScope ks(c, "walk_right");
-		walk_right_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(a, sd, v, seg_link.p, seg_reach.p,
+		walk_right_kernel<KeyT><<<walk_blocks, kExtendWarps * 32, 0, c->stream>>>(a, sd, v, seg_desc.p, seg_members.p, seg_link.p, seg_reach.p,
 		                                                                          defer.p, defer_count, seg_left.p, seg_left_state.p,
 		                                                                          defer_left.p, defer_count + 1);
 		MEMS_CUDA(cudaGetLastError());
@@ -1743,10 +1984,14 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	}
 #ifdef MEMS_WALK_STATS
 	{
-		unsigned long long st[16];
+		unsigned long long st[48];
 		MEMS_CUDA(cudaMemcpyFromSymbol(st, g_walk_stats, sizeof st));
-		fprintf(stderr, "walk_right: n_seg=%u probes=%llu max=%llu hist:", n_seg, st[0], st[1]);
-		for (int i = 2; i < 16; ++i) fprintf(stderr, " %llu", st[i]);
+		fprintf(stderr, "walk_right (group phase): n_seg=%u probes=%llu; to the warp: right %llu left %llu; walks by log2(probes):", n_seg, st[0], st[8], st[9]);
+		for (int i = 2; i < 8; ++i) fprintf(stderr, " %llu", st[i]);
+		fprintf(stderr, "\n  finished by a group, by log2(distance): linked");
+		for (int i = 16; i < 32; ++i) fprintf(stderr, " %llu", st[i]);
+		fprintf(stderr, "\n  ended");
+		for (int i = 32; i < 48; ++i) fprintf(stderr, " %llu", st[i]);
 		fprintf(stderr, "\n");
 		memset(st, 0, sizeof st);
 		MEMS_CUDA(cudaMemcpyToSymbol(g_walk_stats, st, sizeof st));
@@ -1768,13 +2013,13 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		KernelScope ks(c, "finish_segments");
 		finish_segments_kernel<<<seg_blocks, 256, 0, c->stream>>>(v, seg_link.p, seg_reach.p, first.p, first_excl.p, seg_left.p,
 		                                                          seg_left_state.p, comp_rep.p, comp_left.p, comp_right.p,
-		                                                          comp_suspect.p, left_todo.p, left_todo_count.p);
+		                                                          comp_suspect.p, slot_of_seg.p, left_todo.p, left_todo_count.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{
 		KernelScope ks(c, "walk_left");  // at most one listed segment per component: warps past the list's end leave at once
-		walk_left_kernel<KeyT><<<(n_comp + kExtendWarps - 1) / kExtendWarps, kExtendWarps * 32, 0, c->stream>>>(
-		    a, sd, v, left_todo.p, left_todo_count.p, first_excl.p, comp_left.p, defer_left.p, defer_count + 1);
+		walk_left_kernel<KeyT><<<(n_comp + kSegsPerWalkBlock - 1) / kSegsPerWalkBlock, kExtendWarps * 32, 0, c->stream>>>(
+		    a, sd, seg_desc.p, seg_members.p, left_todo.p, left_todo_count.p, first_excl.p, comp_left.p, defer_left.p, defer_count + 1);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	{

@@ -19,6 +19,7 @@
 //      buffers, or (PEER) into per-digit destinations that may be other GPUs' exchange windows.
 // Tiles take their index from an atomic ticket, which guarantees that all predecessors of a running
 // tile are themselves running or finished (forward progress of the look-back).
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -399,71 +400,110 @@ void launch_histogram(Ctx* c, bool key64, const void* d_keys, uint64_t n, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// exclusive scan (used for stream compaction of hits / segments / output records)
+// exclusive scan (stream compaction of hits / segments / output records): ONE launch per scan.
+// Chained tiles with decoupled look-back: a tile publishes its sum, warp 0 polls 32 predecessors at a time until it
+// meets an inclusive prefix.  The tile states live in a buffer the context keeps across calls; every scan stamps its
+// states with a fresh epoch, so stale words of earlier scans read as "not ready" and nothing has to be zeroed, and tiles
+// take their index from a ticket counter whose start value the host tracks (predecessors of a running tile are
+// themselves running or done).  The three-kernel form this replaces (reduce / scan the sums / apply) cost 3-5
+// launches per scan, 12 of the ~50 launches of a match-finding call.
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr uint64_t kScanPartial = 1ull << 32, kScanInclusive = 2ull << 32;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_tot, uint32_t* total) {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t incl = v;
+__device__ __forceinline__ uint64_t ld_state(const uint64_t* p) {
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_state(uint64_t* p, uint64_t v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_chained_kernel(const uint32_t* in, uint32_t* out, uint64_t n,  // in may alias out (in-place scan)
+                    uint64_t* state, uint32_t ticket_base, uint32_t epoch, uint32_t* total_out) {
+	__shared__ uint32_t s_tot[kScanThreads / 32];
+	__shared__ uint32_t s_tile, s_excl;
+	const int tid = threadIdx.x, lane = tid & 31;
+	if (tid == 0) s_tile = atomicAdd(reinterpret_cast<uint32_t*>(state), 1u) - ticket_base;
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	uint64_t* status = state + 1;
+	const uint64_t stamp = (uint64_t)epoch << 34;
+	const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)tid * kScanItems;  // blocked: a thread owns 16 in a row
+	uint32_t v[kScanItems];
+	if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+#pragma unroll
+		for (int k = 0; k < kScanItems; k += 4) {
+			const uint4 q = *reinterpret_cast<const uint4*>(in + base + k);
+			v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < kScanItems; ++k) v[k] = base + k < n ? in[base + k] : 0u;
+	}
+	uint32_t sum = 0;
+#pragma unroll
+	for (int k = 0; k < kScanItems; ++k) sum += v[k];
+	// block-wide exclusive scan of the thread sums
+	uint32_t incl = sum;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
 		if (lane >= o) incl += t;
 	}
-	if (lane == 31) s_tot[warp] = incl;
+	if (lane == 31) s_tot[tid >> 5] = incl;
 	__syncthreads();
 	uint32_t woff = 0, tot = 0;
 #pragma unroll
 	for (int w = 0; w < kScanThreads / 32; ++w) {
-		uint32_t t = s_tot[w];
-		if (w < warp) woff += t;
+		const uint32_t t = s_tot[w];
+		if (w < (tid >> 5)) woff += t;
 		tot += t;
 	}
-	*total = tot;
+	if (tid < 32) {  // warp 0: publish, look back
+		if (lane == 0) st_state(status + tile, stamp | (tile == 0 ? kScanInclusive : kScanPartial) | tot);
+		uint32_t excl = 0;
+		if (tile != 0) {
+			int64_t look = (int64_t)tile - 1;
+			for (;;) {
+				const int64_t idx = look - lane;
+				const uint64_t s = idx >= 0 ? ld_state(status + idx) : (stamp | kScanInclusive);
+				const uint32_t flag = (s >> 34) == (uint64_t)epoch ? (uint32_t)(s >> 32) & 3u : 0u;
+				const uint32_t ready = __ballot_sync(0xffffffffu, flag != 0u);
+				const uint32_t inclusive = __ballot_sync(0xffffffffu, flag == 2u);
+				const uint32_t need = inclusive ? (2u << (__ffs((int)inclusive) - 1)) - 1u : 0xffffffffu;  // lanes up to the first inclusive
+				if ((ready & need) != need) continue;  // a predecessor in reach has not published yet: poll again
+				excl += __reduce_add_sync(0xffffffffu, (need >> lane) & 1u ? (uint32_t)s : 0u);
+				if (inclusive) break;
+				look -= 32;
+			}
+			if (lane == 0) st_state(status + tile, stamp | kScanInclusive | (uint64_t)(uint32_t)(excl + tot));
+		}
+		if (lane == 0) s_excl = excl;
+	}
 	__syncthreads();
-	return woff + incl - v;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ partial) {
-	__shared__ uint32_t s_tot[kScanThreads / 32];
-	uint64_t base = (uint64_t)blockIdx.x * kScanTile;
-	uint32_t sum = 0;
+	uint32_t off = s_excl + woff + incl - sum;
+	if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
 #pragma unroll
-	for (int k = 0; k < kScanItems; ++k) {
-		uint64_t i = base + (uint64_t)k * kScanThreads + threadIdx.x;
-		if (i < n) sum += in[i];
-	}
-	uint32_t tot;
-	block_exclusive_scan(sum, s_tot, &tot);
-	if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-scan_apply_kernel(const uint32_t* in, uint32_t* out, uint64_t n,  // in may alias out (in-place scan)
-                  const uint32_t* partial_excl, uint32_t* total_out) {
-	__shared__ uint32_t s_tot[kScanThreads / 32];
-	uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;  // blocked: thread owns 8 in a row
-	uint32_t v[kScanItems];
-	uint32_t sum = 0;
+		for (int k = 0; k < kScanItems; k += 4) {
+			uint4 q;
+			q.x = off; off += v[k];
+			q.y = off; off += v[k + 1];
+			q.z = off; off += v[k + 2];
+			q.w = off; off += v[k + 3];
+			*reinterpret_cast<uint4*>(out + base + k) = q;
+		}
+	} else {
 #pragma unroll
-	for (int k = 0; k < kScanItems; ++k) {
-		uint64_t i = base + k;
-		v[k] = i < n ? in[i] : 0u;
-		sum += v[k];
+		for (int k = 0; k < kScanItems; ++k) {
+			if (base + k < n) out[base + k] = off;
+			off += v[k];
+		}
 	}
-	uint32_t tot;
-	uint32_t excl = block_exclusive_scan(sum, s_tot, &tot);
-	uint32_t off = (partial_excl ? partial_excl[blockIdx.x] : 0u) + excl;
-#pragma unroll
-	for (int k = 0; k < kScanItems; ++k) {
-		uint64_t i = base + k;
-		if (i < n) out[i] = off;
-		off += v[k];
-	}
-	if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = off;
+	if (total_out && tid == kScanThreads - 1 && (uint64_t)(tile + 1) * kScanTile >= n) *total_out = off;
 }
 
 void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n, uint32_t* d_total) {
@@ -471,25 +511,23 @@ void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t 
 		if (d_total) MEMS_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint32_t), c->stream));
 		return;
 	}
-	uint64_t n_blocks = (n + kScanTile - 1) / kScanTile;
-	if (n_blocks == 1) {
-		KernelScope ks(c, "scan");
-		scan_apply_kernel<<<1, kScanThreads, 0, c->stream>>>(d_in, d_out, n, nullptr, d_total);
-		MEMS_CUDA(cudaGetLastError());
-		return;
+	const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+	if (n_tiles + 1 > c->scan_cap || c->scan_epoch >= (1u << 30) - 1u) {  // (re)create the tile states: zero = no epoch
+		const size_t cap = std::max<size_t>(n_tiles + 1, std::max<size_t>(c->scan_cap, 1u << 16));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		if (c->scan_state) cudaFree(c->scan_state);
+		c->scan_state = nullptr;
+		MEMS_CUDA(cudaMalloc((void**)&c->scan_state, cap * sizeof(uint64_t)));
+		MEMS_CUDA(cudaMemsetAsync(c->scan_state, 0, cap * sizeof(uint64_t), c->stream));
+		c->scan_cap = cap;
+		c->scan_epoch = 0;
+		c->scan_ticket_base = 0;
 	}
-	DevBuf<uint32_t> partial(c, n_blocks);
-	{
-		KernelScope ks(c, "scan");
-		scan_reduce_kernel<<<(unsigned)n_blocks, kScanThreads, 0, c->stream>>>(d_in, n, partial.p);
-		MEMS_CUDA(cudaGetLastError());
-	}
-	exclusive_scan_u32(c, partial.p, partial.p, n_blocks, nullptr);
-	{
-		KernelScope ks(c, "scan");
-		scan_apply_kernel<<<(unsigned)n_blocks, kScanThreads, 0, c->stream>>>(d_in, d_out, n, partial.p, d_total);
-		MEMS_CUDA(cudaGetLastError());
-	}
+	KernelScope ks(c, "scan");
+	scan_chained_kernel<<<(unsigned)n_tiles, kScanThreads, 0, c->stream>>>(d_in, d_out, n, c->scan_state, c->scan_ticket_base,
+	                                                                        ++c->scan_epoch, d_total);
+	MEMS_CUDA(cudaGetLastError());
+	c->scan_ticket_base += (uint32_t)n_tiles;
 }
 
 }  // namespace mems
