@@ -2692,19 +2692,22 @@ pack_hits_kernel(MatchArgs a, const uint32_t* __restrict__ hid, const uint32_t* 
 		off = mem_off[i];
 		out_len[i] = l;
 	}
-	// (lanes past n_hits hold len = 0: their turns copy nothing)  Eight hits' first 32 members are in flight at a time —
-	// one hit per turn would leave the warp waiting for a single dependent load — the rare longer lists follow.
-#pragma unroll 8
-	for (uint32_t k = 0; k < 32; ++k) {
-		const uint32_t sk = __shfl_sync(0xffffffffu, s, k), lk = __shfl_sync(0xffffffffu, len, k);
-		const uint32_t ok = __shfl_sync(0xffffffffu, off, k);
-		if (lane < lk) out_mem[ok + lane] = a.vals[sk + lane] | (strand_of<KeyT>(a.keys, sk + lane) << 31);
+	// (lanes past n_hits hold len = 0: their turns copy nothing)  Four hits per turn, eight lanes each (most hits have at
+	// most eight members), all eight turns' loads in flight at once; the rare longer lists follow in the same shape.
+	const uint32_t sub = lane & 7u, grp = lane >> 3;
+#pragma unroll
+	for (uint32_t k = 0; k < 8; ++k) {
+		const uint32_t src = k * 4u + grp;
+		const uint32_t sk = __shfl_sync(0xffffffffu, s, src), lk = __shfl_sync(0xffffffffu, len, src);
+		const uint32_t ok = __shfl_sync(0xffffffffu, off, src);
+		if (sub < lk) out_mem[ok + sub] = a.vals[sk + sub] | (strand_of<KeyT>(a.keys, sk + sub) << 31);
 	}
-	if (__any_sync(0xffffffffu, len > 32u)) {
-		for (uint32_t k = 0; k < 32; ++k) {
-			const uint32_t sk = __shfl_sync(0xffffffffu, s, k), lk = __shfl_sync(0xffffffffu, len, k);
-			const uint32_t ok = __shfl_sync(0xffffffffu, off, k);
-			for (uint32_t t = 32 + lane; t < lk; t += 32) out_mem[ok + t] = a.vals[sk + t] | (strand_of<KeyT>(a.keys, sk + t) << 31);
+	if (__any_sync(0xffffffffu, len > 8u)) {
+		for (uint32_t k = 0; k < 8; ++k) {
+			const uint32_t src = k * 4u + grp;
+			const uint32_t sk = __shfl_sync(0xffffffffu, s, src), lk = __shfl_sync(0xffffffffu, len, src);
+			const uint32_t ok = __shfl_sync(0xffffffffu, off, src);
+			for (uint32_t t = 8u + sub; t < lk; t += 8u) out_mem[ok + t] = a.vals[sk + t] | (strand_of<KeyT>(a.keys, sk + t) << 31);
 		}
 	}
 }
