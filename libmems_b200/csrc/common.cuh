@@ -236,6 +236,52 @@ void launch_histogram(Ctx* c, bool key64, const void* d_keys, uint64_t n, const 
 // exclusive prefix sum of n u32 values (in -> out, may alias); *d_total (optional, device) gets the sum
 void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n, uint32_t* d_total);
 
+// Chained tiles with decoupled look-back (the scans, the run/hit kernel): the tile states live in Ctx::scan_state and are
+// stamped with an epoch per launch, so nothing is zeroed between launches; tiles take their index from the ticket counter
+// in state[0], whose start value the host tracks.
+struct ChainTicket {
+	uint64_t* state;  // [0] ticket counter, [1 + tile] status word: epoch << 34 | flag << 32 | value
+	uint32_t ticket_base, epoch;
+};
+ChainTicket reserve_chain_tiles(Ctx* c, uint64_t n_tiles);
+#ifdef __CUDACC__
+constexpr uint64_t kScanPartial = 1ull << 32, kScanInclusive = 2ull << 32;
+
+__device__ __forceinline__ uint64_t ld_state(const uint64_t* p) {
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_state(uint64_t* p, uint64_t v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// exclusive prefix of this tile's total over all earlier tiles, by warp 0 of the CTA (all 32 lanes call); publishes the
+// tile's own state.  Returns the prefix in every lane of the warp.
+__device__ __forceinline__ uint32_t chain_lookback(uint64_t* status, uint32_t tile, uint32_t epoch, uint32_t tot, int lane) {
+	const uint64_t stamp = (uint64_t)epoch << 34;
+	if (lane == 0) st_state(status + tile, stamp | (tile == 0 ? kScanInclusive : kScanPartial) | tot);
+	uint32_t excl = 0;
+	if (tile != 0) {
+		int64_t look = (int64_t)tile - 1;
+		for (;;) {
+			const int64_t idx = look - lane;
+			const uint64_t s = idx >= 0 ? ld_state(status + idx) : (stamp | kScanInclusive);
+			const uint32_t flag = (s >> 34) == (uint64_t)epoch ? (uint32_t)(s >> 32) & 3u : 0u;
+			const uint32_t ready = __ballot_sync(0xffffffffu, flag != 0u);
+			const uint32_t inclusive = __ballot_sync(0xffffffffu, flag == 2u);
+			const uint32_t need = inclusive ? (2u << (__ffs((int)inclusive) - 1)) - 1u : 0xffffffffu;  // lanes up to the first inclusive
+			if ((ready & need) != need) continue;  // a predecessor in reach has not published yet: poll again
+			excl += __reduce_add_sync(0xffffffffu, (need >> lane) & 1u ? (uint32_t)s : 0u);
+			if (inclusive) break;
+			look -= 32;
+		}
+		if (lane == 0) st_state(status + tile, stamp | kScanInclusive | (uint64_t)(uint32_t)(excl + tot));
+	}
+	return excl;
+}
+#endif
+
 
 // ---- batch.cu ----
 // All sequences handed to one create call: packed sequences, the union of their seeds sorted by key, and

@@ -77,194 +77,157 @@ __device__ __forceinline__ uint32_t strand_of(const void* keys, uint32_t i) {
 	return (uint32_t)(reinterpret_cast<const KeyT*>(keys)[i] & 1);
 }
 
-// ------------------------------------------------------------------------------------------------ 1. run scan
+// ------------------------------------------------------------------------------------------------ 1. runs -> hits
 constexpr int kScanBlock = 256;
+constexpr int kRunItems = 8;                         // consecutive union entries per thread
+constexpr int kRunTile = kScanBlock * kRunItems;     // per CTA
+constexpr uint32_t kRunOk = 0x80000000u;
 
-// run_info[i] = number of union entries in the hit that starts at i (0 = no hit starts here)
-//
-// Warp-cooperative: a warp looks at 32 consecutive union entries and decides the runs that START in its first
-// `own` lanes (the next warp starts `own` entries further, so the windows overlap by 32 - own entries and
-// runs of up to that length close inside the window).  Heads and run ends are two ballots; a sequence that
-// occurs twice in a run is found with one MATCH.ANY on (run start, sequence); every decision is then bit
-// arithmetic on warp-uniform masks — no per-thread loop over the run, no divergent loads.  Runs that do not
-// close inside the window (longer than the overlap: repeats, or more sequences than the overlap) are walked
-// serially by their head lane as before.
-struct ScanShape {
-	uint32_t own;             // run heads a warp decides: entries [warp * own, warp * own + own)
-	uint32_t chunks_per_cta;  // a CTA takes this many consecutive chunks of kScanBlock / 32 warps
-};
-__host__ __device__ inline uint32_t scan_chunk_entries(const ScanShape& sh) { return sh.own * (kScanBlock / 32); }
-
-template <class KeyT>
-__device__ __forceinline__ uint16_t serial_run(const MatchArgs& a, uint32_t i, uint64_t mk, uint32_t* my_run) {
-	uint32_t len = 1;
-	bool ok = true;
-	if (a.mode == MEMS_MODE_MEMHASH) {
-		// at most one occurrence per sequence (repeat_tolerance 0), >= 2 sequences
-		// (sequence numbers relative to the run's problem: a problem has at most MEMS_MAX_SEQS sequences, a batch of many more)
-		const uint32_t g0 = a.n_seqs > 64 ? a.meta[a.vals[i] >> a.pos_bits].group_first : 0u;
-		uint64_t seen = 1ull << ((a.vals[i] >> a.pos_bits) - g0);
-		uint32_t j = i + 1;
-		while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
-			if (ok) {
-				uint64_t bit = 1ull << ((a.vals[j] >> a.pos_bits) - g0);
-				if (seen & bit) ok = false;
-				seen |= bit;
-			}
-			++len;
-			++j;
-		}
-		if (a.seq_set && seen != a.seq_set) ok = false;  // MaskedMemHash::HashMatch, MaskedMemHash.cpp:50-60
-	} else {
-		uint32_t j = i + 1;
-		while (j < a.n && masked_of<KeyT>(a.keys, j) == mk && len <= kRunCap) {
-			++len;
-			++j;
-		}
-	}
-	*my_run = len;
-	if (len > kRunCap) ok = false;
-	return ok ? (uint16_t)len : (uint16_t)0;
-}
-
+// Equal-seed runs of the sorted union -> hits (MatchFinder::SearchRange, MatchFinder.cpp:253-337, and the policies
+// MemHash::EnumerateMatches, MemHash.cpp:139-162 / RepeatHash.cpp:34-45 / MaskedMemHash.cpp:50-60), ONE kernel.
+// A thread owns 8 consecutive union entries (128-bit loads) and decides every run that STARTS among them in one
+// forward pass with a few registers of state: run length, the set of sequences seen, "a sequence occurred twice".  A
+// run still open at the thread's last entry is followed into the neighbours' entries (L1/L2 hits; runs are short).
+// The hits leave in union order: per-thread counts are scanned inside the CTA and every thread writes (first entry,
+// length) of its hits to the CTA's own kRunTile / 2 slots of a staging array — no CTA waits for another (a chained
+// look-back over ~20 k small tiles cost more than the kernel's whole memory time) — and hit_gather_kernel closes the gaps
+// once the tile counts are scanned: 6 bytes per hit instead of a flag per union entry.
 template <class KeyT>
 __global__ void __launch_bounds__(kScanBlock)
-run_scan_kernel(MatchArgs a, ScanShape sh, uint16_t* __restrict__ run_info, uint32_t* __restrict__ block_hits,
+run_hits_kernel(MatchArgs a, uint32_t* __restrict__ stage_start, uint16_t* __restrict__ stage_len, uint32_t* __restrict__ tile_hits,
                 uint32_t* __restrict__ max_run) {
-	__shared__ uint32_t s_cnt[kScanBlock / 32];
-	__shared__ uint32_t s_max[kScanBlock / 32];
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const KeyT* keys = reinterpret_cast<const KeyT*>(a.keys);
-	const uint32_t lanemask_lt = (1u << lane) - 1u;
-	const int n_set = __popcll(a.seq_set);
-	const int seq_bits = 32 - __clz(max(a.n_seqs - 1, 1));
-	uint32_t hits = 0, longest = 0;  // per warp (kept in lane 0) / per lane
-	for (uint32_t c = 0; c < sh.chunks_per_cta; ++c) {
-		const uint64_t g0 = ((uint64_t)(blockIdx.x * sh.chunks_per_cta + c) * (kScanBlock / 32) + warp) * sh.own;
-		if (g0 >= a.n) break;  // warp-uniform
-		const uint32_t i = (uint32_t)g0 + lane;
-		const bool in = i < a.n;
-		const KeyT mk = in ? (KeyT)(keys[i] >> 1) : (KeyT)0;
-		const uint32_t seq = in ? a.vals[i] >> a.pos_bits : 0u;
-		// neighbours' keys straight from memory (L1 hits): shuffles, like MATCH, queue in the MIO pipe, which bounds
-		// this kernel (ncu: mio_throttle is the top stall with MATCH.ANY + 64-bit shuffles)
-		const bool has_prev = i > 0, has_next = i + 1 < a.n;
-		const KeyT prev_mk = in && has_prev ? (KeyT)(keys[i - 1] >> 1) : (KeyT)0;
-		const KeyT next_mk = in && has_next ? (KeyT)(keys[i + 1] >> 1) : (KeyT)0;
-		const bool head = in && (!has_prev || prev_mk != mk);
-		const bool end = in && (!has_next || next_mk != mk);
-		const uint32_t heads = __ballot_sync(0xffffffffu, head), ends = __ballot_sync(0xffffffffu, end);
-		// the run this lane belongs to: from the nearest head at or below it to the nearest end at or above it
-		const uint32_t at_or_below = heads & (lanemask_lt | (1u << lane));
-		const uint32_t at_or_above = ends & ~lanemask_lt;
-		uint32_t dups = 0, foreign = 0;
-		if (a.mode == MEMS_MODE_MEMHASH) {
-			// lanes holding the same sequence: one ballot per bit of the sequence id
-			uint32_t same_seq = 0xffffffffu;
-			for (int b = 0; b < seq_bits; ++b) {
-				const bool bit = (seq >> b) & 1u;
-				const uint32_t m = __ballot_sync(0xffffffffu, bit);
-				same_seq &= bit ? m : ~m;
-			}
-			// earlier lanes of my run (runs that began before the window are decided by the previous warp)
-			const uint32_t run_from = at_or_below ? 31u - (uint32_t)__clz((int)at_or_below) : 32u;
-			const uint32_t earlier = run_from < 32u ? lanemask_lt & ~((1u << run_from) - 1u) : 0u;
-			dups = __ballot_sync(0xffffffffu, in && (same_seq & earlier) != 0u);
-			if (a.seq_set) foreign = __ballot_sync(0xffffffffu, in && !((a.seq_set >> seq) & 1ull));
-		}
-		uint16_t info = 0;
-		uint32_t my_run = 0;
-		if (head && lane < sh.own) {
-			if (at_or_above) {
-				const uint32_t e = (uint32_t)__ffs((int)at_or_above) - 1u;
-				const uint32_t len = e - lane + 1u;
-				const uint32_t members = (2u << e) - (1u << lane);  // lanes lane..e (e = 31 wraps to the right mask)
-				if (len >= 2u) {
-					my_run = len;
-					bool ok = true;  // len <= 32 < kRunCap
-					if (a.mode == MEMS_MODE_MEMHASH) {
-						ok = (dups & members) == 0u;
-						if (a.seq_set) ok = ok && (foreign & members) == 0u && (int)len == n_set;  // MaskedMemHash.cpp:50-60
-					}
-					if (ok) info = (uint16_t)len;
-				}
-			} else {  // the run goes on past the window
-				info = serial_run<KeyT>(a, i, (uint64_t)mk, &my_run);
-			}
-		}
-		if (in && lane < sh.own) run_info[i] = info;
-		const uint32_t b = __ballot_sync(0xffffffffu, info != 0);
-		hits += __popc(b);
-		longest = max(longest, my_run);
-	}
-	longest = __reduce_max_sync(0xffffffffu, longest);
-	if (lane == 0) {
-		s_cnt[warp] = hits;
-		s_max[warp] = longest;
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t t = 0, mx = 0;
-		for (int w = 0; w < kScanBlock / 32; ++w) {
-			t += s_cnt[w];
-			mx = max(mx, s_max[w]);
-		}
-		block_hits[blockIdx.x] = t;
-		if (mx > 1) atomicMax(max_run, mx);  // one atomic per CTA
-	}
-}
-
-// hits in key order: every CTA compacts the entries run_scan_kernel's CTA of the same index decided;
-// a thread takes 8 consecutive entries (one 128-bit load), a CTA 2048 per round
-__global__ void __launch_bounds__(kScanBlock)
-hit_compact_kernel(const uint16_t* __restrict__ run_info, uint32_t n, ScanShape sh, const uint32_t* __restrict__ block_off,
-                   uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len) {
-	__shared__ uint32_t s_cnt[kScanBlock / 32];
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint64_t per_cta = (uint64_t)scan_chunk_entries(sh) * sh.chunks_per_cta;  // a multiple of 8
-	const uint64_t first = (uint64_t)blockIdx.x * per_cta;
-	const uint64_t last = first + per_cta < n ? first + per_cta : n;
-	uint32_t off = block_off[blockIdx.x];
-	for (uint64_t base = first; base < last; base += kScanBlock * 8) {
-		const uint64_t i0 = base + (uint64_t)threadIdx.x * 8;
-		uint16_t info[8];
-		if (i0 + 8 <= last) {
-			const uint4 raw = *reinterpret_cast<const uint4*>(run_info + i0);
-			const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-			for (int k = 0; k < 8; ++k) info[k] = (uint16_t)(r[k >> 1] >> ((k & 1) * 16));
+	__shared__ uint32_t s_tot[kScanBlock / 32], s_max[kScanBlock / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t tile = blockIdx.x;
+	const KeyT* __restrict__ keys = reinterpret_cast<const KeyT*>(a.keys);
+	const uint64_t n = a.n;
+	const uint64_t i0 = (uint64_t)tile * kRunTile + (uint64_t)tid * kRunItems;
+	KeyT mk[kRunItems];
+	uint32_t sq[kRunItems];
+	if (i0 + kRunItems <= n && ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(a.vals)) & 15u) == 0) {
+		if (sizeof(KeyT) == 4) {
+			const uint4 q0 = *reinterpret_cast<const uint4*>(keys + i0), q1 = *reinterpret_cast<const uint4*>(keys + i0 + 4);
+			mk[0] = (KeyT)(q0.x >> 1); mk[1] = (KeyT)(q0.y >> 1); mk[2] = (KeyT)(q0.z >> 1); mk[3] = (KeyT)(q0.w >> 1);
+			mk[4] = (KeyT)(q1.x >> 1); mk[5] = (KeyT)(q1.y >> 1); mk[6] = (KeyT)(q1.z >> 1); mk[7] = (KeyT)(q1.w >> 1);
 		} else {
 #pragma unroll
-			for (int k = 0; k < 8; ++k) info[k] = i0 + k < last ? run_info[i0 + k] : (uint16_t)0;
-		}
-		uint32_t mine = 0;
-#pragma unroll
-		for (int k = 0; k < 8; ++k) mine += info[k] != 0;
-		uint32_t incl = mine;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += t;
-		}
-		if (lane == 31) s_cnt[warp] = incl;
-		__syncthreads();
-		uint32_t at = off + incl - mine, total = 0;
-#pragma unroll
-		for (uint32_t w = 0; w < kScanBlock / 32; ++w) {
-			const uint32_t cnt = s_cnt[w];
-			if (w < warp) at += cnt;
-			total += cnt;
-		}
-#pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			if (info[k]) {
-				hit_start[at] = (uint32_t)(i0 + k);
-				hit_len[at] = info[k];
-				++at;
+			for (int k = 0; k < kRunItems; k += 2) {
+				const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(keys + i0 + k);
+				mk[k] = (KeyT)(q.x >> 1);
+				mk[k + 1] = (KeyT)(q.y >> 1);
 			}
 		}
-		off += total;
-		__syncthreads();
+		const uint4 v0 = *reinterpret_cast<const uint4*>(a.vals + i0), v1 = *reinterpret_cast<const uint4*>(a.vals + i0 + 4);
+		sq[0] = v0.x; sq[1] = v0.y; sq[2] = v0.z; sq[3] = v0.w;
+		sq[4] = v1.x; sq[5] = v1.y; sq[6] = v1.z; sq[7] = v1.w;
+	} else {
+#pragma unroll
+		for (int k = 0; k < kRunItems; ++k) {
+			const bool in = i0 + k < n;
+			mk[k] = in ? (KeyT)(keys[i0 + k] >> 1) : (KeyT)0;
+			sq[k] = in ? a.vals[i0 + k] : 0u;
+		}
+	}
+	const bool memhash = a.mode == MEMS_MODE_MEMHASH;
+	const bool grouped = a.n_seqs > 64;  // a batch of many problems: sequence bits are relative to the run's problem
+	// forward pass: rec[k] / rec_at[k] = the run that closed right before entry k (length | kRunOk, first entry)
+	uint32_t rec[kRunItems + 1], rec_at[kRunItems + 1];
+	bool open = false, dup = false;
+	uint32_t len = 0, at = 0, g0 = 0, longest = 0;
+	uint64_t seen = 0;
+	KeyT cur = 0;
+	auto close = [&](uint32_t& r) {  // the open run ends: a hit if the policy takes it
+		r = 0;
+		if (len >= 2u) {
+			longest = max(longest, len);
+			bool ok = len <= kRunCap;
+			if (memhash) ok = ok && !dup && (!a.seq_set || seen == a.seq_set);  // one occurrence per sequence; MaskedMemHash: exactly this set
+			r = len | (ok ? kRunOk : 0u);
+		}
+	};
+	const KeyT before = i0 > 0 && i0 < n ? (KeyT)(keys[i0 - 1] >> 1) : (KeyT)0;
+#pragma unroll
+	for (int k = 0; k < kRunItems; ++k) {
+		const bool in = i0 + k < n;
+		const bool same = in && (k == 0 ? (i0 > 0 && mk[0] == before) : mk[k] == mk[k - 1]);
+		rec[k] = 0;
+		rec_at[k] = at;
+		if (!same) {  // entry k starts a run (or lies past the end)
+			if (open) close(rec[k]);
+			open = in;
+			if (in) {
+				at = (uint32_t)(i0 + k);
+				len = 1;
+				dup = false;
+				cur = mk[k];
+				const uint32_t g = sq[k] >> a.pos_bits;
+				g0 = grouped ? a.meta[g].group_first : 0u;
+				seen = 1ull << (g - g0);
+			}
+		} else if (open) {  // (entries of a run that began before this thread's first entry are someone else's)
+			const uint64_t bit = 1ull << ((sq[k] >> a.pos_bits) - g0);
+			dup |= (seen & bit) != 0ull;
+			seen |= bit;
+			++len;
+		}
+	}
+	rec[kRunItems] = 0;
+	rec_at[kRunItems] = at;
+	if (open) {  // follow the last run into the neighbours' entries
+		uint64_t j = i0 + kRunItems;
+		while (j < n && (KeyT)(keys[j] >> 1) == cur && len <= kRunCap) {
+			const uint64_t bit = 1ull << ((a.vals[j] >> a.pos_bits) - g0);
+			dup |= (seen & bit) != 0ull;
+			seen |= bit;
+			++len;
+			++j;
+		}
+		close(rec[kRunItems]);
+	}
+	uint32_t mine = 0;
+#pragma unroll
+	for (int k = 1; k <= kRunItems; ++k) mine += rec[k] >> 31;
+	// CTA-wide exclusive scan of the counts, then the chain
+	uint32_t incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	longest = __reduce_max_sync(0xffffffffu, longest);
+	if (lane == 31) s_tot[warp] = incl;
+	if (lane == 0) s_max[warp] = longest;
+	__syncthreads();
+	uint32_t woff = 0, tot = 0, mx = 0;
+#pragma unroll
+	for (int w = 0; w < kScanBlock / 32; ++w) {
+		const uint32_t t = s_tot[w];
+		if (w < warp) woff += t;
+		tot += t;
+		mx = max(mx, s_max[w]);
+	}
+	if (tid == 0) {
+		tile_hits[tile] = tot;
+		if (mx > 1u) atomicMax(max_run, mx);  // one atomic per CTA
+	}
+	uint32_t out = tile * (uint32_t)(kRunTile / 2) + woff + incl - mine;
+#pragma unroll
+	for (int k = 1; k <= kRunItems; ++k) {
+		if (rec[k] & kRunOk) {
+			stage_start[out] = rec_at[k];
+			stage_len[out] = (uint16_t)(rec[k] & 0xffffu);
+			++out;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+hit_gather_kernel(const uint32_t* __restrict__ stage_start, const uint16_t* __restrict__ stage_len, const uint32_t* __restrict__ tile_hits,
+                  const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len) {
+	const uint32_t tile = blockIdx.x, cnt = tile_hits[tile], off = tile_off[tile], from = tile * (uint32_t)(kRunTile / 2);
+	for (uint32_t r = threadIdx.x; r < cnt; r += kScanBlock) {
+		hit_start[off + r] = stage_start[from + r];
+		hit_len[off + r] = stage_len[from + r];
 	}
 }
 
@@ -1699,23 +1662,18 @@ struct HitSet {
 template <class KeyT>
 static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	const uint32_t n = a.n;
-	// overlap of the warps' windows = the longest run that must close inside one (up to 16 sequences' worth)
-	ScanShape sh;
-	sh.own = 32u - (uint32_t)std::min(std::max(a.max_group, 2), 16);
-	if (a.mode != MEMS_MODE_MEMHASH) sh.own = 24;  // repeat policy: copies per family, not sequences, set the run length
-	const uint64_t n_chunks = ((uint64_t)n + scan_chunk_entries(sh) - 1) / scan_chunk_entries(sh);
-	sh.chunks_per_cta = (uint32_t)std::max<uint64_t>(1, n_chunks / ((uint64_t)c->sm_count * 16));
-	const uint32_t n_blocks = (uint32_t)((n_chunks + sh.chunks_per_cta - 1) / sh.chunks_per_cta);
-	DevBuf<uint16_t> run_info(c, n);
-	DevBuf<uint32_t> block_hits(c, n_blocks + 1), scalars(c, 2);
+	const uint64_t n_tiles = ((uint64_t)n + kRunTile - 1) / kRunTile;
+	// a hit has at least two entries: a tile's kRunTile / 2 staging slots hold whatever it finds
+	DevBuf<uint32_t> stage_start(c, n_tiles * (kRunTile / 2)), tile_hits(c, n_tiles), tile_off(c, n_tiles), scalars(c, 2);
+	DevBuf<uint16_t> stage_len(c, n_tiles * (kRunTile / 2));
 	MEMS_CUDA(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(uint32_t), c->stream));
 	{
-		KernelScope ks(c, "run_scan", (double)n * (sizeof(KeyT) + 2.0));
-		run_scan_kernel<KeyT><<<n_blocks, kScanBlock, 0, c->stream>>>(a, sh, run_info.p, block_hits.p, scalars.p + 0);
+		KernelScope ks(c, "run_hits", (double)n * (sizeof(KeyT) + 4.0));
+		run_hits_kernel<KeyT><<<(unsigned)n_tiles, kScanBlock, 0, c->stream>>>(a, stage_start.p, stage_len.p, tile_hits.p, scalars.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
-	exclusive_scan_u32(c, block_hits.p, block_hits.p, n_blocks, scalars.p + 1);
-	uint32_t h_scal[2];
+	exclusive_scan_u32(c, tile_hits.p, tile_off.p, n_tiles, scalars.p + 1);
+	uint32_t h_scal[2];  // [0] longest run, [1] hits
 	MEMS_CUDA(cudaMemcpyAsync(h_scal, scalars.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
 	MEMS_CUDA(cudaStreamSynchronize(c->stream));
 	hits.max_run = h_scal[0];
@@ -1724,8 +1682,8 @@ static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	hits.start = DevBuf<uint32_t>(c, hits.n);
 	hits.len = DevBuf<uint16_t>(c, hits.n);
 	{
-		KernelScope ks(c, "hit_compact", (double)n * 2.0);
-		hit_compact_kernel<<<n_blocks, kScanBlock, 0, c->stream>>>(run_info.p, n, sh, block_hits.p, hits.start.p, hits.len.p);
+		KernelScope ks(c, "hit_gather", (double)hits.n * 12.0);
+		hit_gather_kernel<<<(unsigned)n_tiles, kScanBlock, 0, c->stream>>>(stage_start.p, stage_len.p, tile_hits.p, tile_off.p, hits.start.p, hits.len.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 }

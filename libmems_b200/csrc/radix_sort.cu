@@ -410,17 +410,6 @@ void launch_histogram(Ctx* c, bool key64, const void* d_keys, uint64_t n, const 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr uint64_t kScanPartial = 1ull << 32, kScanInclusive = 2ull << 32;
-
-__device__ __forceinline__ uint64_t ld_state(const uint64_t* p) {
-	uint64_t v;
-	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_state(uint64_t* p, uint64_t v) {
-	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(kScanThreads)
 scan_chained_kernel(const uint32_t* in, uint32_t* out, uint64_t n,  // in may alias out (in-place scan)
                     uint64_t* state, uint32_t ticket_base, uint32_t epoch, uint32_t* total_out) {
@@ -431,7 +420,6 @@ scan_chained_kernel(const uint32_t* in, uint32_t* out, uint64_t n,  // in may al
 	__syncthreads();
 	const uint32_t tile = s_tile;
 	uint64_t* status = state + 1;
-	const uint64_t stamp = (uint64_t)epoch << 34;
 	const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)tid * kScanItems;  // blocked: a thread owns 16 in a row
 	uint32_t v[kScanItems];
 	if (base + kScanItems <= n && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
@@ -464,24 +452,7 @@ scan_chained_kernel(const uint32_t* in, uint32_t* out, uint64_t n,  // in may al
 		tot += t;
 	}
 	if (tid < 32) {  // warp 0: publish, look back
-		if (lane == 0) st_state(status + tile, stamp | (tile == 0 ? kScanInclusive : kScanPartial) | tot);
-		uint32_t excl = 0;
-		if (tile != 0) {
-			int64_t look = (int64_t)tile - 1;
-			for (;;) {
-				const int64_t idx = look - lane;
-				const uint64_t s = idx >= 0 ? ld_state(status + idx) : (stamp | kScanInclusive);
-				const uint32_t flag = (s >> 34) == (uint64_t)epoch ? (uint32_t)(s >> 32) & 3u : 0u;
-				const uint32_t ready = __ballot_sync(0xffffffffu, flag != 0u);
-				const uint32_t inclusive = __ballot_sync(0xffffffffu, flag == 2u);
-				const uint32_t need = inclusive ? (2u << (__ffs((int)inclusive) - 1)) - 1u : 0xffffffffu;  // lanes up to the first inclusive
-				if ((ready & need) != need) continue;  // a predecessor in reach has not published yet: poll again
-				excl += __reduce_add_sync(0xffffffffu, (need >> lane) & 1u ? (uint32_t)s : 0u);
-				if (inclusive) break;
-				look -= 32;
-			}
-			if (lane == 0) st_state(status + tile, stamp | kScanInclusive | (uint64_t)(uint32_t)(excl + tot));
-		}
+		const uint32_t excl = chain_lookback(status, tile, epoch, tot, lane);
 		if (lane == 0) s_excl = excl;
 	}
 	__syncthreads();
@@ -506,12 +477,7 @@ scan_chained_kernel(const uint32_t* in, uint32_t* out, uint64_t n,  // in may al
 	if (total_out && tid == kScanThreads - 1 && (uint64_t)(tile + 1) * kScanTile >= n) *total_out = off;
 }
 
-void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n, uint32_t* d_total) {
-	if (n == 0) {
-		if (d_total) MEMS_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint32_t), c->stream));
-		return;
-	}
-	const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+ChainTicket reserve_chain_tiles(Ctx* c, uint64_t n_tiles) {
 	if (n_tiles + 1 > c->scan_cap || c->scan_epoch >= (1u << 30) - 1u) {  // (re)create the tile states: zero = no epoch
 		const size_t cap = std::max<size_t>(n_tiles + 1, std::max<size_t>(c->scan_cap, 1u << 16));
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
@@ -523,11 +489,21 @@ void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t 
 		c->scan_epoch = 0;
 		c->scan_ticket_base = 0;
 	}
-	KernelScope ks(c, "scan");
-	scan_chained_kernel<<<(unsigned)n_tiles, kScanThreads, 0, c->stream>>>(d_in, d_out, n, c->scan_state, c->scan_ticket_base,
-	                                                                        ++c->scan_epoch, d_total);
-	MEMS_CUDA(cudaGetLastError());
+	ChainTicket t{c->scan_state, c->scan_ticket_base, ++c->scan_epoch};
 	c->scan_ticket_base += (uint32_t)n_tiles;
+	return t;
+}
+
+void exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n, uint32_t* d_total) {
+	if (n == 0) {
+		if (d_total) MEMS_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint32_t), c->stream));
+		return;
+	}
+	const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+	const ChainTicket t = reserve_chain_tiles(c, n_tiles);
+	KernelScope ks(c, "scan");
+	scan_chained_kernel<<<(unsigned)n_tiles, kScanThreads, 0, c->stream>>>(d_in, d_out, n, t.state, t.ticket_base, t.epoch, d_total);
+	MEMS_CUDA(cudaGetLastError());
 }
 
 }  // namespace mems

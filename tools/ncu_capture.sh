@@ -10,7 +10,7 @@ capture() {  # regex, launches to skip, tag
 }
 capture 'onesweep_kernel<unsigned int, \(int\)256, \(int\)5, \(int\)8' 10 onesweep_u32
 capture 'mems::segment_flag_kernel' 2 segment_flag
-capture 'mems::run_scan_kernel' 2 run_scan
+capture 'mems::run_hits_kernel' 2 run_hits
 capture 'mems::hit_describe_kernel' 2 hit_describe
 capture 'mems::extract_kernel' 2 extract
 capture 'mems::long_walk_right_kernel' 2 long_walk_right
