@@ -309,10 +309,65 @@ __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
 // ------------------------------------------------------------------------------------------------ 2. describe
 constexpr int kMaxHitPasses = 8;
 
+// A hit of at most 8 members as registers: its members in merged (sequence, position) order relative to the first.
+// Two hits lie on one diagonal iff their signatures are equal.
+struct HitSig {
+	uint32_t len;      // members; kSigLong = more than 8: compared through memory (same_diagonal)
+	uint32_t so[4];    // (sequence << 1 | orientation) of members 0..7, 16 bits each
+	uint32_t diag[7];  // members 1..7: position minus / plus the first member's, by orientation
+};
+constexpr uint32_t kSigLong = 0xffffffffu;
+
+__device__ __forceinline__ HitSig make_sig(const MatchArgs& a, uint32_t len, const uint32_t (&v)[8], const uint32_t (&st)[8]) {
+	HitSig g;
+	g.len = len;
+#pragma unroll
+	for (int t = 0; t < 4; ++t) g.so[t] = 0;
+#pragma unroll
+	for (int t = 0; t < 7; ++t) g.diag[t] = 0;
+	const uint32_t sf = st[0], x0 = v[0] & a.pos_mask;
+	g.so[0] = (v[0] >> a.pos_bits) << 1;
+#pragma unroll
+	for (int t = 1; t < 8; ++t) {
+		if ((uint32_t)t < len) {
+			const uint32_t o = st[t] ^ sf, p = v[t] & a.pos_mask;
+			g.so[t >> 1] |= (((v[t] >> a.pos_bits) << 1) | o) << (16 * (t & 1));
+			g.diag[t - 1] = o ? p + x0 : p - x0;  // (32-bit wrap is one-to-one here: |p - x0| < 2^30, p + x0 < 2^31)
+		}
+	}
+	return g;
+}
+// The signature as hit_describe_kernel leaves it for segment_flag_kernel: 64 bytes per hit, in hit order.  There the
+// members of a hit are neighbours in the union and cost one coalesced pass; gathered again in diagonal order (where
+// neighbours sit at random places of the union) they were 1.6 GB of DRAM sectors per config-2 step.
+struct __align__(16) HitSigRec {
+	HitSig sig;
+	uint32_t hit_start, members, pad[2];
+};
+static_assert(sizeof(HitSigRec) == 64, "one 64-byte record per hit");
+__device__ __forceinline__ HitSigRec load_sig_rec(const HitSigRec* __restrict__ p) {
+	const uint4* q = reinterpret_cast<const uint4*>(p);
+	const uint4 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
+	HitSigRec r;
+	r.sig.len = a0.x; r.sig.so[0] = a0.y; r.sig.so[1] = a0.z; r.sig.so[2] = a0.w;
+	r.sig.so[3] = a1.x; r.sig.diag[0] = a1.y; r.sig.diag[1] = a1.z; r.sig.diag[2] = a1.w;
+	r.sig.diag[3] = a2.x; r.sig.diag[4] = a2.y; r.sig.diag[5] = a2.z; r.sig.diag[6] = a2.w;
+	r.hit_start = a3.x; r.members = a3.y; r.pad[0] = 0; r.pad[1] = 0;
+	return r;
+}
+__device__ __forceinline__ void store_sig_rec(HitSigRec* __restrict__ p, const HitSig& g, uint32_t hit_start, uint32_t members) {
+	uint4* q = reinterpret_cast<uint4*>(p);
+	q[0] = make_uint4(g.len, g.so[0], g.so[1], g.so[2]);
+	q[1] = make_uint4(g.so[3], g.diag[0], g.diag[1], g.diag[2]);
+	q[2] = make_uint4(g.diag[3], g.diag[4], g.diag[5], g.diag[6]);
+	q[3] = make_uint4(hit_start, members, 0u, 0u);
+}
+
 template <class KeyT>
 __global__ void __launch_bounds__(256)
 hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_t* __restrict__ hit_len, uint32_t n_hits,
-                    uint64_t* __restrict__ hkey, uint32_t* __restrict__ hid, uint32_t* __restrict__ hist, SortPlan plan) {
+                    uint64_t* __restrict__ hkey, uint32_t* __restrict__ hid, uint32_t* __restrict__ hist, SortPlan plan,
+                    HitSigRec* __restrict__ sig) {  // sig: optional
 	__shared__ uint32_t s_hist[kMaxHitPasses * 256];
 	for (int i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) s_hist[i] = 0;
 	__syncthreads();
@@ -327,6 +382,7 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 		if (len <= 8) {  // the usual case: members as registers, no dependent loads
 			uint32_t v[8], st8[8];
 			sorted_members8<KeyT>(a, s, len, v, st8);
+			if (sig) store_sig_rec(sig + h, make_sig(a, len, v, st8), s, len);
 			sf = st8[0];
 			x0 = v[0] & a.pos_mask;
 			hash = mix64(0x1234567ull + len, v[0] >> a.pos_bits);
@@ -341,6 +397,11 @@ hit_describe_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, uint16_
 				}
 			}
 		} else {
+			if (sig) {
+				HitSig g{};
+				g.len = kSigLong;
+				store_sig_rec(sig + h, g, s, len);
+			}
 			MemberIter<KeyT> it(a, s, len);
 			uint32_t val, st;
 			it.next(val, st);
@@ -424,42 +485,18 @@ __device__ bool same_diagonal(const MatchArgs& a, uint32_t sa, uint32_t la, uint
 constexpr uint8_t kFlagHead = 1;      // starts a new segment
 constexpr uint8_t kFlagSameDiag = 2;  // same diagonal as the previous entry in sorted order
 
-// A hit of at most 8 members as registers: its members in merged (sequence, position) order relative to the first.
-// Two hits lie on one diagonal iff their signatures are equal.  A thread builds the signature of its own hit once and
-// takes its predecessor's from the neighbouring lane, so every member list is gathered from the union once, not twice
-// (the gathers are what this kernel costs: the lists of hits that are neighbours here sit at random places there).
-struct HitSig {
-	uint32_t len;      // members; kSigLong = more than 8: compared through memory (same_diagonal)
-	uint32_t so[4];    // (sequence << 1 | orientation) of members 0..7, 16 bits each
-	uint32_t diag[7];  // members 1..7: position minus / plus the first member's, by orientation
-};
-constexpr uint32_t kSigLong = 0xffffffffu;
-
+// A thread builds the signature of its own hit once (or reads the record hit_describe_kernel left) and takes its
+// predecessor's from the neighbouring lane.
 template <class KeyT>
 __device__ __forceinline__ HitSig load_sig(const MatchArgs& a, uint32_t s, uint32_t len) {
-	HitSig g;
-	g.len = len;
-#pragma unroll
-	for (int t = 0; t < 4; ++t) g.so[t] = 0;
-#pragma unroll
-	for (int t = 0; t < 7; ++t) g.diag[t] = 0;
 	if (len > 8) {
+		HitSig g{};
 		g.len = kSigLong;
 		return g;
 	}
 	uint32_t v[8], st[8];
 	sorted_members8<KeyT>(a, s, len, v, st);
-	const uint32_t sf = st[0], x0 = v[0] & a.pos_mask;
-	g.so[0] = (v[0] >> a.pos_bits) << 1;
-#pragma unroll
-	for (int t = 1; t < 8; ++t) {
-		if ((uint32_t)t < len) {
-			const uint32_t o = st[t] ^ sf, p = v[t] & a.pos_mask;
-			g.so[t >> 1] |= (((v[t] >> a.pos_bits) << 1) | o) << (16 * (t & 1));
-			g.diag[t - 1] = o ? p + x0 : p - x0;  // (32-bit wrap is one-to-one here: |p - x0| < 2^30, p + x0 < 2^31)
-		}
-	}
-	return g;
+	return make_sig(a, len, v, st);
 }
 
 template <class KeyT>
@@ -467,7 +504,7 @@ __global__ void __launch_bounds__(256)
 segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ hid,
                     const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len, uint32_t n_hits,
                     uint8_t* __restrict__ flags, uint32_t* __restrict__ is_head, uint32_t* __restrict__ collision_seen,
-                    uint8_t* __restrict__ suspect) {
+                    uint8_t* __restrict__ suspect, const HitSigRec* __restrict__ sig) {  // sig: optional (hit order)
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool valid = i < n_hits;
 	const uint32_t lane = threadIdx.x & 31;
@@ -480,9 +517,16 @@ segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const
 	for (int t = 0; t < 7; ++t) mine.diag[t] = 0;
 	if (valid) {
 		const uint32_t h = hid[i];
-		s_mine = hit_start[h];
-		l_mine = hit_len[h] & ~kFirstStrandBit;
-		mine = load_sig<KeyT>(a, s_mine, l_mine);
+		if (sig) {
+			const HitSigRec r = load_sig_rec(sig + h);
+			mine = r.sig;
+			s_mine = r.hit_start;
+			l_mine = r.members;
+		} else {
+			s_mine = hit_start[h];
+			l_mine = hit_len[h] & ~kFirstStrandBit;
+			mine = load_sig<KeyT>(a, s_mine, l_mine);
+		}
 	}
 	// the predecessor's hit: from the lane below, or (first lane of a warp) gathered like the own one
 	HitSig prev;
@@ -499,9 +543,16 @@ segment_flag_kernel(MatchArgs a, int L, const uint64_t* __restrict__ hkey, const
 		if ((k >> a.pos_bits) == (kp >> a.pos_bits)) {
 			if (lane == 0) {
 				const uint32_t hb = hid[i - 1];
-				s_prev = hit_start[hb];
-				l_prev = hit_len[hb] & ~kFirstStrandBit;
-				prev = load_sig<KeyT>(a, s_prev, l_prev);
+				if (sig) {
+					const HitSigRec r = load_sig_rec(sig + hb);
+					prev = r.sig;
+					s_prev = r.hit_start;
+					l_prev = r.members;
+				} else {
+					s_prev = hit_start[hb];
+					l_prev = hit_len[hb] & ~kFirstStrandBit;
+					prev = load_sig<KeyT>(a, s_prev, l_prev);
+				}
 			}
 			bool same;
 			if (mine.len == kSigLong || prev.len == kSigLong) {
@@ -1823,6 +1874,8 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	SortPlan plan = make_sort_plan(a.hit_key_bits);
 	DevBuf<uint64_t> hk_a(c, given_hkey ? 0 : n_hits), hk_b(c, n_hits);
 	DevBuf<uint32_t> hid_a(c, n_hits), hid_b(c, n_hits), hist(c, (size_t)plan.n_passes * 256);
+	DevBuf<HitSigRec> sig;  // signatures in hit order (hits that arrive described — sharded — are compared through their members)
+	if (!given_hkey) sig = DevBuf<HitSigRec>(c, n_hits);
 	MEMS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)plan.n_passes * 256 * sizeof(uint32_t), c->stream));
 	const uint32_t hit_blocks = (n_hits + 255) / 256;
 	const uint32_t describe_blocks = std::min(hit_blocks, (uint32_t)c->sm_count * 8u);
@@ -1833,7 +1886,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	} else {
 		KernelScope ks(c, "hit_describe");
 		hit_describe_kernel<KeyT><<<describe_blocks, 256, 0, c->stream>>>(a, hit_start.p, hit_len.p, n_hits, hk_a.p, hid_a.p,
-		                                                                  hist.p, plan);
+		                                                                  hist.p, plan, sig.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	void* kp[2] = {given_hkey ? given_hkey : hk_a.p, hk_b.p};
@@ -1849,7 +1902,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	{
 		KernelScope ks(c, "segment_flag");
 		segment_flag_kernel<KeyT><<<hit_blocks, 256, 0, c->stream>>>(a, L, hkey, hid, hit_start.p, hit_len.p, n_hits,
-		                                                             flags.p, is_head.p, scalars.p + 4, suspect.p);
+		                                                             flags.p, is_head.p, scalars.p + 4, suspect.p, sig.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
 	exclusive_scan_u32(c, is_head.p, seg_of.p, n_hits, scalars.p + 2);
@@ -3017,7 +3070,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 		const uint32_t hb = (n1 + 255) / 256, describe_blocks = std::min(hb, (uint32_t)c->sm_count * 8u);
 		{
 			KernelScope ks(c, "hit_describe");
-			hit_describe_kernel<KeyT><<<describe_blocks, 256, 0, c->stream>>>(a1, hits1.start.p, hits1.len.p, n1, hk_a.p, hid_a.p, hist.p, hplan);
+			hit_describe_kernel<KeyT><<<describe_blocks, 256, 0, c->stream>>>(a1, hits1.start.p, hits1.len.p, n1, hk_a.p, hid_a.p, hist.p, hplan, nullptr);
 			MEMS_CUDA(cudaGetLastError());
 		}
 		void* kp[2] = {hk_a.p, hk_b.p};
