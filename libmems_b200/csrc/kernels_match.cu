@@ -616,7 +616,10 @@ __global__ void segment_compact_kernel(const uint32_t* __restrict__ is_head, con
 constexpr int kExtendWarps = 4;
 constexpr int kMemberTile = 64;  // members staged in shared memory per warp (MEMS_MAX_SEQS fits at once)
 constexpr int kProbeWindows = 1024;  // windows one warp tests per probe
-constexpr int kWarpProbeBudget = 6;  // probes a single warp spends on one walk before deferring it to a whole CTA
+#ifndef MEMS_WARP_BUDGET
+#define MEMS_WARP_BUDGET 6
+#endif
+constexpr int kWarpProbeBudget = MEMS_WARP_BUDGET;  // probes a single warp spends on one walk before deferring it to a whole CTA
 // Nine walks in ten end within a few hundred windows (config 2: 88 % of the segments need ONE 1024-window probe), so
 // the walk kernels start every segment on a GROUP of kGroupLanes lanes — 32 windows per lane as before, several
 // segments per warp — and only the walks that outlast kGroupProbeBudget group probes continue on the whole warp.
@@ -1247,7 +1250,10 @@ walk_left_kernel(MatchArgs a, const __grid_constant__ SeedDesc sd, const SegDesc
 constexpr int kLongWarps = 16;   // warps per CTA: two CTAs share an SM, so one's barrier waits overlap the other's probes
 constexpr int kWarpSpan = kProbeWindows;
 constexpr int kLongSpan = kLongWarps * kWarpSpan;  // 16384 windows between barriers
-constexpr int kCtaRoundBudget = 24; // rounds one CTA spends on a walk before the whole grid takes it over
+#ifndef MEMS_CTA_BUDGET
+#define MEMS_CTA_BUDGET 24
+#endif
+constexpr int kCtaRoundBudget = MEMS_CTA_BUDGET; // rounds one CTA spends on a walk before the whole grid takes it over
 
 struct ChainSummary {
 	int first, chain_end, last;  // 1-based distances inside the summarised span, 0 = no match
@@ -2063,7 +2069,9 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	}
 	if (mode != MEMS_MODE_REPEAT && (uint64_t)n_comp * (uint64_t)(a.max_group + 2) > 0xffffffffull)
 		throw Error(MEMS_ERR_UNSUPPORTED, "match list larger than 2^32 values; search fewer sequences per call");
-	const uint32_t n_flat = d2h_u32(c, scalars.p + 5);
+	// every record of a one-problem MemHash / Pairwise call has SeqCount + 2 values: the size is known without asking the device
+	const bool fixed_records = mode != MEMS_MODE_REPEAT && a.max_group == a.n_seqs && !many;
+	const uint32_t n_flat = fixed_records ? n_comp * (uint32_t)(a.n_seqs + 2) : d2h_u32(c, scalars.p + 5);
 	DevBuf<int64_t> d_flat(c, n_flat);
 	{
 		KernelScope ks(c, "emit");
