@@ -87,7 +87,8 @@ constexpr uint32_t kRunOk = 0x80000000u;
 // MemHash::EnumerateMatches, MemHash.cpp:139-162 / RepeatHash.cpp:34-45 / MaskedMemHash.cpp:50-60), ONE kernel.
 // A thread owns 8 consecutive union entries (128-bit loads) and decides every run that STARTS among them in one
 // forward pass with a few registers of state: run length, the set of sequences seen, "a sequence occurred twice".  A
-// run still open at the thread's last entry is followed into the neighbours' entries (L1/L2 hits; runs are short).
+// run still open at the thread's last entry ends in the next thread's leading entries: their summary comes from the
+// next lane by shuffle (long runs, and the last lane of a warp, follow the run through memory instead).
 // The hits leave in union order: per-thread counts are scanned inside the CTA and every thread writes (first entry,
 // length) of its hits to the CTA's own kRunTile / 2 slots of a staging array — no CTA waits for another (a chained
 // look-back over ~20 k small tiles cost more than the kernel's whole memory time) — and hit_gather_kernel closes the gaps
@@ -146,12 +147,24 @@ run_hits_kernel(MatchArgs a, uint32_t* __restrict__ stage_start, uint16_t* __res
 		}
 	};
 	const KeyT before = i0 > 0 && i0 < n ? (KeyT)(keys[i0 - 1] >> 1) : (KeyT)0;
+	// the thread's leading entries that continue its predecessor's run: what the thread before needs to close that run
+	bool leading = true, lead_dup = false;
+	uint32_t lead_len = 0;
+	uint64_t lead_seen = 0;
+	const uint32_t lead_g0 = grouped && i0 < n ? a.meta[sq[0] >> a.pos_bits].group_first : 0u;
 #pragma unroll
 	for (int k = 0; k < kRunItems; ++k) {
 		const bool in = i0 + k < n;
 		const bool same = in && (k == 0 ? (i0 > 0 && mk[0] == before) : mk[k] == mk[k - 1]);
 		rec[k] = 0;
 		rec_at[k] = at;
+		leading = leading && same;
+		if (leading) {
+			const uint64_t bit = 1ull << ((sq[k] >> a.pos_bits) - lead_g0);
+			lead_dup |= (lead_seen & bit) != 0ull;
+			lead_seen |= bit;
+			++lead_len;
+		}
 		if (!same) {  // entry k starts a run (or lies past the end)
 			if (open) close(rec[k]);
 			open = in;
@@ -173,16 +186,30 @@ run_hits_kernel(MatchArgs a, uint32_t* __restrict__ stage_start, uint16_t* __res
 	}
 	rec[kRunItems] = 0;
 	rec_at[kRunItems] = at;
-	if (open) {  // follow the last run into the neighbours' entries
-		uint64_t j = i0 + kRunItems;
-		while (j < n && (KeyT)(keys[j] >> 1) == cur && len <= kRunCap) {
-			const uint64_t bit = 1ull << ((a.vals[j] >> a.pos_bits) - g0);
-			dup |= (seen & bit) != 0ull;
-			seen |= bit;
-			++len;
-			++j;
+	{
+		// The run still open at the thread's last entry goes on in the next thread's leading entries: from the next lane's
+		// registers.  Only if that lane's entries all belong to the run too (or the lane sits in another warp) is the
+		// run followed through memory.
+		const uint32_t next_len = __shfl_down_sync(0xffffffffu, lead_len, 1);
+		const uint64_t next_seen = __shfl_down_sync(0xffffffffu, lead_seen, 1);
+		const bool next_dup = __shfl_down_sync(0xffffffffu, (int)lead_dup, 1) != 0;
+		if (open) {
+			if (lane < 31 && next_len < (uint32_t)kRunItems) {
+				dup |= next_dup || (seen & next_seen) != 0ull;
+				seen |= next_seen;
+				len += next_len;
+			} else {
+				uint64_t j = i0 + kRunItems;
+				while (j < n && (KeyT)(keys[j] >> 1) == cur && len <= kRunCap) {
+					const uint64_t bit = 1ull << ((a.vals[j] >> a.pos_bits) - g0);
+					dup |= (seen & bit) != 0ull;
+					seen |= bit;
+					++len;
+					++j;
+				}
+			}
+			close(rec[kRunItems]);
 		}
-		close(rec[kRunItems]);
 	}
 	uint32_t mine = 0;
 #pragma unroll

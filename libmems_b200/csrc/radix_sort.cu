@@ -27,8 +27,17 @@
 namespace mems {
 
 constexpr int kRadix = 256;
-constexpr int kTile = 4096;  // pairs per CTA
-constexpr int kMinB32 = 5, kMinB64 = 4;  // resident CTAs per SM the kernels are compiled for
+#ifndef MEMS_RADIX_TILE
+#define MEMS_RADIX_TILE 4096
+#endif
+#ifndef MEMS_RADIX_MINB32
+#define MEMS_RADIX_MINB32 5
+#endif
+#ifndef MEMS_RADIX_MINB64
+#define MEMS_RADIX_MINB64 4
+#endif
+constexpr int kTile = MEMS_RADIX_TILE;  // pairs per CTA
+constexpr int kMinB32 = MEMS_RADIX_MINB32, kMinB64 = MEMS_RADIX_MINB64;  // resident CTAs per SM the kernels are compiled for
 
 constexpr uint32_t kFlagPartial = 0x40000000u;
 constexpr uint32_t kFlagInclusive = 0x80000000u;

@@ -10,7 +10,7 @@ import json, sys
 d = json.loads(open("gpurun_out/tune.json").read().strip().splitlines()[-1])
 k = d["kernels"]
 print(sys.argv[1], "ms/step %.3f" % d["ms_per_step"], "kernel %.3f" % d["roofline"]["kernel_ms_per_step"],
-      " ".join("%s %.3f" % (n, k[n]["ms_per_step"]) for n in ("walk_right", "walk_left", "long_walk_right", "long_walk_left", "giant_walk_right", "giant_walk_left") if n in k),
+      " ".join("%s %.3f" % (n, k[n]["ms_per_step"]) for n in (__import__("os").environ.get("TUNE_KERNELS") or "walk_right walk_left long_walk_right long_walk_left giant_walk_right giant_walk_left").split() if n in k),
       "matches", d["matches_per_step"])
 PY
 done
