@@ -1596,6 +1596,29 @@ __global__ void suspect_list_kernel(const uint8_t* __restrict__ comp_suspect, co
 	if (at < cap) list[at] = make_uint2(comp, rec_off[comp]);
 }
 
+// records of the listed (suspect) components, side by side (records of one size R)
+__global__ void suspect_records_kernel(const int64_t* __restrict__ flat, const uint2* __restrict__ list, uint32_t n_sus, uint32_t R,
+                                       int64_t* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_sus * R) return;
+	out[i] = flat[(size_t)list[i / R].y + i % R];
+}
+// the record list without the dropped components (ascending list of component numbers; records of one size R)
+__global__ void drop_records_kernel(const int64_t* __restrict__ flat, uint32_t n_comp, uint32_t R, const uint32_t* __restrict__ drops,
+                                    uint32_t n_drop, int64_t* __restrict__ out) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (uint64_t)n_comp * R) return;
+	const uint32_t comp = (uint32_t)(i / R);
+	uint32_t lo = 0, hi = n_drop;  // dropped components before (or at) comp
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) / 2;
+		if (drops[mid] <= comp) lo = mid + 1;
+		else hi = mid;
+	}
+	if (lo && drops[lo - 1] == comp) return;
+	out[i - (uint64_t)lo * R] = flat[i];
+}
+
 // hit members in merged order, for the host-side table emulation (ORDER_REFERENCE)
 template <class KeyT>
 __global__ void gather_members_kernel(MatchArgs a, const uint32_t* __restrict__ hit_start, const uint16_t* __restrict__ hit_len,
@@ -2106,22 +2129,89 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 		                                                      comp_left.p, comp_right.p, rec_off.p, n_comp, d_flat.p);
 		MEMS_CUDA(cudaGetLastError());
 	}
+	// Components are distinct by construction unless two diagonals shared a hash bucket: a foreign entry between two hits
+	// of one diagonal hides them from each other and both may report the same component.  Every component that can be
+	// involved was marked on the device (comp_suspect).  For records of one size the few marked records are compared on
+	// the host BEFORE the list leaves the device and the duplicates are left out there: taking them out of a list of
+	// hundreds of MB on the host (config 5: 633 MB per rank) cost more than the whole device part of the call.
+	const int64_t* d_result = d_flat.p;
+	uint32_t n_result = n_flat;
+	size_t n_drop_device = 0;
+	bool deduped_on_device = false;
+	DevBuf<int64_t> d_flat_kept;
+	if (order != MEMS_ORDER_REFERENCE && collision_seen && fixed_records) {
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));  // h_sus_count
+		const uint32_t n_sus = h_sus_count, R = (uint32_t)a.n_seqs + 2u;
+		if (n_sus <= sus_cap) {
+			deduped_on_device = true;
+			if (n_sus > 1) {
+				DevBuf<int64_t> sus_rec(c, (size_t)n_sus * R);
+				{
+					KernelScope ks(c, "suspect_records");
+					suspect_records_kernel<<<(n_sus * R + 255) / 256, 256, 0, c->stream>>>(d_flat.p, sus_list.p, n_sus, R, sus_rec.p);
+					MEMS_CUDA(cudaGetLastError());
+				}
+				std::vector<uint2> h_list(n_sus);
+				std::vector<int64_t> h_rec((size_t)n_sus * R);
+				MEMS_CUDA(cudaMemcpyAsync(h_list.data(), sus_list.p, (size_t)n_sus * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+				MEMS_CUDA(cudaMemcpyAsync(h_rec.data(), sus_rec.p, h_rec.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+				MEMS_CUDA(cudaStreamSynchronize(c->stream));
+				std::vector<uint32_t> idx(n_sus);
+				for (uint32_t k = 0; k < n_sus; ++k) idx[k] = k;
+				auto rec_of = [&](uint32_t k) { return Rec{h_rec.data() + (size_t)k * R}; };
+				std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {  // by record, then by component: the first stays
+					return rec_less(rec_of(x), rec_of(y)) || (!rec_less(rec_of(y), rec_of(x)) && h_list[x].x < h_list[y].x);
+				});
+				std::vector<uint32_t> drops;
+				for (uint32_t k = 1; k < n_sus; ++k)
+					if (rec_equal(rec_of(idx[k]), rec_of(idx[k - 1]))) drops.push_back(h_list[idx[k]].x);
+				if (!drops.empty()) {
+					std::sort(drops.begin(), drops.end());
+					n_drop_device = drops.size();
+					DevBuf<uint32_t> d_drops(c, drops.size());
+					MEMS_CUDA(cudaMemcpyAsync(d_drops.p, drops.data(), drops.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+					n_result = n_flat - (uint32_t)drops.size() * R;
+					d_flat_kept = DevBuf<int64_t>(c, n_result);
+					KernelScope ks(c, "drop_records");
+					drop_records_kernel<<<(unsigned)(((uint64_t)n_comp * R + 255) / 256), 256, 0, c->stream>>>(d_flat.p, n_comp, R, d_drops.p,
+					                                                                                         (uint32_t)drops.size(), d_flat_kept.p);
+					MEMS_CUDA(cudaGetLastError());
+					MEMS_CUDA(cudaStreamSynchronize(c->stream));  // `drops` leaves scope
+					d_result = d_flat_kept.p;
+				}
+			}
+		}
+	}
 	// D2H straight into a page-locked buffer that the result object keeps (no pageable staging, no copy)
 	out.flat.owner = ctx;
-	out.flat.pinned = (int64_t*)c->pinned_get((size_t)n_flat * sizeof(int64_t), &out.flat.pinned_cap);
-	out.flat.pinned_n = n_flat;
+	out.flat.pinned = (int64_t*)c->pinned_get((size_t)n_result * sizeof(int64_t), &out.flat.pinned_cap);
+	out.flat.pinned_n = n_result;
 	const int64_t* raw = out.flat.pinned;
 	{
-		CopyScope cs(c, "copy_out_matches", (double)n_flat * sizeof(int64_t));
-		MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_flat.p, (size_t)n_flat * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+		CopyScope cs(c, "copy_out_matches", (double)n_result * sizeof(int64_t));
+		MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_result, (size_t)n_result * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
 	}
 
 	if (order != MEMS_ORDER_REFERENCE) {
 		MEMS_CUDA(cudaStreamSynchronize(c->stream));
-		// Components are distinct by construction unless two diagonals shared a hash bucket: a foreign entry
-		// between two hits of one diagonal hides them from each other and both may report the same component.
-		// Every component that can be involved was marked on the device (comp_suspect), so only those few
-		// records are compared; a sorted list (ORDER_CANONICAL) is produced on the host when asked for.
+		if (deduped_on_device) {
+			if (order == MEMS_ORDER_CANONICAL) {
+				std::vector<Rec> recs = split_records(raw, n_result);
+				std::sort(recs.begin(), recs.end(), rec_less);
+				recs.erase(std::unique(recs.begin(), recs.end(), rec_equal), recs.end());
+				out.flat.vec.reserve(n_result);
+				for (const Rec& r2 : recs) out.flat.vec.insert(out.flat.vec.end(), r2.p, r2.p + r2.size());
+				out.flat.release();
+				out.n_matches = recs.size();
+			} else {
+				out.n_matches = n_comp - n_drop_device;
+			}
+			out.mem_count = out.n_matches;
+			out.collisions = out.n_hits - out.n_matches;
+			return;
+		}
+		// (records of several sizes — many problems per call — and overfull suspect lists: the duplicates are taken out
+		// on the host)
 		std::vector<char> drop;
 		size_t n_drop = 0;
 		if (collision_seen) {
