@@ -314,13 +314,20 @@ def main():
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        info, flat, walls = None, None, []
+        info, pend, walls = None, None, []
         for _ in range(steps):
             t0 = time.perf_counter()
-            flat = None  # the previous step's MatchList goes back to the library's page-locked pool before the next call
-            flat, info = step(bufs)
+            # The records of a step leave the device behind its last kernel (mems_b200.h, mems_matches_wait): the previous
+            # step's MatchList is given back only after this step's call has been issued, so its D2H copy overlaps this
+            # step's kernels.  Every copy lies inside the timed region: the last one is waited for before the end mark.
+            prev = pend
+            pend, info = step(bufs)
+            prev = None  # noqa: F841 - waits for its records, then returns its page-locked buffer to the library's pool
             walls.append(1e3 * (time.perf_counter() - t0))
+        pend.wait()
         b.record(stream)
+        flat = pend.records()
+        pend = None
         print("[bench r%d] host ms per step: %s" % (rank, " ".join("%.2f" % w for w in walls)), file=sys.stderr)
         barrier()
         ms = a.elapsed_time(b)
@@ -336,10 +343,10 @@ def main():
         def step(bufs):
             smls = ctx.create_smls([(b.data_ptr(), b.numel()) for b in bufs], sd)
             sampler.tick()  # the GPU is sorting; no CUDA call of this process is in flight
-            flat, info = ctx.find_matches(smls, mode=m)
+            pend, info = ctx.find_matches(smls, mode=m, wait=False)
             for s in smls:
                 s.close()
-            return flat, info
+            return pend, info
         return step
 
     parity = None
@@ -363,13 +370,14 @@ def main():
 
         def step(bufs):
             seqs = [(b.data_ptr(), b.numel()) if b is not None else None for b in bufs]
-            res = ctx.find_matches_sharded(comm, seqs, lens, seed, mode=match_mode)
+            res = ctx.find_matches_sharded(comm, seqs, lens, seed, mode=match_mode, wait=False)
             sampler.tick()  # (one collective call per step: the sample falls between two steps)
             return res
 
         # ---- parity of the sharded MatchList, before anything is timed: the union of the ranks' shares against a
         # single-GPU run of the same input on rank 0 (both as canonically sorted record lists)
-        flat, info = step(dev)
+        pend, info = step(dev)
+        flat = pend.records()
         shares = [None] * world
         dist.all_gather_object(shares, np.asarray(flat).copy())
         if rank == 0:
@@ -386,7 +394,7 @@ def main():
                       "single_gpu_digest": dig_1, "equal": bool(dig_sh == dig_1 and n_sh == n_sh_distinct == n_1),
                       "how": "sha256 of the canonically sorted union of all ranks' records vs mems_find_matches on rank 0 over the same genomes"}
             print("[bench] sharded parity:", parity, file=sys.stderr)
-        del shares, flat
+        del shares, flat, pend
         dist.barrier()
         del gs
 
@@ -491,7 +499,10 @@ def main():
                     # MatchList, and of all kernels; the rest of ms_per_step is launch gaps and host round trips
                     "h2d_ms": prof_e2e.get("copy_in_sequences", {}).get("ms", 0.0) / n_split,
                     "d2h_ms": prof_e2e.get("copy_out_matches", {}).get("ms", 0.0) / n_split,
-                    "kernel_ms": e2e_kernel_ms, "bracketed_ms_per_step": ms_e2e_prof / n_split},
+                    "kernel_ms": e2e_kernel_ms, "bracketed_ms_per_step": ms_e2e_prof / n_split,
+                    "delivery": "every step's MatchList is copied to page-locked host memory inside the timed region; the copy "
+                                "of step i runs on the library's copy stream while step i+1's kernels run (the records are waited "
+                                "for when the caller asks for them, mems_matches_wait); the bracketed pass copies in line"},
             "gpu_launches": launches, "matches_per_step": n_matches_total, "hits_per_step": n_hits_total,
             "matches_per_s": n_matches_total * args.steps / (ms_dev / 1e3),
             "roofline": roofline, "kernels": kernels, "clocks": clocks,
@@ -585,7 +596,7 @@ def run_extras(mems, synth, ctx, comm, rank, world, timed, single_step):
 
         def step(bufs):
             seqs = [(b.data_ptr(), b.numel()) if b is not None else None for b in bufs]
-            return ctx.find_matches_sharded(comm, seqs, lens, sd)
+            return ctx.find_matches_sharded(comm, seqs, lens, sd, wait=False)
 
         timed(step, bufs, warm)
         ms, flat, info = timed(step, bufs, steps)

@@ -167,6 +167,12 @@ int mems_matches_info(mems_matches_t m, mems_matches_info_t* out);
 int mems_matches_copy(mems_matches_t m, int64_t* flat_out);
 /* The same records in place (n_flat int64 values), valid until mems_matches_destroy: no copy. */
 const int64_t* mems_matches_data(mems_matches_t m);
+/* Records in MEMS_ORDER_ANY are delivered asynchronously: mems_find_matches[_sharded] returns when its last kernel is
+ * queued and the device-to-host copy of the records runs behind it.  mems_matches_data / mems_matches_copy /
+ * mems_matches_destroy wait for the copy themselves; mems_matches_wait only waits.  A caller that issues its next call
+ * before touching the records of the previous one gets the copy overlapped with that call's kernels; the counts of
+ * mems_matches_info are valid at once. */
+int mems_matches_wait(mems_matches_t m);
 void mems_matches_destroy(mems_matches_t m);
 
 /* ---- sharded match finding: one process per GPU, NCCL over NVLink ----

@@ -53,7 +53,7 @@ EXPORTS = [
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_clone", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_find_matches_many", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_destroy",
+    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_find_matches_many", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_wait", "mems_matches_destroy",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_shard_exchange_plan", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
     "mems_test_hooks",
@@ -108,6 +108,7 @@ def load():
     lib.mems_matches_info.argtypes = [_vp, ctypes.POINTER(MatchesInfo)]
     lib.mems_matches_copy.argtypes = [_vp, _vp]
     lib.mems_matches_data.argtypes = [_vp]
+    lib.mems_matches_wait.argtypes = [_vp]
     lib.mems_matches_data.restype = ctypes.POINTER(ctypes.c_int64)
     lib.mems_matches_destroy.argtypes = [_vp]
     lib.mems_comm_unique_id.argtypes = [_vp]
@@ -212,6 +213,26 @@ class _MatchHandle:
             pass
 
 
+class PendingMatches:
+    """The records of a call made with wait=False: they are still on their way from the device (mems_b200.h,
+    mems_matches_wait).  records() waits for them and returns the zero-copy view."""
+
+    def __init__(self, lib, keep, n_flat):
+        self.lib, self._keep, self.n_flat = lib, keep, n_flat
+
+    def records(self):
+        if self.n_flat == 0:
+            return np.zeros(0, np.int64)
+        view = np.ctypeslib.as_array(self.lib.mems_matches_data(self._keep.h), shape=(self.n_flat,))  # waits
+        flat = view.view(_OwnedArray)
+        flat._keep = self._keep
+        return flat
+
+    def wait(self):
+        self.lib.mems_matches_wait(self._keep.h)
+        return self
+
+
 class _OwnedArray(np.ndarray):
     """ndarray view that keeps the owning match handle alive."""
     _keep = None
@@ -269,9 +290,11 @@ class Context:
         return [SortedMerList(self, _vp(out[i])) for i in range(n)]
 
     # -- match finding --------------------------------------------------------------------------------
-    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0, table=None, start_points=None):
+    def find_matches(self, smls, mode=MODE_MEMHASH, order=ORDER_ANY, table_size=0, seq_mask=0, table=None, start_points=None,
+                     wait=True):
         """MemHash / RepeatHash / PairwiseMatchFinder ::FindMatches (start_points: FindMatchesFromPosition).  Returns
-        (flat, info): flat = int64 records [SeqCount, Length, Start(0), ...] (see flat_to_matches)."""
+        (flat, info): flat = int64 records [SeqCount, Length, Start(0), ...] (see flat_to_matches); with wait=False a
+        PendingMatches in place of flat (the records may still be on their way from the device)."""
         n = len(smls)
         arr = (_vp * n)(*[s.h for s in smls])
         sp = (_u64 * n)(*[int(x) for x in start_points]) if start_points is not None else None
@@ -283,6 +306,8 @@ class Context:
         info = MatchesInfo()
         self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
         d = {k: (float if k == "host_replay_ms" else int)(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        if not wait:
+            return PendingMatches(self.lib, keep, int(info.n_flat)), d
         if info.n_flat == 0:
             return np.zeros(0, np.int64), d
         # zero-copy view of the library's (page-locked) result buffer; it lives as long as the array does
@@ -322,9 +347,9 @@ class Context:
         self._check(self.lib.mems_comm_create(self.h, ctypes.addressof(buf), rank, world, ctypes.byref(h)))
         return Communicator(self, h, rank, world)
 
-    def find_matches_sharded(self, comm, seqs, lens, seed, mode=MODE_MEMHASH, order=ORDER_ANY):
+    def find_matches_sharded(self, comm, seqs, lens, seed, mode=MODE_MEMHASH, order=ORDER_ANY, wait=True):
         """Collective.  seqs: list over ALL sequences; entries outside this rank's block may be None.
-        Returns this rank's share of the matches (flat, info)."""
+        Returns this rank's share of the matches (flat, info); wait=False as in find_matches."""
         n = len(lens)
         parts = [(_host_ptr(s) if s is not None else (0, 0, None)) for s in seqs]
         ptrs = (_vp * n)(*[p[0] for p in parts])
@@ -337,6 +362,8 @@ class Context:
         info = MatchesInfo()
         self._check(self.lib.mems_matches_info(h, ctypes.byref(info)))
         d = {k: (float if k == "host_replay_ms" else int)(getattr(info, k)) for k, _ in MatchesInfo._fields_}
+        if not wait:
+            return PendingMatches(self.lib, keep, int(info.n_flat)), d
         if info.n_flat == 0:
             return np.zeros(0, np.int64), d
         view = np.ctypeslib.as_array(self.lib.mems_matches_data(h), shape=(int(info.n_flat),))

@@ -371,6 +371,12 @@ int mems_matches_copy(mems_matches_t m, int64_t* flat_out) {
 
 const int64_t* mems_matches_data(mems_matches_t m) { return m ? m->r.flat.data() : nullptr; }
 
+int mems_matches_wait(mems_matches_t m) {
+	if (!m) return fail(nullptr, MEMS_ERR_INVALID, "null argument");
+	m->r.flat.wait();
+	return MEMS_OK;
+}
+
 void mems_matches_destroy(mems_matches_t m) { delete m; }
 
 // ------------------------------------------------------------------------------------------------ sharded

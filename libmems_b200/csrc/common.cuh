@@ -84,6 +84,7 @@ struct Ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
+	cudaStream_t copy_stream = nullptr;  // results leave on it behind the call's last kernel (FlatRecords::wait)
 	int sm_count = 148;
 	bool profiling = false;
 	uint64_t launch_count = 0;
@@ -368,14 +369,34 @@ void shard_exchange_plan(const uint32_t* hist_all, int world, int rank, const ui
 // ---- kernels_match.cu ----
 // [SeqCount, Length, starts...] records on the host: either a page-locked buffer borrowed from the context
 // (filled straight by the D2H copy) or, when the host re-ordered the records, a plain vector.
+//
+// Delivery is asynchronous where the host has nothing left to do with the records (ORDER_ANY): the call returns once
+// its last kernel is queued, the D2H copy runs on the context's copy stream behind it, and `wait()` — called by every
+// accessor of the records — blocks until they have arrived.  A caller that issues its next call first gets the copy
+// overlapped with that call's kernels (the copy is 5-40 % of a step: 12 MB per config-2 step, 633 MB per rank and
+// config-5 step).
 struct FlatRecords {
 	std::shared_ptr<Ctx> owner;
 	int64_t* pinned = nullptr;
 	size_t pinned_cap = 0, pinned_n = 0;
 	std::vector<int64_t> vec;
-	const int64_t* data() const { return pinned ? pinned : vec.data(); }
+	cudaEvent_t ready = nullptr;  // recorded behind the copy into `pinned`
+	void* dev_keep = nullptr;     // the copy's device source, released once it has arrived
+	void wait() {
+		if (!ready) return;
+		cudaEventSynchronize(ready);
+		owner->event_put(ready);
+		ready = nullptr;
+		if (dev_keep) owner->free(dev_keep);
+		dev_keep = nullptr;
+	}
+	const int64_t* data() {
+		wait();
+		return pinned ? pinned : vec.data();
+	}
 	size_t size() const { return pinned ? pinned_n : vec.size(); }
 	void release() {
+		wait();
 		if (pinned) owner->pinned_put(pinned, pinned_cap);
 		pinned = nullptr;
 		pinned_n = 0;

@@ -216,6 +216,10 @@ void Ctx::prof_collect() {
 Ctx::~Ctx() {
 	cudaSetDevice(device);
 	if (stream) cudaStreamSynchronize(stream);
+	if (copy_stream) {
+		cudaStreamSynchronize(copy_stream);
+		cudaStreamDestroy(copy_stream);
+	}
 	for (auto& kv : prof)
 		for (auto& pr : kv.second.pending) {
 			cudaEventDestroy(pr.first);

@@ -2187,6 +2187,27 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	out.flat.pinned = (int64_t*)c->pinned_get((size_t)n_result * sizeof(int64_t), &out.flat.pinned_cap);
 	out.flat.pinned_n = n_result;
 	const int64_t* raw = out.flat.pinned;
+	// Nothing left for the host to do with the records (any order, no duplicate in doubt): they leave on the copy stream
+	// behind the emit kernel and the call returns without waiting for them (FlatRecords::wait).
+	const bool async_out = order == MEMS_ORDER_ANY && !many && !c->profiling && (!collision_seen || deduped_on_device);
+	if (async_out) {
+		if (!c->copy_stream) MEMS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		cudaEvent_t emitted = c->get_event();
+		MEMS_CUDA(cudaEventRecord(emitted, c->stream));
+		MEMS_CUDA(cudaStreamWaitEvent(c->copy_stream, emitted, 0));
+		c->event_put(emitted);  // (the wait is already queued; the event may be recorded again)
+		MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_result, (size_t)n_result * sizeof(int64_t), cudaMemcpyDeviceToHost, c->copy_stream));
+		out.flat.ready = c->get_event();
+		MEMS_CUDA(cudaEventRecord(out.flat.ready, c->copy_stream));
+		// the source outlives this function: the result object frees it when the copy has arrived
+		DevBuf<int64_t>& src = d_result == d_flat.p ? d_flat : d_flat_kept;
+		out.flat.dev_keep = src.p;
+		src.p = nullptr;
+		out.n_matches = n_comp - n_drop_device;
+		out.mem_count = out.n_matches;
+		out.collisions = out.n_hits - out.n_matches;
+		return;
+	}
 	{
 		CopyScope cs(c, "copy_out_matches", (double)n_result * sizeof(int64_t));
 		MEMS_CUDA(cudaMemcpyAsync(out.flat.pinned, d_result, (size_t)n_result * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
