@@ -164,7 +164,7 @@ std::shared_ptr<Batch> prepare_batch_from_ascii(std::shared_ptr<Ctx> ctx, int n_
 	// the flag travels to the host behind the pack; whoever queued the rest of the build calls check_gap()
 	b->h_gap = c->host_words_get();
 	b->gap_ready = c->get_event();
-	MEMS_CUDA(cudaMemcpyAsync(b->h_gap, gap_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	c->fetch_async(b->h_gap, gap_flag.p, 1);
 	MEMS_CUDA(cudaEventRecord(b->gap_ready, c->stream));
 	return b;
 }

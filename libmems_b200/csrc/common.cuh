@@ -115,10 +115,18 @@ struct Ctx {
 	std::vector<std::pair<void*, size_t>> pinned_free;
 	void* pinned_get(size_t bytes, size_t* capacity);
 	void pinned_put(void* p, size_t capacity);
-	// small page-locked words for counters the host waits on (asynchronous D2H needs page-locked memory)
+	// small page-locked, device-mapped words for counters the host waits on
 	std::vector<uint32_t*> host_words_free;
 	uint32_t* host_words_get();  // 16 uint32
 	void host_words_put(uint32_t* p);
+	// Counters and small tables the host needs in the middle of a call (data-dependent sizes) are WRITTEN BY A KERNEL
+	// into mapped page-locked memory instead of copied by the DMA engine: a cudaMemcpy of four bytes queues behind
+	// whatever the device-to-host engine is busy with — the previous call's MatchList on the copy stream — and made
+	// every round trip of the next call wait for that whole copy.
+	void fetch_async(uint32_t* host_words, const uint32_t* d_src, uint32_t n_words);  // into words of host_words_get()
+	void fetch(void* dst, const void* d_src, size_t bytes);  // synchronous: kernel into the staging area, wait, memcpy
+	uint32_t* fetch_stage = nullptr;
+	size_t fetch_stage_words = 0;
 	void event_put(cudaEvent_t e) { free_events.push_back(e); }
 	cudaEvent_t get_event();
 	void prof_begin(const char* name, double bytes);

@@ -162,8 +162,36 @@ uint32_t* Ctx::host_words_get() {
 		return p;
 	}
 	uint32_t* p = nullptr;
-	MEMS_CUDA(cudaHostAlloc((void**)&p, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+	MEMS_CUDA(cudaHostAlloc((void**)&p, 16 * sizeof(uint32_t), cudaHostAllocMapped));
 	return p;
+}
+
+__global__ void fetch_words_kernel(uint32_t* __restrict__ host_dst, const uint32_t* __restrict__ src, uint32_t n) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) host_dst[i] = src[i];
+}
+
+void Ctx::fetch_async(uint32_t* host_words, const uint32_t* d_src, uint32_t n_words) {
+	fetch_words_kernel<<<1, 32, 0, stream>>>(host_words, d_src, n_words);  // (unified addressing: the mapped pointer is the device's too)
+	MEMS_CUDA(cudaGetLastError());
+}
+
+void Ctx::fetch(void* dst, const void* d_src, size_t bytes) {
+	const size_t words = (bytes + 3) / 4;
+	if (words > fetch_stage_words) {
+		if (fetch_stage) {
+			MEMS_CUDA(cudaStreamSynchronize(stream));
+			cudaFreeHost(fetch_stage);
+			fetch_stage = nullptr;
+		}
+		const size_t cap = std::max<size_t>(words, 16384);
+		MEMS_CUDA(cudaHostAlloc((void**)&fetch_stage, cap * 4, cudaHostAllocMapped));
+		fetch_stage_words = cap;
+	}
+	// (sources are 4-byte aligned device arrays; a trailing partial word reads inside the arena's 512-byte granule)
+	fetch_words_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 64), 256, 0, stream>>>(fetch_stage, (const uint32_t*)d_src, (uint32_t)words);
+	MEMS_CUDA(cudaGetLastError());
+	MEMS_CUDA(cudaStreamSynchronize(stream));
+	memcpy(dst, fetch_stage, bytes);
 }
 
 void Ctx::host_words_put(uint32_t* p) {
@@ -228,6 +256,7 @@ Ctx::~Ctx() {
 	for (auto e : free_events) cudaEventDestroy(e);
 	for (auto& pb : pinned_free) cudaFreeHost(pb.first);
 	for (uint32_t* p : host_words_free) cudaFreeHost(p);
+	if (fetch_stage) cudaFreeHost(fetch_stage);
 	for (auto& sl : arena_slabs) cudaFree(sl.first);
 	if (scan_state) cudaFree(scan_state);
 	if (own_stream && stream) cudaStreamDestroy(stream);

@@ -1656,8 +1656,7 @@ namespace {
 
 uint32_t d2h_u32(Ctx* c, const uint32_t* d) {
 	uint32_t v = 0;
-	MEMS_CUDA(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	c->fetch(&v, d, sizeof v);
 	return v;
 }
 
@@ -1781,8 +1780,7 @@ static void find_hits(Ctx* c, const MatchArgs& a, HitSet& hits) {
 	}
 	exclusive_scan_u32(c, tile_hits.p, tile_off.p, n_tiles, scalars.p + 1);
 	uint32_t h_scal[2];  // [0] longest run, [1] hits
-	MEMS_CUDA(cudaMemcpyAsync(h_scal, scalars.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	c->fetch(h_scal, scalars.p, sizeof h_scal);
 	hits.max_run = h_scal[0];
 	hits.n = h_scal[1];
 	if (hits.n == 0) return;
@@ -1885,8 +1883,7 @@ static void find_pair_hits(Ctx* c, const MatchArgs& a, HitSet& hits, DevBuf<uint
 	}
 	exclusive_scan_u32(c, cnt.p, off.p, n, scalars.p + 1);
 	uint32_t h_scal[2];
-	MEMS_CUDA(cudaMemcpyAsync(h_scal, scalars.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	c->fetch(h_scal, scalars.p, sizeof h_scal);
 	hits.max_run = h_scal[0];
 	hits.n = h_scal[1];
 	if (hits.n == 0) return;
@@ -2066,8 +2063,7 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 #endif
 	exclusive_scan_u32(c, first.p, first_excl.p, n_seg, scalars.p + 3);
 	uint32_t h_tail[2];  // [n_comp, diagonal-hash collision seen]
-	MEMS_CUDA(cudaMemcpyAsync(h_tail, scalars.p + 3, sizeof h_tail, cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	c->fetch(h_tail, scalars.p + 3, sizeof h_tail);
 	const uint32_t n_comp = h_tail[0];
 	const bool collision_seen = h_tail[1] != 0;
 	DevBuf<uint32_t> comp_rep(c, n_comp), comp_left(c, n_comp), comp_right(c, n_comp), rec_size(c, n_comp), rec_off(c, n_comp);
@@ -2109,13 +2105,24 @@ static void extend_hits(std::shared_ptr<Ctx> ctx, const MatchArgs& a, const Seed
 	const uint32_t sus_cap = 1u << 16;
 	DevBuf<uint2> sus_list(c, collision_seen ? sus_cap : 1);
 	DevBuf<uint32_t> sus_count(c, 1);
-	uint32_t h_sus_count = 0;
+	struct HostWord {  // a mapped page-locked word the device writes (Ctx::fetch_async), given back when the call is over
+		Ctx* c;
+		uint32_t* w;
+		bool queued = false;
+		explicit HostWord(Ctx* ctx) : c(ctx), w(ctx->host_words_get()) { w[0] = 0; }
+		~HostWord() {
+			if (queued) cudaStreamSynchronize(c->stream);  // the write into it must have landed before the word is reused
+			c->host_words_put(w);
+		}
+	} sus_word(c);
+	volatile uint32_t& h_sus_count = sus_word.w[0];
 	if (collision_seen) {
 		MEMS_CUDA(cudaMemsetAsync(sus_count.p, 0, sizeof(uint32_t), c->stream));
 		KernelScope ks(c, "suspect_list");
 		suspect_list_kernel<<<comp_blocks, 256, 0, c->stream>>>(comp_suspect.p, rec_off.p, n_comp, sus_list.p, sus_cap, sus_count.p);
 		MEMS_CUDA(cudaGetLastError());
-		MEMS_CUDA(cudaMemcpyAsync(&h_sus_count, sus_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+		c->fetch_async(sus_word.w, sus_count.p, 1);
+		sus_word.queued = true;
 	}
 	if (mode != MEMS_MODE_REPEAT && (uint64_t)n_comp * (uint64_t)(a.max_group + 2) > 0xffffffffull)
 		throw Error(MEMS_ERR_UNSUPPORTED, "match list larger than 2^32 values; search fewer sequences per call");
@@ -3030,8 +3037,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	DevBuf<uint32_t> hist_all(c, (size_t)258 * W);
 	comm_all_gather_u64(comm, reinterpret_cast<const uint64_t*>(hist_top.p), reinterpret_cast<uint64_t*>(hist_all.p), 129);
 	std::vector<uint32_t> h_raw((size_t)258 * W), h_all((size_t)256 * W);
-	MEMS_CUDA(cudaMemcpyAsync(h_raw.data(), hist_all.p, h_raw.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	c->fetch(h_raw.data(), hist_all.p, h_raw.size() * sizeof(uint32_t));
 	for (int p = 0; p < W; ++p) {
 		const int code = (int)h_raw[(size_t)258 * p + 256];
 		if (code != MEMS_OK) {
@@ -3241,8 +3247,7 @@ static void find_matches_sharded_typed(std::shared_ptr<Ctx> ctx, Comm* comm, con
 	}
 	comm_all_gather_u64(comm, d_counts.p, d_counts.p + 2 * W, (size_t)2 * W);
 	std::vector<uint64_t> h_counts((size_t)2 * W * W);
-	MEMS_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p + 2 * W, h_counts.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-	MEMS_CUDA(cudaStreamSynchronize(c->stream));
+	c->fetch(h_counts.data(), d_counts.p + 2 * W, h_counts.size() * sizeof(uint64_t));
 	std::vector<uint64_t> hs(W), hr(W), ms(W), mr(W);
 	std::vector<uint64_t> hit_counts((size_t)W * W), mem_counts((size_t)W * W);
 	for (int p = 0; p < W; ++p)
