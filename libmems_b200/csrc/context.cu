@@ -171,6 +171,7 @@ __global__ void fetch_words_kernel(uint32_t* __restrict__ host_dst, const uint32
 }
 
 void Ctx::fetch_async(uint32_t* host_words, const uint32_t* d_src, uint32_t n_words) {
+	launch_count++;
 	fetch_words_kernel<<<1, 32, 0, stream>>>(host_words, d_src, n_words);  // (unified addressing: the mapped pointer is the device's too)
 	MEMS_CUDA(cudaGetLastError());
 }
@@ -188,6 +189,7 @@ void Ctx::fetch(void* dst, const void* d_src, size_t bytes) {
 		fetch_stage_words = cap;
 	}
 	// (sources are 4-byte aligned device arrays; a trailing partial word reads inside the arena's 512-byte granule)
+	launch_count++;
 	fetch_words_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 64), 256, 0, stream>>>(fetch_stage, (const uint32_t*)d_src, (uint32_t)words);
 	MEMS_CUDA(cudaGetLastError());
 	MEMS_CUDA(cudaStreamSynchronize(stream));
