@@ -401,3 +401,34 @@ def test_many_small_problems_in_one_call(ctx, orc):
         ctx.find_matches_many([[b"ACGT" * 20] * 65], mems.get_seed(7))
     with pytest.raises(mems.MemsError):
         ctx.find_matches_many([[b"ACGT" * 20] * 2] * 129, mems.get_seed(7))
+
+
+def test_asynchronous_delivery(ctx, orc):
+    """MEMS_ORDER_ANY records leave the device behind the call's last kernel (mems_b200.h, mems_matches_wait): calls
+    issued back to back before any of their MatchLists is read — the device buffers of one call are reused by the next
+    while its copy may still be in flight — must each deliver exactly the oracle's set, in any order of reading."""
+    seed = mems.get_seed(13)
+    jobs = [synth.genome_family(3 + (t % 3), 30000 + 7000 * t, seed=300 + t, n_indels=4, max_indel=20) for t in range(6)]
+    want = [canonical(orc.find_matches(0, gs, seed)[0]) for gs in jobs]
+    pending = []
+    for rnd in range(2):
+        for gs in jobs:
+            smls = ctx.create_smls(gs, seed)
+            pend, info = ctx.find_matches(smls, wait=False)
+            for s in smls:
+                s.close()
+            pending.append((pend, info))
+    # read them newest first, half of them after an explicit wait
+    for k in reversed(range(len(pending))):
+        pend, info = pending[k]
+        if k % 2:
+            pend.wait()
+        got = mems.flat_to_matches(pend.records())
+        assert len(got) == info["n_matches"]
+        assert canonical(got) == want[k % len(jobs)]
+    # a MatchList that is never read is simply given back
+    smls = ctx.create_smls(jobs[0], seed)
+    pend, info = ctx.find_matches(smls, wait=False)
+    del pend
+    flat, _ = ctx.find_matches(smls)
+    assert canonical(mems.flat_to_matches(flat)) == want[0]
