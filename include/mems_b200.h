@@ -231,6 +231,9 @@ uint64_t mems_launch_count(mems_ctx_t ctx);
  * gets before it moves on to the CTA-wide and grid-wide walkers.  0 restores production behaviour.  Results are the
  * same either way. */
 int mems_test_hooks(mems_ctx_t ctx, int hash_bits, int walk_budget);
+/* Randomised self-check of the bookkeeping of the context's device-memory arena on made-up addresses (host code only,
+ * runs without a GPU): 0 = passed, anything else names the violated invariant (csrc/context.cu). */
+int mems_selftest_arena(uint64_t seed, int rounds);
 
 #ifdef __cplusplus
 }

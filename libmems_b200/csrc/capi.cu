@@ -443,6 +443,8 @@ int mems_find_matches_sharded(mems_ctx_t ctx, mems_comm_t comm, int n_seqs, cons
 	});
 }
 
+int mems_selftest_arena(uint64_t seed, int rounds) { return arena_selftest(seed, rounds); }
+
 // ------------------------------------------------------------------------------------------------ measurement
 int mems_profile_enable(mems_ctx_t ctx, int on) {
 	if (!ctx) return fail(nullptr, MEMS_ERR_INVALID, "null context");

@@ -73,6 +73,31 @@ struct Error : std::runtime_error {
 			                         __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
 	} while (0)
 
+// Bookkeeping of the context's device-memory arena (context.cu): blocks inside slabs, best fit, free neighbours of one
+// slab merged.  Plain host code — it never touches the memory it hands out — so tests/test_abi_cpu.py can drive it without
+// a GPU (mems_selftest_arena).
+struct Arena {
+	static constexpr size_t kAlign = 512;
+	std::vector<std::pair<char*, size_t>> slabs;
+	std::map<char*, size_t> free_by_addr;
+	std::multimap<size_t, char*> free_by_size;
+	std::unordered_map<char*, size_t> used;
+	size_t reserved = 0;
+
+	static size_t round_up(size_t bytes) { return ((bytes ? bytes : 1) + kAlign - 1) & ~(kAlign - 1); }
+	void add_slab(char* base, size_t bytes);
+	void* take(size_t bytes);  // bytes already rounded; nullptr: no free block is large enough
+	bool give(void* p);        // false: not a block of this arena
+	// slabs that are completely free leave the arena; the caller releases their memory
+	std::vector<std::pair<char*, size_t>> drop_idle_slabs();
+
+private:
+	void insert_free(char* p, size_t bytes);
+	void erase_free(std::map<char*, size_t>::iterator it);
+};
+
+int arena_selftest(uint64_t seed, int rounds);  // context.cu
+
 struct ProfEntry {
 	uint64_t launches = 0;
 	double ms = 0, bytes = 0;
@@ -99,14 +124,7 @@ struct Ctx {
 	void* alloc(size_t bytes);  // stream-ordered on `stream`: arena of cudaMalloc'ed slabs, no driver call once warm
 	void free(void* p);
 	std::mutex arena_mutex;
-	std::vector<std::pair<char*, size_t>> arena_slabs;
-	std::map<char*, size_t> arena_free;             // free blocks by address (merged with their neighbours on free)
-	std::multimap<size_t, char*> arena_by_size;     // the same blocks by size (best fit)
-	std::unordered_map<char*, size_t> arena_used;
-	size_t arena_reserved = 0;
-	void arena_insert_free(char* p, size_t bytes);
-	void arena_erase_free(std::map<char*, size_t>::iterator it);
-	void arena_release_idle_slabs();
+	Arena arena;
 	// tile states of the chained scans (exclusive_scan_u32): [0] ticket counter, [1..] one word per tile, stamped by epoch
 	uint64_t* scan_state = nullptr;
 	size_t scan_cap = 0;

@@ -37,95 +37,185 @@ struct SlowCall {
 // by work enqueued later on the same stream) and a repeated workload makes no driver call at all in the steady state.
 // cudaMallocAsync's pool went back to the driver for the large blocks of every step on the pool's boxes — milliseconds each,
 // and hundreds of milliseconds whenever another tenant of the node held the kernel driver's lock.
-static constexpr size_t kArenaAlign = 512, kSlabMin = 32u << 20, kSlabRound = 2u << 20;
+static constexpr size_t kSlabMin = 32u << 20, kSlabRound = 2u << 20;
 
-void Ctx::arena_insert_free(char* p, size_t bytes) {
-	arena_free[p] = bytes;
-	arena_by_size.insert({bytes, p});
+void Arena::insert_free(char* p, size_t bytes) {
+	free_by_addr[p] = bytes;
+	free_by_size.insert({bytes, p});
 }
 
-void Ctx::arena_erase_free(std::map<char*, size_t>::iterator it) {
-	auto range = arena_by_size.equal_range(it->second);
+void Arena::erase_free(std::map<char*, size_t>::iterator it) {
+	auto range = free_by_size.equal_range(it->second);
 	for (auto j = range.first; j != range.second; ++j)
 		if (j->second == it->first) {
-			arena_by_size.erase(j);
+			free_by_size.erase(j);
 			break;
 		}
-	arena_free.erase(it);
+	free_by_addr.erase(it);
 }
 
-void Ctx::arena_release_idle_slabs() {
-	for (size_t i = 0; i < arena_slabs.size();) {
-		auto it = arena_free.find(arena_slabs[i].first);
-		if (it != arena_free.end() && it->second == arena_slabs[i].second) {
-			arena_erase_free(it);
-			cudaFree(arena_slabs[i].first);
-			arena_reserved -= arena_slabs[i].second;
-			arena_slabs.erase(arena_slabs.begin() + i);
+void Arena::add_slab(char* base, size_t bytes) {
+	slabs.push_back({base, bytes});
+	reserved += bytes;
+	insert_free(base, bytes);
+}
+
+void* Arena::take(size_t bytes) {
+	auto fit = free_by_size.lower_bound(bytes);  // best fit
+	if (fit == free_by_size.end()) return nullptr;
+	char* p = fit->second;
+	const size_t have = fit->first;
+	free_by_size.erase(fit);
+	free_by_addr.erase(p);
+	if (have > bytes) insert_free(p + bytes, have - bytes);
+	used[p] = bytes;
+	return p;
+}
+
+bool Arena::give(void* ptr) {
+	auto u = used.find((char*)ptr);
+	if (u == used.end()) return false;
+	char* p = u->first;
+	size_t bytes = u->second;
+	used.erase(u);
+	// merge with free neighbours of the same slab
+	size_t si = 0;
+	while (si < slabs.size() && !(p >= slabs[si].first && p < slabs[si].first + slabs[si].second)) ++si;
+	char* lo = slabs[si].first;
+	char* hi = lo + slabs[si].second;
+	auto next = free_by_addr.lower_bound(p);
+	if (next != free_by_addr.end() && next->first == p + bytes && next->first < hi) {
+		bytes += next->second;
+		erase_free(next);
+	}
+	auto prev = free_by_addr.lower_bound(p);
+	if (prev != free_by_addr.begin()) {
+		--prev;
+		if (prev->first >= lo && prev->first + prev->second == p) {
+			p = prev->first;
+			bytes += prev->second;
+			erase_free(prev);
+		}
+	}
+	insert_free(p, bytes);
+	return true;
+}
+
+std::vector<std::pair<char*, size_t>> Arena::drop_idle_slabs() {
+	std::vector<std::pair<char*, size_t>> idle;
+	for (size_t i = 0; i < slabs.size();) {
+		auto it = free_by_addr.find(slabs[i].first);
+		if (it != free_by_addr.end() && it->second == slabs[i].second) {
+			erase_free(it);
+			idle.push_back(slabs[i]);
+			reserved -= slabs[i].second;
+			slabs.erase(slabs.begin() + i);
 		} else {
 			++i;
 		}
 	}
+	return idle;
 }
 
 void* Ctx::alloc(size_t bytes) {
-	bytes = (std::max<size_t>(bytes, 1) + kArenaAlign - 1) & ~(kArenaAlign - 1);
+	bytes = Arena::round_up(bytes);
 	std::lock_guard<std::mutex> lock(arena_mutex);
-	auto fit = arena_by_size.lower_bound(bytes);
-	if (fit == arena_by_size.end()) {  // grow: one more slab (cudaMalloc synchronises the device; warm-up only)
+	void* p = arena.take(bytes);
+	if (!p) {  // grow: one more slab (cudaMalloc synchronises the device; warm-up only)
 		const size_t slab = std::max(kSlabMin, (bytes + kSlabRound - 1) & ~(kSlabRound - 1));
-		void* p = nullptr;
+		void* base = nullptr;
 		SlowCall sc("cudaMalloc", slab);
-		cudaError_t e = cudaMalloc(&p, slab);
+		cudaError_t e = cudaMalloc(&base, slab);
 		if (e == cudaErrorMemoryAllocation) {  // give idle slabs back (their last users may still run: wait for them) and retry
 			cudaGetLastError();
 			MEMS_CUDA(cudaStreamSynchronize(stream));
-			arena_release_idle_slabs();
-			e = cudaMalloc(&p, slab);
+			for (auto& sl : arena.drop_idle_slabs()) cudaFree(sl.first);
+			e = cudaMalloc(&base, slab);
 		}
 		MEMS_CUDA(e);
-		arena_slabs.push_back({(char*)p, slab});
-		arena_reserved += slab;
-		arena_insert_free((char*)p, slab);
-		fit = arena_by_size.lower_bound(bytes);
+		arena.add_slab((char*)base, slab);
+		p = arena.take(bytes);
 	}
-	char* p = fit->second;
-	const size_t have = fit->first;
-	arena_by_size.erase(fit);
-	arena_free.erase(p);
-	if (have > bytes) arena_insert_free(p + bytes, have - bytes);
-	arena_used[p] = bytes;
 	return p;
 }
 
 void Ctx::free(void* ptr) {
 	if (!ptr) return;
 	std::lock_guard<std::mutex> lock(arena_mutex);
-	auto u = arena_used.find((char*)ptr);
-	if (u == arena_used.end()) return;  // not ours
-	char* p = u->first;
-	size_t bytes = u->second;
-	arena_used.erase(u);
-	// merge with free neighbours of the same slab
-	size_t si = 0;
-	while (si < arena_slabs.size() && !(p >= arena_slabs[si].first && p < arena_slabs[si].first + arena_slabs[si].second)) ++si;
-	char* lo = arena_slabs[si].first;
-	char* hi = lo + arena_slabs[si].second;
-	auto next = arena_free.lower_bound(p);
-	if (next != arena_free.end() && next->first == p + bytes && next->first < hi) {
-		bytes += next->second;
-		arena_erase_free(next);
-	}
-	auto prev = arena_free.lower_bound(p);
-	if (prev != arena_free.begin()) {
-		--prev;
-		if (prev->first >= lo && prev->first + prev->second == p) {
-			p = prev->first;
-			bytes += prev->second;
-			arena_erase_free(prev);
+	arena.give(ptr);  // (not ours: ignored)
+}
+
+// Randomised self-check of the arena's bookkeeping on made-up addresses (no device needed): blocks never overlap,
+// never leave their slab, everything given back merges into whole slabs again.  0 = passed.
+int arena_selftest(uint64_t seed, int rounds) {
+	Arena a;
+	uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+	auto rnd = [&]() {
+		x ^= x << 13;
+		x ^= x >> 7;
+		x ^= x << 17;
+		return x;
+	};
+	char* const base = reinterpret_cast<char*>(uintptr_t(1) << 40);
+	size_t next_slab = 0;
+	std::map<char*, size_t> live;  // what the test holds
+	auto check = [&]() -> int {
+		// live blocks and free blocks tile every slab exactly
+		size_t total = 0;
+		for (auto& kv : live) total += kv.second;
+		for (auto& kv : a.free_by_addr) total += kv.second;
+		if (total != a.reserved) return 1;
+		if (a.free_by_addr.size() != a.free_by_size.size() || a.used.size() != live.size()) return 2;
+		std::map<char*, size_t> all(live);
+		for (auto& kv : a.free_by_addr)
+			if (!all.insert(kv).second) return 3;
+		char* end = nullptr;
+		for (auto& kv : all) {
+			if (end && kv.first < end) return 4;  // overlap
+			end = kv.first + kv.second;
 		}
+		// two free blocks never touch inside one slab
+		for (auto it = a.free_by_addr.begin(); it != a.free_by_addr.end(); ++it) {
+			auto nx = std::next(it);
+			if (nx == a.free_by_addr.end() || it->first + it->second != nx->first) continue;
+			bool boundary = false;
+			for (auto& sl : a.slabs) boundary |= sl.first == nx->first;
+			if (!boundary) return 5;
+		}
+		return 0;
+	};
+	for (int r = 0; r < rounds; ++r) {
+		const bool want_alloc = live.size() < 4 || (rnd() % 100) < 55;
+		if (want_alloc) {
+			const size_t bytes = Arena::round_up((size_t)(rnd() % (rnd() % 8 == 0 ? (64u << 20) : (1u << 20))));
+			void* p = a.take(bytes);
+			if (!p) {
+				const size_t slab = std::max<size_t>(32u << 20, (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1));
+				a.add_slab(base + next_slab, slab);
+				next_slab += slab;  // slabs adjacent in address space: merging must still stop at their borders
+				p = a.take(bytes);
+				if (!p) return 10;
+			}
+			if ((reinterpret_cast<uintptr_t>(p) & (Arena::kAlign - 1)) != 0) return 11;
+			if (!live.insert({(char*)p, bytes}).second) return 12;
+		} else {
+			auto it = live.begin();
+			std::advance(it, (long)(rnd() % live.size()));
+			if (!a.give(it->first)) return 13;
+			live.erase(it);
+		}
+		if ((r % 64) == 0)
+			if (int e = check()) return 100 + e;
 	}
-	arena_insert_free(p, bytes);
+	if (a.give(base - 4096)) return 14;  // a foreign pointer is refused
+	for (auto& kv : live)
+		if (!a.give(kv.first)) return 15;
+	live.clear();
+	if (int e = check()) return 200 + e;
+	const size_t n_slabs = a.slabs.size();
+	if (a.free_by_addr.size() != n_slabs) return 16;  // every slab is one free block again
+	if (a.drop_idle_slabs().size() != n_slabs || a.reserved != 0 || !a.free_by_addr.empty()) return 17;
+	return 0;
 }
 
 void* Ctx::pinned_get(size_t bytes, size_t* capacity) {
@@ -259,7 +349,7 @@ Ctx::~Ctx() {
 	for (auto& pb : pinned_free) cudaFreeHost(pb.first);
 	for (uint32_t* p : host_words_free) cudaFreeHost(p);
 	if (fetch_stage) cudaFreeHost(fetch_stage);
-	for (auto& sl : arena_slabs) cudaFree(sl.first);
+	for (auto& sl : arena.slabs) cudaFree(sl.first);
 	if (scan_state) cudaFree(scan_state);
 	if (own_stream && stream) cudaStreamDestroy(stream);
 }

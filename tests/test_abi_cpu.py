@@ -40,6 +40,17 @@ def test_seed_table_matches_reference_golden():
     assert mems.get_seed(13, 9) == (1 << 13) - 1  # rank > 5 -> solid
 
 
+def test_arena_bookkeeping_selftest():
+    """The device-memory arena of a context (csrc/context.cu) is plain host bookkeeping over cudaMalloc'ed slabs: its
+    randomised self-check (made-up addresses, no device) must hold for blocks never overlapping or leaving their slab,
+    free neighbours merging, whole slabs coming back once everything is returned."""
+    lib = mems.load()
+    lib.mems_selftest_arena.argtypes = [ctypes.c_uint64, ctypes.c_int]
+    lib.mems_selftest_arena.restype = ctypes.c_int
+    for seed in range(8):
+        assert lib.mems_selftest_arena(seed, 20000) == 0, seed
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
