@@ -60,6 +60,10 @@ void mems_ctx_destroy(mems_ctx_t ctx);
 const char* mems_last_error(mems_ctx_t ctx);
 /* block until all work queued on the context's stream is done */
 int mems_ctx_synchronize(mems_ctx_t ctx);
+/* A context keeps the device memory of earlier calls (an arena of cudaMalloc'ed slabs) so that repeated work makes no
+ * driver call.  mems_ctx_trim waits for the context's work and gives the slabs no live object (SML, MatchList in flight)
+ * occupies back to the driver; *reserved_bytes (may be NULL) = what the context still holds. */
+int mems_ctx_trim(mems_ctx_t ctx, uint64_t* reserved_bytes);
 /* pinned host memory helpers (optional; any host pointer is accepted by the calls below) */
 int mems_host_alloc(void** ptr, uint64_t bytes);
 void mems_host_free(void* ptr);

@@ -53,7 +53,7 @@ EXPORTS = [
     "mems_get_default_seed_weight", "mems_ctx_create", "mems_ctx_destroy", "mems_last_error",
     "mems_ctx_synchronize", "mems_host_alloc", "mems_host_free", "mems_sml_create", "mems_sml_create_batch",
     "mems_sml_destroy", "mems_sml_clone", "mems_sml_info", "mems_sml_read", "mems_sml_seed_mers", "mems_sml_find_mer",
-    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_find_matches_many", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_wait", "mems_matches_destroy", "mems_selftest_arena",
+    "mems_sml_packed", "mems_sml_seed_occurrence", "mems_find_matches", "mems_find_matches_many", "mems_table_create", "mems_table_clear", "mems_table_destroy", "mems_table_add", "mems_table_matches", "mems_matches_info", "mems_matches_copy", "mems_matches_data", "mems_matches_wait", "mems_matches_destroy", "mems_selftest_arena", "mems_ctx_trim",
     "mems_comm_unique_id", "mems_comm_create", "mems_comm_destroy", "mems_shard_sequence_range",
     "mems_shard_bucket_owners", "mems_shard_exchange_plan", "mems_find_matches_sharded", "mems_profile_enable", "mems_profile_reset", "mems_profile_get", "mems_launch_count",
     "mems_test_hooks",
@@ -270,6 +270,12 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.mems_ctx_synchronize(self.h))
+
+    def trim(self):
+        """Give the device memory no live object occupies back to the driver; returns the bytes still held."""
+        left = _u64()
+        self._check(self.lib.mems_ctx_trim(self.h, ctypes.byref(left)))
+        return int(left.value)
 
     # -- SML construction -----------------------------------------------------------------------------
     def create_sml(self, seq, seed):

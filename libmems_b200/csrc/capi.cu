@@ -90,6 +90,19 @@ int mems_ctx_synchronize(mems_ctx_t ctx) {
 	return guarded(ctx->c.get(), [&] { MEMS_CUDA(cudaStreamSynchronize(ctx->c->stream)); });
 }
 
+int mems_ctx_trim(mems_ctx_t ctx, uint64_t* reserved_bytes) {
+	if (!ctx) return fail(nullptr, MEMS_ERR_INVALID, "null context");
+	return guarded(ctx->c.get(), [&] {
+		Ctx* c = ctx->c.get();
+		MEMS_CUDA(cudaSetDevice(c->device));
+		MEMS_CUDA(cudaStreamSynchronize(c->stream));
+		if (c->copy_stream) MEMS_CUDA(cudaStreamSynchronize(c->copy_stream));
+		std::lock_guard<std::mutex> lock(c->arena_mutex);
+		for (auto& sl : c->arena.drop_idle_slabs()) cudaFree(sl.first);
+		if (reserved_bytes) *reserved_bytes = c->arena.reserved;
+	});
+}
+
 int mems_host_alloc(void** ptr, uint64_t bytes) {
 	return guarded(nullptr, [&] { MEMS_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault)); });
 }

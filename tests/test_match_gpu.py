@@ -432,3 +432,26 @@ def test_asynchronous_delivery(ctx, orc):
     del pend
     flat, _ = ctx.find_matches(smls)
     assert canonical(mems.flat_to_matches(flat)) == want[0]
+
+
+def test_context_trim_gives_idle_memory_back(orc):
+    """mems_ctx_trim: the arena's slabs without a live object go back to the driver; what is still alive (an SML) keeps
+    its slab and stays usable, and the context works as before afterwards."""
+    c = gpu_context()
+    seed = mems.get_seed(13)
+    gs = synth.genome_family(3, 40000, seed=77, n_indels=4, max_indel=20)
+    want = canonical(orc.find_matches(0, gs, seed)[0])
+    smls = c.create_smls(gs, seed)
+    flat, _ = c.find_matches(smls, order=mems.ORDER_CANONICAL)
+    assert mems.flat_to_matches(flat) == want
+    held = c.trim()
+    assert held > 0  # the SMLs are alive
+    flat, _ = c.find_matches(smls, order=mems.ORDER_CANONICAL)
+    assert mems.flat_to_matches(flat) == want
+    for s in smls:
+        s.close()
+    del flat
+    assert c.trim() == 0
+    flat, _ = c.find_matches(c.create_smls(gs, seed), order=mems.ORDER_CANONICAL)
+    assert mems.flat_to_matches(flat) == want
+    c.close()
